@@ -1,0 +1,85 @@
+"""Seeded synthetic DLO frames: the workload generator for tests and bench.py.
+
+Mirrors the data shapes the reference's front-end hands to trackdlo::tracking_step
+(trackdlo_node.cpp:242 float32-origin points; :254-277, :346-360 visibility lists).
+"""
+import numpy as np
+
+L_CURVE = 0.8
+SEED0 = 20231010
+
+
+def curve(t):
+    t = np.asarray(t, dtype=np.float64)
+    return np.stack([L_CURVE * (t - 0.5), 0.08 * np.sin(2 * np.pi * t), 0.65 + 0.03 * np.cos(3 * t)], axis=-1)
+
+
+def observed_curve(t, frame_idx):
+    t = np.asarray(t, dtype=np.float64)
+    ph = 0.1 * frame_idx
+    off = 0.01 * np.stack([np.sin(3 * t + ph), np.cos(2 * t + ph), np.zeros_like(t)], axis=-1)
+    return curve(t) + off
+
+
+def rest_arclengths(Y):
+    seg = np.linalg.norm(np.diff(Y, axis=0), axis=1)
+    return np.concatenate([[0.0], np.cumsum(seg)])
+
+
+def visibility(Y, X, rest, tau_vis=0.008, d_vis=0.06):
+    """visible_nodes / visible_nodes_extended as built by trackdlo_node.cpp:254-277,346-360
+    (self-occlusion raster excluded)."""
+    Nn = Y.shape[0]
+    dmin = np.full(Nn, np.inf)
+    for lo in range(0, X.shape[0], 65536):
+        d = np.linalg.norm(Y[:, None, :] - X[None, lo:lo + 65536, :], axis=2)
+        dmin = np.minimum(dmin, d.min(axis=1))
+    vis = [int(m) for m in range(Nn) if dmin[m] <= tau_vis]
+    ext = []
+    for i in range(len(vis) - 1):
+        ext.append(vis[i])
+        if abs(rest[vis[i + 1]] - rest[vis[i]]) <= d_vis:
+            ext.extend(range(vis[i] + 1, vis[i + 1]))
+    if vis:
+        ext.append(vis[-1])
+    return np.asarray(vis, np.int32), np.asarray(ext, np.int32)
+
+
+def make_frame(frame_idx, n_nodes=50, n_points=20000, occlusion=0.0, tau_vis=0.008, d_vis=0.06,
+               outlier_frac=0.01, noise=0.002):
+    """One independent frame: dict(X [Mp,3] f64, Y [Nn,3], rest [Nn], vis, vis_ext)."""
+    rng = np.random.default_rng(SEED0 + frame_idx)
+    Y = curve(np.linspace(0.0, 1.0, n_nodes))
+    t = rng.random(n_points)
+    X = observed_curve(t, frame_idx) + rng.normal(0.0, noise, size=(n_points, 3))
+    n_out = int(round(outlier_frac * n_points))
+    if n_out:
+        idx = rng.choice(n_points, size=n_out, replace=False)
+        X[idx] = np.array([0.0, 0.0, 0.65]) + rng.uniform(-0.3, 0.3, size=(n_out, 3))
+    if occlusion > 0:
+        keep = ~((t >= 0.3) & (t <= 0.3 + occlusion))
+        X = X[keep]
+    X = X.astype(np.float32).astype(np.float64)      # trackdlo_node.cpp:242
+    rest = rest_arclengths(Y)
+    vis, ext = visibility(Y, X, rest, tau_vis, d_vis)
+    return dict(X=np.ascontiguousarray(X), Y=Y, rest=rest, vis=vis, vis_ext=ext)
+
+
+def make_batch(n_frames, first_frame=0, **kw):
+    """Ragged batch in the C-ABI layout: X concatenated [sum Mp, 3], x_offsets [F+1], Y [F,Nn,3], ..."""
+    frames = [make_frame(first_frame + f, **kw) for f in range(n_frames)]
+    offs = np.zeros(n_frames + 1, np.int64)
+    offs[1:] = np.cumsum([f["X"].shape[0] for f in frames])
+    voff = np.zeros(n_frames + 1, np.int64)
+    voff[1:] = np.cumsum([len(f["vis"]) for f in frames])
+    eoff = np.zeros(n_frames + 1, np.int64)
+    eoff[1:] = np.cumsum([len(f["vis_ext"]) for f in frames])
+    return dict(
+        frames=frames,
+        X=np.ascontiguousarray(np.concatenate([f["X"] for f in frames], axis=0)),
+        x_offsets=offs,
+        Y=np.ascontiguousarray(np.stack([f["Y"] for f in frames])),
+        rest=np.ascontiguousarray(np.stack([f["rest"] for f in frames])),
+        vis=np.concatenate([f["vis"] for f in frames]).astype(np.int32), vis_offsets=voff,
+        vis_ext=np.concatenate([f["vis_ext"] for f in frames]).astype(np.int32), vis_ext_offsets=eoff,
+    )
