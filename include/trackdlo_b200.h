@@ -1,0 +1,153 @@
+/* trackdlo_b200 -- C ABI of the B200-native TrackDLO registration path.
+ *
+ * Drop-in boundary for the reference's per-frame CPD/MCT EM registration:
+ *   trackdlo::cpd_lle       (trackdlo/include/trackdlo.h:81-95,  trackdlo/src/trackdlo.cpp:161-441)
+ *   trackdlo::tracking_step (trackdlo/include/trackdlo.h:97-102, trackdlo/src/trackdlo.cpp:900-999)
+ * extended with a batch dimension over independent frames (BASELINE.json north_star).
+ * The Eigen-facing `class trackdlo` with the reference's exact signature lives in
+ * include/trackdlo_adapter.hpp and calls only the functions below.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns TDLO_OK (0) or a negative error code and
+ *     records a message retrievable with tdlo_last_error().
+ *   - all matrices are row-major doubles: points [n][3] (xyz interleaved), nodes [n][3],
+ *     priors [k][4] = {node_idx, x, y, z} exactly as trackdlo.cpp:247-250 reads them.
+ *   - ragged per-frame arrays use CSR-style offsets ([n_frames+1], int64).
+ *   - `*_device` entry points take DEVICE pointers and are stream-ordered (asynchronous);
+ *     the plain entry points take HOST pointers, copy in, run, copy out and synchronise.
+ *   - one context per host thread / GPU; contexts are not re-entrant (the reference class is
+ *     single-threaded too, trackdlo_node.cpp:643).
+ *   - there is no CPU fallback: every entry point fails with TDLO_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef TRACKDLO_B200_H
+#define TRACKDLO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDLO_OK 0
+#define TDLO_ERR_INVALID (-1)   /* bad argument / capacity exceeded */
+#define TDLO_ERR_CUDA (-2)      /* CUDA runtime error (see tdlo_last_error) */
+#define TDLO_ERR_NOMEM (-3)
+
+/* per-frame status word written to `status[f]` (bit mask) */
+#define TDLO_ST_NOT_CONVERGED 1  /* cpd_lle would return false (trackdlo.cpp:433-437)            */
+#define TDLO_ST_SINGULAR 2       /* zero / non-finite pivot in the A W = B solve                */
+#define TDLO_ST_TOO_FEW_NODES 4  /* fewer than 4 nodes: reference indexes out of range (:313-321) */
+#define TDLO_ST_EMPTY_CLOUD 8    /* no point within prune_radius of any node (reference divides by 0) */
+#define TDLO_ST_TRAVERSE_UB 16   /* traverse_euclidean / prior merge hit a path that is undefined
+                                    behaviour in the reference; result is defined
+                                    but has no reference counterpart                              */
+#define TDLO_ST_PRE_NOT_CONVERGED 32 /* tracking_step: the pre-processing registration hit max_iter */
+
+#define TDLO_MAX_NODES 256
+
+typedef struct tdlo_ctx tdlo_ctx;
+
+/* Arguments of trackdlo::cpd_lle (trackdlo.h:81-95) that are not per-frame data. */
+typedef struct tdlo_cpd_params {
+    double beta;                 /* MCT kernel width                                   */
+    double lambda;               /* MCT weight                                         */
+    double lle_weight;           /* gamma, used iff include_lle                        */
+    double mu;                   /* outlier ratio, 0 < mu < 1                          */
+    double tol;                  /* mean node displacement threshold (trackdlo.cpp:424) */
+    double alpha;                /* correspondence-prior weight                        */
+    double k_vis;                /* visibility strength (trackdlo.cpp:358-379)          */
+    double visibility_threshold; /* tau_vis (trackdlo.cpp:291)                          */
+    double prune_radius;         /* 0.1 in the reference (trackdlo.cpp:190)             */
+    int32_t max_iter;
+    int32_t include_lle;
+} tdlo_cpd_params;
+
+/* Constructor arguments of class trackdlo (trackdlo.h:59-71). */
+typedef struct tdlo_track_params {
+    double visibility_threshold, beta, lambda, alpha, k_vis, mu, tol;
+    double beta_pre_proc, lambda_pre_proc, lle_weight;
+    double prune_radius;         /* 0.1 */
+    int32_t max_iter;
+    int32_t reserved;
+} tdlo_track_params;
+
+/* A batch of independent cpd_lle problems.  Pointers are all-host or all-device depending on
+ * the entry point.  Optional arrays may be NULL. */
+typedef struct tdlo_cpd_batch {
+    int32_t n_frames;
+    int32_t node_stride;        /* row stride (in nodes) of Y / priors / W / H; >= every n_nodes[f] */
+    const double* X;            /* [x_offsets[n_frames]][3]  X_orig of every frame, concatenated   */
+    const int64_t* x_offsets;   /* [n_frames+1]                                                     */
+    const int32_t* n_nodes;     /* [n_frames] or NULL (= node_stride for all frames)                */
+    double* Y;                  /* [n_frames][node_stride][3]  in: Y, out: registered Y             */
+    double* sigma2;             /* [n_frames] in/out; 0 selects the data-driven init (:271-273)     */
+    const double* priors;       /* [n_frames][node_stride][4] or NULL                               */
+    const int32_t* n_priors;    /* [n_frames] or NULL                                               */
+    const int32_t* n_visible;   /* [n_frames] or NULL: visible_nodes.size() (cpd_lle only uses the
+                                   size of that vector, trackdlo.cpp:358)                           */
+    const double* H;            /* optional [n_frames][node_stride][node_stride] LLE matrix
+                                   H=(I-L)^T(I-L); NULL -> computed on the device (:236-237)        */
+    double* W;                  /* optional out [n_frames][node_stride][3] last W (:415)           */
+    int32_t* iters;             /* optional out [n_frames] EM iterations executed                   */
+    int32_t* status;            /* optional out [n_frames] TDLO_ST_* mask                           */
+} tdlo_cpd_batch;
+
+/* A batch of independent tracking_step problems (one tracker object each). */
+typedef struct tdlo_track_batch {
+    int32_t n_frames;
+    int32_t n_nodes;             /* nodes per tracker (Y_.rows()); same for the whole batch         */
+    const double* X;             /* [x_offsets[n_frames]][3]                                         */
+    const int64_t* x_offsets;    /* [n_frames+1]                                                     */
+    double* Y;                   /* [n_frames][n_nodes][3]  in: Y_, out: tracking result             */
+    double* sigma2;              /* [n_frames] in/out sigma2_                                        */
+    const double* geodesic_coord;/* [n_frames][n_nodes] rest arc-lengths (initialize_geodesic_coord) */
+    const int32_t* visible;      /* ragged visible_nodes                                             */
+    const int64_t* visible_offsets;      /* [n_frames+1]                                             */
+    const int32_t* visible_ext;  /* ragged visible_nodes_extended (sorted ascending)                 */
+    const int64_t* visible_ext_offsets;  /* [n_frames+1]                                             */
+    const double* H_pre;         /* optional [n_frames][n_nodes][n_nodes] LLE matrix of the guide
+                                    nodes for the pre-processing call (leading |vis_ext|^2 block,
+                                    row stride n_nodes); NULL -> computed on the device              */
+    double* guide_nodes;         /* optional out [n_frames][n_nodes][3] (first |vis_ext| rows valid) */
+    double* priors;              /* optional out [n_frames][2*n_nodes][4] correspondence_priors_     */
+    int32_t* n_priors;           /* optional out [n_frames]                                          */
+    int32_t* iters;              /* optional out [n_frames][2] {pre-proc, main} EM iterations        */
+    int32_t* status;             /* optional out [n_frames]                                          */
+    int32_t* state;              /* optional out [n_frames] 0 all visible,1 mid occluded,2 tail occluded,
+                                    3 head occluded,4 both ends occluded (trackdlo.cpp:929-995)      */
+} tdlo_track_batch;
+
+/* Creates a context on CUDA device `device`.  Capacities bound later batches:
+ * max_frames frames per call, max_nodes <= TDLO_MAX_NODES nodes per frame,
+ * max_points_total points summed over a batch. */
+int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32_t max_nodes, int64_t max_points_total);
+void tdlo_destroy(tdlo_ctx* ctx);
+const char* tdlo_last_error(const tdlo_ctx* ctx);   /* ctx may be NULL: last create() error */
+const char* tdlo_version(void);
+
+/* trackdlo::cpd_lle over a batch.  Host pointers; synchronous. */
+int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* batch, const tdlo_cpd_params* params);
+/* Same with device pointers; asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int tdlo_cpd_lle_batched_device(tdlo_ctx* ctx, const tdlo_cpd_batch* batch, const tdlo_cpd_params* params,
+                                void* stream);
+
+/* trackdlo::tracking_step over a batch.  Host pointers; synchronous. */
+int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch* batch, const tdlo_track_params* params);
+/* Same with device pointers; asynchronous on `stream`. */
+int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* batch,
+                                      const tdlo_track_params* params, void* stream);
+
+/* Launch geometry of the most recent call (for benchmarks / profiling):
+ * info[0]=cluster size, [1]=CTAs launched, [2]=threads per CTA, [3]=dynamic smem bytes,
+ * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */
+int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]);
+
+/* Overrides the automatic cluster-size choice (0 = automatic; 1,2,4,8,16). */
+int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t cluster_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACKDLO_B200_H */

@@ -1,0 +1,223 @@
+"""ctypes binding of the C ABI (include/trackdlo_b200.h) used by tests/ and bench.py.
+
+This is plumbing only: every call goes straight into libtrackdlo_b200.so (hand-written sm_100a
+CUDA).  There is no CPU fallback -- if the library is missing or no B200 is present the calls
+raise.  Argument names follow trackdlo::cpd_lle / trackdlo::tracking_step
+(trackdlo/include/trackdlo.h:81-102).
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrackdlo_b200.so")
+
+ST_NOT_CONVERGED, ST_SINGULAR, ST_TOO_FEW_NODES, ST_EMPTY_CLOUD, ST_TRAVERSE_UB, ST_PRE_NOT_CONVERGED = 1, 2, 4, 8, 16, 32
+
+ABI_SYMBOLS = [
+    "tdlo_create", "tdlo_destroy", "tdlo_last_error", "tdlo_version",
+    "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
+    "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
+    "tdlo_last_launch_info", "tdlo_set_cluster_size",
+]
+
+
+class TdloError(RuntimeError):
+    pass
+
+
+class CpdParamsC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("beta", "lambda_", "lle_weight", "mu", "tol", "alpha", "k_vis",
+                                           "visibility_threshold", "prune_radius")] + \
+               [("max_iter", C.c_int32), ("include_lle", C.c_int32)]
+
+
+class TrackParamsC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("visibility_threshold", "beta", "lambda_", "alpha", "k_vis", "mu", "tol",
+                                           "beta_pre_proc", "lambda_pre_proc", "lle_weight", "prune_radius")] + \
+               [("max_iter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CpdBatchC(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("node_stride", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("X", "x_offsets", "n_nodes", "Y", "sigma2", "priors", "n_priors",
+                                           "n_visible", "H", "W", "iters", "status")]
+
+
+class TrackBatchC(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_nodes", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "sigma2", "geodesic_coord", "visible",
+                                           "visible_offsets", "visible_ext", "visible_ext_offsets", "H_pre",
+                                           "guide_nodes", "priors", "n_priors", "iters", "status", "state")]
+
+
+@dataclass
+class CpdParams:
+    """Non-data arguments of trackdlo::cpd_lle (trackdlo.h:81-95); defaults = launch/trackdlo.launch."""
+    beta: float = 0.35
+    lambda_: float = 50000.0
+    lle_weight: float = 10.0
+    mu: float = 0.1
+    max_iter: int = 50
+    tol: float = 0.0002
+    include_lle: bool = False
+    alpha: float = 0.0
+    k_vis: float = 0.0
+    visibility_threshold: float = 0.01
+    prune_radius: float = 0.1
+
+    def to_c(self):
+        return CpdParamsC(self.beta, self.lambda_, self.lle_weight, self.mu, self.tol, self.alpha, self.k_vis,
+                          self.visibility_threshold, self.prune_radius, self.max_iter, int(self.include_lle))
+
+
+@dataclass
+class TrackParams:
+    """Constructor arguments of class trackdlo (trackdlo.h:59-71); defaults = launch/trackdlo.launch."""
+    visibility_threshold: float = 0.008
+    beta: float = 0.35
+    lambda_: float = 50000.0
+    alpha: float = 3.0
+    k_vis: float = 50.0
+    mu: float = 0.1
+    max_iter: int = 50
+    tol: float = 0.0002
+    beta_pre_proc: float = 3.0
+    lambda_pre_proc: float = 1.0
+    lle_weight: float = 10.0
+    prune_radius: float = 0.1
+
+    def to_c(self):
+        return TrackParamsC(self.visibility_threshold, self.beta, self.lambda_, self.alpha, self.k_vis, self.mu,
+                            self.tol, self.beta_pre_proc, self.lambda_pre_proc, self.lle_weight, self.prune_radius,
+                            self.max_iter, 0)
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libtrackdlo_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TdloError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.tdlo_last_error.restype = C.c_char_p
+        lib.tdlo_last_error.argtypes = [C.c_void_p]
+        lib.tdlo_version.restype = C.c_char_p
+        lib.tdlo_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int64]
+        lib.tdlo_destroy.argtypes = [C.c_void_p]
+        lib.tdlo_destroy.restype = None
+        lib.tdlo_cpd_lle_batched.argtypes = [C.c_void_p, C.POINTER(CpdBatchC), C.POINTER(CpdParamsC)]
+        lib.tdlo_cpd_lle_batched_device.argtypes = [C.c_void_p, C.POINTER(CpdBatchC), C.POINTER(CpdParamsC), C.c_void_p]
+        lib.tdlo_tracking_step_batched.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC)]
+        lib.tdlo_tracking_step_batched_device.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC), C.c_void_p]
+        lib.tdlo_last_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
+        _lib = lib
+    return _lib
+
+
+def _np(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a if shape is None else a.reshape(shape)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())          # torch tensor (host pinned or device)
+
+
+class Context:
+    """One tdlo_ctx (one GPU, one host thread)."""
+
+    def __init__(self, max_frames, max_nodes, max_points_total, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.tdlo_create(C.byref(self.h), device, max_frames, max_nodes, max_points_total)
+        if rc != 0:
+            raise TdloError(f"tdlo_create failed ({rc}): {self.lib.tdlo_last_error(None).decode()}")
+        self.max_frames, self.max_nodes = max_frames, max_nodes
+
+    def close(self):
+        if self.h:
+            self.lib.tdlo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TdloError(f"{what} failed ({rc}): {self.lib.tdlo_last_error(self.h).decode()}")
+
+    def set_cluster_size(self, c):
+        self._check(self.lib.tdlo_set_cluster_size(self.h, c), "tdlo_set_cluster_size")
+
+    def launch_info(self):
+        info = (C.c_int32 * 8)()
+        self.lib.tdlo_last_launch_info(self.h, info)
+        keys = ("cluster_size", "ctas", "threads", "smem_bytes", "tile_points", "launches", "ctas_per_sm", "sm_count")
+        return dict(zip(keys, list(info)))
+
+    # ------------------------------------------------------------------ cpd_lle, host buffers
+    def cpd_lle_batched(self, X, x_offsets, Y, sigma2, params: CpdParams, n_nodes=None, priors=None, n_priors=None,
+                        n_visible=None, H=None):
+        """X [sum Mp,3], x_offsets [F+1], Y [F,S,3], sigma2 [F]  ->  dict(Y, sigma2, W, iters, status)."""
+        X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
+        Y = _np(Y, np.float64).copy(); F, S = Y.shape[0], Y.shape[1]
+        s2 = _np(sigma2, np.float64).copy().reshape(F)
+        W = np.zeros((F, S, 3)); iters = np.zeros(F, np.int32); status = np.zeros(F, np.int32)
+        nn = None if n_nodes is None else _np(n_nodes, np.int32)
+        pr = None if priors is None else _np(priors, np.float64, (F, S, 4))
+        npr = None if n_priors is None else _np(n_priors, np.int32)
+        nv = None if n_visible is None else _np(n_visible, np.int32)
+        Hc = None if H is None else _np(H, np.float64, (F, S, S))
+        b = CpdBatchC(F, S, _ptr(X), _ptr(xo), _ptr(nn), _ptr(Y), _ptr(s2), _ptr(pr), _ptr(npr), _ptr(nv), _ptr(Hc),
+                      _ptr(W), _ptr(iters), _ptr(status))
+        pc = params.to_c()
+        self._check(self.lib.tdlo_cpd_lle_batched(self.h, C.byref(b), C.byref(pc)), "tdlo_cpd_lle_batched")
+        return dict(Y=Y, sigma2=s2, W=W, iters=iters, status=status)
+
+    def cpd_lle_batched_raw(self, batch: CpdBatchC, params: CpdParamsC, device=False, stream=0):
+        """Thin call with caller-owned buffers (pinned host or device pointers); used by bench.py."""
+        if device:
+            rc = self.lib.tdlo_cpd_lle_batched_device(self.h, C.byref(batch), C.byref(params), C.c_void_p(stream))
+        else:
+            rc = self.lib.tdlo_cpd_lle_batched(self.h, C.byref(batch), C.byref(params))
+        self._check(rc, "tdlo_cpd_lle_batched")
+
+    # ------------------------------------------------------------------ tracking_step, host buffers
+    def tracking_step_batched(self, X, x_offsets, Y, sigma2, geodesic_coord, visible, visible_offsets, visible_ext,
+                              visible_ext_offsets, params: TrackParams, H_pre=None):
+        X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
+        Y = _np(Y, np.float64).copy(); F, N = Y.shape[0], Y.shape[1]
+        s2 = _np(sigma2, np.float64).copy().reshape(F)
+        geo = _np(geodesic_coord, np.float64, (F, N))
+        vis = _np(visible, np.int32); vo = _np(visible_offsets, np.int64)
+        ext = _np(visible_ext, np.int32); eo = _np(visible_ext_offsets, np.int64)
+        Hc = None if H_pre is None else _np(H_pre, np.float64, (F, N, N))
+        guide = np.zeros((F, N, 3)); pri = np.zeros((F, 2 * N, 4)); npri = np.zeros(F, np.int32)
+        iters = np.zeros((F, 2), np.int32); status = np.zeros(F, np.int32); state = np.zeros(F, np.int32)
+        b = TrackBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(s2), _ptr(geo), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo),
+                        _ptr(Hc), _ptr(guide), _ptr(pri), _ptr(npri), _ptr(iters), _ptr(status), _ptr(state))
+        pc = params.to_c()
+        self._check(self.lib.tdlo_tracking_step_batched(self.h, C.byref(b), C.byref(pc)), "tdlo_tracking_step_batched")
+        return dict(Y=Y, sigma2=s2, guide=guide, priors=pri, n_priors=npri, iters=iters, status=status, state=state)
+
+    def tracking_step_batched_raw(self, batch: TrackBatchC, params: TrackParamsC, device=False, stream=0):
+        if device:
+            rc = self.lib.tdlo_tracking_step_batched_device(self.h, C.byref(batch), C.byref(params), C.c_void_p(stream))
+        else:
+            rc = self.lib.tdlo_tracking_step_batched(self.h, C.byref(batch), C.byref(params))
+        self._check(rc, "tdlo_tracking_step_batched")

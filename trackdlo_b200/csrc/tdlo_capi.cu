@@ -1,0 +1,422 @@
+// Host side of the C ABI declared in include/trackdlo_b200.h.
+// Replaces the host-visible surface of trackdlo::cpd_lle / trackdlo::tracking_step
+// (trackdlo/include/trackdlo.h:81-102) for batches of independent frames.
+#include "../../include/trackdlo_b200.h"
+#include "tdlo_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+using namespace tdlo;
+
+struct tdlo_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_frames = 0, max_nodes = 0;
+    long long max_points = 0;
+    cudaStream_t stream = nullptr;
+    // device staging for the host-pointer entry points
+    double *d_X = nullptr, *d_Y = nullptr, *d_sigma2 = nullptr, *d_priors = nullptr, *d_H = nullptr, *d_W = nullptr;
+    double *d_rest = nullptr, *d_guide = nullptr, *d_priors_out = nullptr;
+    long long *d_xoff = nullptr, *d_visoff = nullptr, *d_extoff = nullptr;
+    int *d_nnodes = nullptr, *d_npriors = nullptr, *d_nvis = nullptr, *d_iters = nullptr, *d_status = nullptr;
+    int *d_vis = nullptr, *d_ext = nullptr, *d_npri_out = nullptr, *d_state = nullptr;
+    // workspace
+    double* d_Xc = nullptr;
+    double* d_scratch = nullptr;
+    long long scratch_stride = 0;
+    int scratch_clusters = 0;
+    int* d_queue = nullptr;
+    int cluster_override = 0;
+    long long points_hint = 0;      // points per frame of the current host call (0 = unknown)
+    int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    char err[512] = {0};
+};
+
+static char g_create_err[512] = {0};
+
+static int fail(tdlo_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(ctx, TDLO_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
+
+extern "C" const char* tdlo_version(void) { return "trackdlo_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* tdlo_last_error(const tdlo_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    void* ptrs[] = {ctx->d_X, ctx->d_Y, ctx->d_sigma2, ctx->d_priors, ctx->d_H, ctx->d_W, ctx->d_rest, ctx->d_guide,
+                    ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
+                    ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
+                    ctx->d_Xc, ctx->d_scratch, ctx->d_queue};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32_t max_nodes, int64_t max_points_total) {
+    tdlo_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, TDLO_ERR_INVALID, "tdlo_create: out is NULL");
+    *out = nullptr;
+    if (max_frames < 1 || max_nodes < 4 || max_nodes > TDLO_MAX_NODES || max_points_total < 1)
+        return fail(nullptr, TDLO_ERR_INVALID, "tdlo_create: bad capacities (frames=%d nodes=%d points=%lld)", max_frames,
+                    max_nodes, (long long)max_points_total);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TDLO_ERR_CUDA, "tdlo_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, TDLO_ERR_INVALID, "tdlo_create: device %d out of range", device);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, TDLO_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, TDLO_ERR_CUDA, "tdlo_create: device %d is sm_%d%d; this build targets sm_100a only", device,
+                    prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, TDLO_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    ctx = new tdlo_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_frames = max_frames;
+    ctx->max_nodes = max_nodes;
+    ctx->max_points = max_points_total;
+    const size_t F = max_frames, N = max_nodes, P = (size_t)max_points_total;
+    const Scr sc = scr_layout(max_nodes);
+    ctx->scratch_stride = sc.total;
+    ctx->scratch_clusters = std::min<long long>((long long)ctx->sm_count * 2, (long long)max_frames);
+#define CKC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e2_ = (call);                                                                   \
+        if (e2_ != cudaSuccess) {                                                                   \
+            fail(nullptr, e2_ == cudaErrorMemoryAllocation ? TDLO_ERR_NOMEM : TDLO_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2_)); \
+            tdlo_destroy(ctx);                                                                      \
+            return e2_ == cudaErrorMemoryAllocation ? TDLO_ERR_NOMEM : TDLO_ERR_CUDA;              \
+        }                                                                                           \
+    } while (0)
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(dalloc(&ctx->d_X, P * 3));
+    CKC(dalloc(&ctx->d_Xc, P * 3));
+    CKC(dalloc(&ctx->d_xoff, F + 1));
+    CKC(dalloc(&ctx->d_Y, F * N * 3));
+    CKC(dalloc(&ctx->d_sigma2, F));
+    CKC(dalloc(&ctx->d_priors, F * N * 4));
+    CKC(dalloc(&ctx->d_W, F * N * 3));
+    CKC(dalloc(&ctx->d_rest, F * N));
+    CKC(dalloc(&ctx->d_guide, F * N * 3));
+    CKC(dalloc(&ctx->d_priors_out, F * N * 8));
+    CKC(dalloc(&ctx->d_visoff, F + 1));
+    CKC(dalloc(&ctx->d_extoff, F + 1));
+    CKC(dalloc(&ctx->d_nnodes, F));
+    CKC(dalloc(&ctx->d_npriors, F));
+    CKC(dalloc(&ctx->d_nvis, F));
+    CKC(dalloc(&ctx->d_iters, F * 2));
+    CKC(dalloc(&ctx->d_status, F));
+    CKC(dalloc(&ctx->d_vis, F * N));
+    CKC(dalloc(&ctx->d_ext, F * N));
+    CKC(dalloc(&ctx->d_npri_out, F));
+    CKC(dalloc(&ctx->d_state, F));
+    CKC(dalloc(&ctx->d_scratch, (size_t)ctx->scratch_stride * ctx->scratch_clusters));
+    CKC(dalloc(&ctx->d_queue, 1));
+    // exp table 2^(j/64)
+    double tab[64];
+    for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
+    CKC(cudaMemcpyToSymbol(c_exp_tab, tab, sizeof(tab)));
+#undef CKC
+    *out = ctx;
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t c) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!(c == 0 || c == 1 || c == 2 || c == 4 || c == 8 || c == 16)) return fail(ctx, TDLO_ERR_INVALID, "cluster size must be 0,1,2,4,8,16");
+    ctx->cluster_override = c;
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]) {
+    if (!ctx || !info) return TDLO_ERR_INVALID;
+    memcpy(info, ctx->info, sizeof(ctx->info));
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------
+typedef void (*kern_t)(const KArgs);
+
+static int pick_tile(int nmax, int budget) {
+    int best = 0;
+    for (int t = 32; t <= kMaxThreads; t += 32)
+        if (smem_layout(nmax, t).total <= budget) best = t;
+    return best;
+}
+
+static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points_per_frame_hint) {
+    CK(cudaSetDevice(ctx->device));
+    const int nmax = a.nmax;
+    // ---- kernel variant + tile
+    const int budget2 = 113 * 1024, budget1 = 227 * 1024;
+    kern_t kern;
+    int tile, occ, npw;
+    const int t2 = pick_tile(nmax, budget2);
+    if (nmax <= 64 && t2 >= 192 && (t2 / 32) * 8 >= nmax) { kern = tdlo_em_kernel<8, 2>; tile = t2; occ = 2; npw = 8; }
+    else {
+        tile = pick_tile(nmax, budget1);
+        occ = 1;
+        if (tile < 32) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
+        if ((tile / 32) * 8 >= nmax) { kern = tdlo_em_kernel<8, 1>; npw = 8; }
+        else { kern = tdlo_em_kernel<16, 1>; npw = 16; }
+    }
+    (void)npw;
+    const int smem = smem_layout(nmax, tile).total;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // ---- cluster size
+    int C = ctx->cluster_override;
+    if (C == 0) {
+        const long long slots = (long long)ctx->sm_count * occ;
+        C = 1;
+        while (C < kMaxCluster && (long long)a.n_frames * (C * 2) <= slots) C *= 2;
+        if (points_per_frame_hint > 0) {          // do not split a frame finer than ~2 tiles per CTA
+            int cap = 1;
+            while (cap < kMaxCluster && (long long)cap * 2 * tile * 2 <= points_per_frame_hint) cap *= 2;
+            C = std::min(C, cap);
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int max_clusters = 0;
+    for (;;) {
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(C, 1, 1);
+        cfg.blockDim = dim3(tile, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+        if (e == cudaSuccess && max_clusters > 0) break;
+        cudaGetLastError();
+        if (C == 1) return fail(ctx, TDLO_ERR_CUDA, "kernel does not fit (smem %d B, tile %d): %s", smem, tile, cudaGetErrorString(e));
+        C /= 2;
+    }
+    int n_clusters = std::min(std::min(a.n_frames, max_clusters), ctx->scratch_clusters);
+    if (n_clusters < 1) n_clusters = 1;
+    cfg.gridDim = dim3(n_clusters * C, 1, 1);
+    a.tile = tile;
+    a.Xc = ctx->d_Xc;
+    a.scratch = ctx->d_scratch;
+    a.scratch_stride = ctx->scratch_stride;
+    a.queue = ctx->d_queue;
+    a.scr_nodes = ctx->max_nodes;
+    CK(cudaMemsetAsync(ctx->d_queue, 0, sizeof(int), stream));
+    CK(cudaLaunchKernelEx(&cfg, kern, a));
+    ctx->info[0] = C; ctx->info[1] = n_clusters * C; ctx->info[2] = tile; ctx->info[3] = smem; ctx->info[4] = tile;
+    ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
+    return TDLO_OK;
+}
+
+static CpdP to_dev(const tdlo_cpd_params& p) {
+    CpdP d;
+    d.beta = p.beta; d.lambda = p.lambda; d.gamma = p.lle_weight; d.mu = p.mu; d.tol = p.tol; d.alpha = p.alpha;
+    d.k_vis = p.k_vis; d.tau = p.visibility_threshold; d.prune_radius = p.prune_radius;
+    d.max_iter = p.max_iter; d.include_lle = p.include_lle;
+    return d;
+}
+
+static int check_params(tdlo_ctx* ctx, double mu, double beta, int max_iter, double radius) {
+    if (!(mu > 0.0 && mu < 1.0)) return fail(ctx, TDLO_ERR_INVALID, "mu must be in (0,1)");
+    if (!(beta > 0.0)) return fail(ctx, TDLO_ERR_INVALID, "beta must be > 0");
+    if (max_iter < 0) return fail(ctx, TDLO_ERR_INVALID, "max_iter must be >= 0");
+    if (!(radius > 0.0)) return fail(ctx, TDLO_ERR_INVALID, "prune_radius must be > 0 (reference: 0.1)");
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_cpd_lle_batched_device(tdlo_ctx* ctx, const tdlo_cpd_batch* b, const tdlo_cpd_params* p, void* stream) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->node_stride < 4 || b->node_stride > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "node_stride %d outside [4,%d]", b->node_stride, ctx->max_nodes);
+    if (!b->X || !b->x_offsets || !b->Y || !b->sigma2) return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2 are required");
+    int rc = check_params(ctx, p->mu, p->beta, p->max_iter, p->prune_radius);
+    if (rc) return rc;
+    if (b->n_frames == 0) { ctx->info[5] = 0; return TDLO_OK; }
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = 0;
+    a.n_frames = b->n_frames; a.node_stride = b->node_stride; a.nmax = b->node_stride;
+    a.X = b->X; a.x_off = reinterpret_cast<const long long*>(b->x_offsets);
+    a.n_nodes = b->n_nodes; a.Y = b->Y; a.sigma2 = b->sigma2;
+    a.priors = b->priors; a.n_priors = b->n_priors; a.n_visible = b->n_visible; a.H = b->H;
+    a.W = b->W; a.iters = b->iters; a.status = b->status;
+    a.p0 = to_dev(*p);
+    a.p1 = a.p0;
+    return launch(ctx, a, (cudaStream_t)stream, ctx->points_hint);
+}
+
+extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* b, const tdlo_track_params* p, void* stream) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->n_nodes < 4 || b->n_nodes > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "n_nodes %d outside [4,%d]", b->n_nodes, ctx->max_nodes);
+    if (!b->X || !b->x_offsets || !b->Y || !b->sigma2 || !b->geodesic_coord || !b->visible || !b->visible_offsets ||
+        !b->visible_ext || !b->visible_ext_offsets)
+        return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2, geodesic_coord and both visibility lists are required");
+    int rc = check_params(ctx, p->mu, p->beta, p->max_iter, p->prune_radius);
+    if (rc) return rc;
+    if (!(p->beta_pre_proc > 0.0)) return fail(ctx, TDLO_ERR_INVALID, "beta_pre_proc must be > 0");
+    if (b->n_frames == 0) { ctx->info[5] = 0; return TDLO_OK; }
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = 1;
+    a.n_frames = b->n_frames; a.node_stride = b->n_nodes; a.nmax = b->n_nodes;
+    a.X = b->X; a.x_off = reinterpret_cast<const long long*>(b->x_offsets);
+    a.Y = b->Y; a.sigma2 = b->sigma2; a.H = b->H_pre;
+    a.iters = b->iters; a.status = b->status;
+    a.rest = b->geodesic_coord;
+    a.vis = b->visible; a.vis_off = reinterpret_cast<const long long*>(b->visible_offsets);
+    a.ext = b->visible_ext; a.ext_off = reinterpret_cast<const long long*>(b->visible_ext_offsets);
+    a.guide_out = b->guide_nodes; a.priors_out = b->priors; a.n_priors_out = b->n_priors; a.state_out = b->state;
+    // pre-processing call: cpd_lle(X, guide, s2, beta_pre, lambda_pre, lle_weight, mu, max_iter, tol, true)
+    // with the header defaults alpha=0, k_vis=0, visibility_threshold=0.01 (trackdlo.cpp:927, trackdlo.h:91-95)
+    a.p0.beta = p->beta_pre_proc; a.p0.lambda = p->lambda_pre_proc; a.p0.gamma = p->lle_weight; a.p0.mu = p->mu;
+    a.p0.tol = p->tol; a.p0.alpha = 0.0; a.p0.k_vis = 0.0; a.p0.tau = 0.01; a.p0.prune_radius = p->prune_radius;
+    a.p0.max_iter = p->max_iter; a.p0.include_lle = 1;
+    // main call (trackdlo.cpp:998)
+    a.p1.beta = p->beta; a.p1.lambda = p->lambda; a.p1.gamma = p->lle_weight; a.p1.mu = p->mu; a.p1.tol = p->tol;
+    a.p1.alpha = p->alpha; a.p1.k_vis = p->k_vis; a.p1.tau = p->visibility_threshold; a.p1.prune_radius = p->prune_radius;
+    a.p1.max_iter = p->max_iter; a.p1.include_lle = 0;
+    return launch(ctx, a, (cudaStream_t)stream, ctx->points_hint);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer entry points: copy in, run, copy out, synchronise
+// ---------------------------------------------------------------------------------------------
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+
+extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, const tdlo_cpd_params* p) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->n_frames == 0) return TDLO_OK;
+    if (b->node_stride < 4 || b->node_stride > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "node_stride %d outside [4,%d]", b->node_stride, ctx->max_nodes);
+    if (!b->X || !b->x_offsets || !b->Y || !b->sigma2) return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2 are required");
+    const size_t F = b->n_frames, S = b->node_stride;
+    const long long total = b->x_offsets[F];
+    if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
+    for (size_t f = 0; f < F; f++) if (b->x_offsets[f + 1] < b->x_offsets[f]) return fail(ctx, TDLO_ERR_INVALID, "x_offsets not monotone");
+    if (total > ctx->max_points) return fail(ctx, TDLO_ERR_INVALID, "%lld points exceed capacity %lld", total, ctx->max_points);
+    if (b->n_nodes) for (size_t f = 0; f < F; f++) if (b->n_nodes[f] > (int)S || b->n_nodes[f] < 0) return fail(ctx, TDLO_ERR_INVALID, "n_nodes[%zu] outside [0,node_stride]", f);
+    CK(cudaSetDevice(ctx->device));
+    if (b->H && !ctx->d_H) CK(dalloc(&ctx->d_H, (size_t)ctx->max_frames * ctx->max_nodes * ctx->max_nodes));
+    H2D(ctx->d_X, b->X, (size_t)total * 3 * sizeof(double));
+    H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
+    H2D(ctx->d_Y, b->Y, F * S * 3 * sizeof(double));
+    H2D(ctx->d_sigma2, b->sigma2, F * sizeof(double));
+    if (b->n_nodes) H2D(ctx->d_nnodes, b->n_nodes, F * sizeof(int));
+    if (b->priors) H2D(ctx->d_priors, b->priors, F * S * 4 * sizeof(double));
+    if (b->n_priors) H2D(ctx->d_npriors, b->n_priors, F * sizeof(int));
+    if (b->n_visible) H2D(ctx->d_nvis, b->n_visible, F * sizeof(int));
+    if (b->H) H2D(ctx->d_H, b->H, F * S * S * sizeof(double));
+    tdlo_cpd_batch d = *b;
+    d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.sigma2 = ctx->d_sigma2;
+    d.n_nodes = b->n_nodes ? ctx->d_nnodes : nullptr;
+    d.priors = b->priors ? ctx->d_priors : nullptr;
+    d.n_priors = b->n_priors ? ctx->d_npriors : nullptr;
+    d.n_visible = b->n_visible ? ctx->d_nvis : nullptr;
+    d.H = b->H ? ctx->d_H : nullptr;
+    d.W = ctx->d_W; d.iters = ctx->d_iters; d.status = ctx->d_status;
+    ctx->points_hint = total / (long long)F;
+    int rc = tdlo_cpd_lle_batched_device(ctx, &d, p, ctx->stream);
+    ctx->points_hint = 0;
+    if (rc) return rc;
+    D2H(b->Y, ctx->d_Y, F * S * 3 * sizeof(double));
+    D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));
+    if (b->W) D2H(b->W, ctx->d_W, F * S * 3 * sizeof(double));
+    if (b->iters) D2H(b->iters, ctx->d_iters, F * sizeof(int));
+    if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch* b, const tdlo_track_params* p) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->n_frames == 0) return TDLO_OK;
+    if (b->n_nodes < 4 || b->n_nodes > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "n_nodes %d outside [4,%d]", b->n_nodes, ctx->max_nodes);
+    if (!b->X || !b->x_offsets || !b->Y || !b->sigma2 || !b->geodesic_coord || !b->visible || !b->visible_offsets ||
+        !b->visible_ext || !b->visible_ext_offsets)
+        return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2, geodesic_coord and both visibility lists are required");
+    const size_t F = b->n_frames, N = b->n_nodes;
+    const long long total = b->x_offsets[F];
+    if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
+    for (size_t f = 0; f < F; f++) if (b->x_offsets[f + 1] < b->x_offsets[f]) return fail(ctx, TDLO_ERR_INVALID, "x_offsets not monotone");
+    if (total > ctx->max_points) return fail(ctx, TDLO_ERR_INVALID, "%lld points exceed capacity %lld", total, ctx->max_points);
+    for (size_t f = 0; f < F; f++) {
+        const long long nv = b->visible_offsets[f + 1] - b->visible_offsets[f], ne = b->visible_ext_offsets[f + 1] - b->visible_ext_offsets[f];
+        if (nv < 0 || nv > (long long)N || ne < 0 || ne > (long long)N) return fail(ctx, TDLO_ERR_INVALID, "frame %zu: visibility list longer than n_nodes", f);
+        for (long long i = 0; i < nv; i++) { const int v = b->visible[b->visible_offsets[f] + i]; if (v < 0 || v >= (int)N) return fail(ctx, TDLO_ERR_INVALID, "frame %zu: visible node %d out of range", f, v); }
+        for (long long i = 0; i < ne; i++) {
+            const int v = b->visible_ext[b->visible_ext_offsets[f] + i];
+            if (v < 0 || v >= (int)N) return fail(ctx, TDLO_ERR_INVALID, "frame %zu: visible_ext node %d out of range", f, v);
+            if (i > 0 && v <= b->visible_ext[b->visible_ext_offsets[f] + i - 1]) return fail(ctx, TDLO_ERR_INVALID, "frame %zu: visible_ext must be strictly ascending", f);
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (b->H_pre && !ctx->d_H) CK(dalloc(&ctx->d_H, (size_t)ctx->max_frames * ctx->max_nodes * ctx->max_nodes));
+    H2D(ctx->d_X, b->X, (size_t)total * 3 * sizeof(double));
+    H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
+    H2D(ctx->d_Y, b->Y, F * N * 3 * sizeof(double));
+    H2D(ctx->d_sigma2, b->sigma2, F * sizeof(double));
+    H2D(ctx->d_rest, b->geodesic_coord, F * N * sizeof(double));
+    H2D(ctx->d_visoff, b->visible_offsets, (F + 1) * sizeof(long long));
+    H2D(ctx->d_extoff, b->visible_ext_offsets, (F + 1) * sizeof(long long));
+    if (b->visible_offsets[F] > 0) H2D(ctx->d_vis, b->visible, (size_t)b->visible_offsets[F] * sizeof(int));
+    if (b->visible_ext_offsets[F] > 0) H2D(ctx->d_ext, b->visible_ext, (size_t)b->visible_ext_offsets[F] * sizeof(int));
+    if (b->H_pre) H2D(ctx->d_H, b->H_pre, F * N * N * sizeof(double));
+    tdlo_track_batch d = *b;
+    d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.sigma2 = ctx->d_sigma2;
+    d.geodesic_coord = ctx->d_rest;
+    d.visible = ctx->d_vis; d.visible_offsets = reinterpret_cast<const int64_t*>(ctx->d_visoff);
+    d.visible_ext = ctx->d_ext; d.visible_ext_offsets = reinterpret_cast<const int64_t*>(ctx->d_extoff);
+    d.H_pre = b->H_pre ? ctx->d_H : nullptr;
+    d.guide_nodes = ctx->d_guide; d.priors = ctx->d_priors_out; d.n_priors = ctx->d_npri_out;
+    d.iters = ctx->d_iters; d.status = ctx->d_status; d.state = ctx->d_state;
+    ctx->points_hint = total / (long long)F;
+    int rc = tdlo_tracking_step_batched_device(ctx, &d, p, ctx->stream);
+    ctx->points_hint = 0;
+    if (rc) return rc;
+    D2H(b->Y, ctx->d_Y, F * N * 3 * sizeof(double));
+    D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));
+    if (b->guide_nodes) D2H(b->guide_nodes, ctx->d_guide, F * N * 3 * sizeof(double));
+    if (b->priors) D2H(b->priors, ctx->d_priors_out, F * N * 8 * sizeof(double));
+    if (b->n_priors) D2H(b->n_priors, ctx->d_npri_out, F * sizeof(int));
+    if (b->iters) D2H(b->iters, ctx->d_iters, F * 2 * sizeof(int));
+    if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
+    if (b->state) D2H(b->state, ctx->d_state, F * sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDLO_OK;
+}

@@ -1,0 +1,1062 @@
+// Device side of the B200-native TrackDLO registration path (sm_100a).
+//
+// One thread-block CLUSTER owns one frame for its whole life: prune -> set-up -> all EM
+// iterations of cpd_lle (trackdlo/src/trackdlo.cpp:161-441), and in tracking mode the full
+// tracking_step (trackdlo.cpp:900-999: pre-processing registration, traverse_euclidean, main
+// registration) without returning to the host.  Clusters pull frames from an atomic queue
+// (persistent scheduling), so data-dependent iteration counts (trackdlo.cpp:424-428) balance
+// automatically.  The Nn x Mp affinity matrix P is never written to HBM: each CTA streams its
+// slice of the frame's points in tiles, keeps one P tile in shared memory and reduces it to
+// P1 / PX partial sums in registers.
+//
+// Everything is fp64 (the reference is MatrixXd end to end; the parity gate is 1e-5 on W).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace tdlo {
+
+constexpr int kMaxThreads = 256;
+constexpr int kMaxCluster = 16;
+constexpr int kMaxNodes = 256;
+
+// status bits (mirror include/trackdlo_b200.h)
+constexpr int ST_NOT_CONVERGED = 1, ST_SINGULAR = 2, ST_TOO_FEW_NODES = 4, ST_EMPTY = 8, ST_TRAVERSE_UB = 16,
+              ST_PRE_NOT_CONVERGED = 32;
+
+struct CpdP {
+    double beta, lambda, gamma, mu, tol, alpha, k_vis, tau, prune_radius;
+    int max_iter, include_lle;
+};
+
+struct KArgs {
+    int mode;            // 0 = batched cpd_lle, 1 = batched tracking_step
+    int n_frames;
+    int node_stride;     // row stride of Y / priors / W / H (nodes)
+    int tile;            // points per tile == blockDim.x
+    int nmax;            // largest node count in the batch (sizes shared memory)
+    // frame data (device pointers)
+    const double* X; const long long* x_off;
+    const int* n_nodes;
+    double* Y; double* sigma2;
+    const double* priors; const int* n_priors; const int* n_visible;
+    const double* H;
+    double* W; int* iters; int* status;
+    // tracking-step extras
+    const double* rest;
+    const int* vis; const long long* vis_off;
+    const int* ext; const long long* ext_off;
+    double* guide_out; double* priors_out; int* n_priors_out; int* state_out;
+    CpdP p0;             // mode 0: the call's params; mode 1: pre-processing registration
+    CpdP p1;             // mode 1: main registration
+    // workspace
+    double* Xc;          // compacted points, same indexing as X
+    double* scratch;     // per-cluster scratch
+    long long scratch_stride;   // doubles per cluster
+    int* queue;          // frame queue counter
+    int scr_nodes;       // node capacity the scratch layout was sized for
+};
+
+__constant__ double c_exp_tab[64];   // 2^(j/64), filled by the host
+
+// ------------------------------------------------------------------------------------------
+// per-cluster global scratch layout (doubles); N = scr_nodes
+// ------------------------------------------------------------------------------------------
+struct Scr {
+    long long G, HG, H, AB, PART, DMIN, GATH, STATE, TRV, PRI, GUIDE, CTL, total;
+};
+__host__ __device__ inline Scr scr_layout(int N) {
+    Scr s;
+    long long o = 0, n2 = (long long)N * N;
+    s.G = o; o += n2;
+    s.HG = o; o += n2;
+    s.H = o; o += n2;
+    s.AB = o; o += (long long)N * (N + 4);
+    s.PART = o; o += (long long)kMaxCluster * (4 * N + 4);
+    s.DMIN = o; o += (long long)kMaxCluster * N;
+    s.GATH = o; o += kMaxCluster * 2;
+    s.STATE = o; o += 3 * N + 8;
+    s.TRV = o; o += 2LL * (N + 2) * 4;
+    s.PRI = o; o += (2LL * N + 4) * 4;
+    s.GUIDE = o; o += 3 * N;
+    s.CTL = o; o += 8;
+    s.total = (o + 15) & ~15LL;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory layout (bytes)
+// ------------------------------------------------------------------------------------------
+struct SmemL {
+    int tab, node4, wbuf, y0, s, vw, yext, jd, hy0, p1, px, wsol, tnew, pacc, red, prow, used, ptile, total;
+};
+__host__ __device__ inline SmemL smem_layout(int N, int tile) {
+    SmemL l;
+    int o = 0;
+    l.tab = o; o += 64 * 8;
+    l.node4 = o; o += N * 32;
+    l.wbuf = o; o += tile * 32;
+    l.y0 = o; o += 3 * N * 8;
+    l.s = o; o += N * 8;
+    l.vw = o; o += N * 8;
+    l.yext = o; o += 3 * N * 8;
+    l.jd = o; o += N * 8;
+    l.hy0 = o; o += 3 * N * 8;
+    l.p1 = o; o += N * 8;
+    l.px = o; o += 3 * N * 8;
+    l.wsol = o; o += 3 * N * 8;
+    l.tnew = o; o += 3 * N * 8;
+    l.pacc = o; o += 4 * N * 8;
+    l.red = o; o += 64 * 8;
+    l.prow = o; o += N * 4;
+    l.used = o; o += N * 4;
+    o = (o + 31) & ~31;
+    l.ptile = o; o += N * tile * 8;
+    l.total = o;
+    return l;
+}
+
+struct Smem {
+    double* tab; double4* node4; double4* wbuf;
+    double *y0, *s, *vw, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *pacc, *red;
+    int *prow, *used;
+    double* ptile;
+};
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; every thread gets the total.  `red` needs >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; w++) t += red[w];
+    return t;
+}
+
+// exp(-z) for z >= 0, fp64, ~1 ulp: 64-entry table + degree-5 polynomial.
+// Results below 2.4e-307 flush to zero (the reference keeps denormals down to 4.9e-324; those
+// terms are > 290 orders of magnitude below the outlier constant c they are added to).
+__device__ __forceinline__ double exp_neg(double z, const double* __restrict__ tab) {
+    const double L = 92.33248261689366;           // 64 / ln 2
+    const double C_HI = 0.010830424696249145;     // ln 2 / 64 (hi)
+    const double C_LO = 3.623510646634843e-19;    // ln 2 / 64 (lo)
+    const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52
+    double t = fma(z, -L, MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -C_HI, -z);
+    r = fma(nf, -C_LO, r);
+    const double tj = tab[n & 63];
+    const int k = n >> 6;
+    const double r2 = r * r;
+    double q = fma(r, 8.3333333333333332e-3, 4.1666666666666664e-2);
+    q = fma(q, r, 1.6666666666666666e-1);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r2, r);
+    double e = fma(tj, p, tj);
+    e = __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
+    return (__double2hiint(z) >= 0x40861000) ? 0.0 : e;     // z >= 706 (or NaN) -> 0
+}
+
+__device__ __forceinline__ double dist2(double ax, double ay, double az, double bx, double by, double bz) {
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// ------------------------------------------------------------------------------------------
+// Prune + order-preserving compaction of this CTA's slice of the frame (trackdlo.cpp:177-195)
+// and the sum of squared distances of the kept points to all nodes (sigma2 init, :263-273).
+// Returns the number of kept points (uniform over the block); *sum_out gets the block sum.
+// ------------------------------------------------------------------------------------------
+__device__ int prune_slice(const Smem& sm, const double* __restrict__ Xraw, long long r0, long long r1,
+                           double* __restrict__ Xc, int Nn, double radius, double* sum_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
+    int* wcnt = reinterpret_cast<int*>(sm.red);      // nw ints
+    int count = 0;
+    double sum2 = 0.0;
+    for (long long base = r0; base < r1; base += tile) {
+        const long long n = base + tid;
+        const bool valid = n < r1;
+        double x = 0, y = 0, z = 0;
+        if (valid) { x = __ldg(Xraw + n * 3); y = __ldg(Xraw + n * 3 + 1); z = __ldg(Xraw + n * 3 + 2); }
+        double best = 1e300, tot = 0.0;
+        for (int j = 0; j < Nn; j++) {
+            const double4 q = sm.node4[j];
+            const double d2 = dist2(q.x, q.y, q.z, x, y, z);
+            tot += d2;
+            best = fmin(best, d2);
+        }
+        const bool keep = valid && (sqrt(best) < radius);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < nw; w++) { const int c = wcnt[w]; if (w < warp) before += c; total += c; }
+        if (keep) {
+            const long long dst = r0 + count + before + __popc(bal & ((1u << lane) - 1u));
+            Xc[dst * 3] = x; Xc[dst * 3 + 1] = y; Xc[dst * 3 + 2] = z;
+            sum2 += tot;
+        }
+        count += total;
+        __syncthreads();
+    }
+    *sum_out = block_sum(sum2, sm.red);
+    return count;
+}
+
+// ------------------------------------------------------------------------------------------
+// Visibility pre-pass: per-node min squared distance to this CTA's points (trackdlo.cpp:279-296).
+// Result (per-CTA partial) is written to dmin_out[0..Nn).
+// ------------------------------------------------------------------------------------------
+__device__ void dmin_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn, double* dmin_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
+    double* wmin = sm.ptile;                   // [nw][Nn], P tile is idle here
+    for (int i = tid; i < nw * Nn; i += tile) wmin[i] = 1e300;
+    __syncthreads();
+    for (int base = 0; base < n_local; base += tile) {
+        const int n = base + tid;
+        const bool valid = n < n_local;
+        double x = 0, y = 0, z = 0;
+        if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
+        for (int j = 0; j < Nn; j++) {
+            const double4 q = sm.node4[j];
+            double d2 = dist2(q.x, q.y, q.z, x, y, z);
+            if (!valid) d2 = 1e300;
+            // warp min of a non-negative double: order == order of its bit pattern
+            const unsigned hi = (unsigned)__double2hiint(d2);
+            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
+            const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+            if (lane == 0) {
+                const double m = __hiloint2double((int)mh, (int)ml);
+                double* slot = wmin + warp * Nn + j;
+                if (m < *slot) *slot = m;
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < Nn; j += tile) {
+        double m = wmin[j];
+        for (int w = 1; w < nw; w++) m = fmin(m, wmin[w * Nn + j]);
+        __stcg(dmin_out + j, m);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused E-step over this CTA's slice (trackdlo.cpp:278-389): distances -> arg-max node ->
+// geodesic distances -> P -> (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.
+// Phase A is thread-per-point (P column into the shared-memory tile); phase B is
+// warp-per-node with lanes over the tile's points and register accumulators.
+// part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
+// ------------------------------------------------------------------------------------------
+template <int NPW, bool VIS>
+__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn,
+                            double sigma2, double c_norm, double rscale, double* part_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
+    const int per_group = nw * NPW;
+    const int ngroups = (Nn + per_group - 1) / per_group;
+    double acc[NPW][4];
+#pragma unroll
+    for (int i = 0; i < NPW; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0; }
+    if (ngroups > 1) {
+        for (int i = tid; i < 4 * Nn; i += tile) sm.pacc[i] = 0.0;
+    }
+    double sxx = 0.0;
+    const double* __restrict__ tab = sm.tab;
+    double* __restrict__ pcol = sm.ptile + tid;
+
+    for (int base = 0; base < n_local; base += tile) {
+        const int n = base + tid;
+        const bool valid = n < n_local;
+        double x = 0, y = 0, z = 0;
+        if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
+
+        // ---- nearest node (== arg-max of the Gaussian P of trackdlo.cpp:298-310)
+        double best = 1e300;
+        int a = 0;
+#pragma unroll 4
+        for (int j = 0; j < Nn; j++) {
+            const double4 q = sm.node4[j];
+            const double d2 = dist2(q.x, q.y, q.z, x, y, z);
+            if (d2 < best) { best = d2; a = j; }
+        }
+        // whole column underflows to 0 in the reference -> maxCoeff returns index 0
+        if ((-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
+        int q1 = a - 1; if (q1 == -1) q1 = 2;
+        int q2 = a + 1; if (q2 == Nn) q2 = Nn - 3;
+        double da, d1, d2n;
+        { const double4 q = sm.node4[a];  da  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        { const double4 q = sm.node4[q1]; d1  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        { const double4 q = sm.node4[q2]; d2n = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        const bool pick1 = d1 < d2n;                     // trackdlo.cpp:324-329
+        const int b = pick1 ? q1 : q2;
+        const double db = pick1 ? d1 : d2n;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const double dlo = a < b ? da : db, dhi = a < b ? db : da;
+        // scaled geodesic coordinate: t = sqrt(0.5/sigma2) * (|s_j - s_ref| + d_ref)
+        const double alo = sm.node4[lo].w + dlo * rscale;        //  s'_lo + d'_lo  (minus s'_j)
+        const double ahi = dhi * rscale - sm.node4[hi].w;        //  d'_hi - s'_hi  (plus  s'_j)
+
+        // ---- P column (trackdlo.cpp:332-354, 358-375)
+        double colsum = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < Nn; j++) {
+            const double sj = sm.node4[j].w;
+            double t = (j <= lo) ? (alo - sj) : (ahi + sj);
+            if (j > lo && j < hi) t = 0.0;               // rows between lo and hi stay 0 (end quirk)
+            double p = exp_neg(t * t, tab);
+            if (VIS) p *= sm.vw[j];
+            colsum += p;
+            pcol[j * tile] = p;
+        }
+        const double den = colsum + c_norm;              // trackdlo.cpp:379 / 382
+        const double w = valid ? 1.0 / den : 0.0;
+        sxx = fma(colsum * w, x * x + y * y + z * z, sxx);   // Pt1_n * |x_n|^2 (trackdlo.cpp:418)
+        sm.wbuf[tid] = make_double4(w, w * x, w * y, w * z);
+        __syncthreads();
+
+        // ---- P1 / PX accumulation (trackdlo.cpp:387-389)
+        for (int g = 0; g < ngroups; g++) {
+            const int m0 = g * per_group + warp;
+            for (int cn = lane; cn < tile; cn += 32) {
+                const double4 w4 = sm.wbuf[cn];
+#pragma unroll
+                for (int i = 0; i < NPW; i++) {
+                    const int m = m0 + nw * i;
+                    if (m < Nn) {
+                        const double p = sm.ptile[m * tile + cn];
+                        acc[i][0] = fma(p, w4.x, acc[i][0]);
+                        acc[i][1] = fma(p, w4.y, acc[i][1]);
+                        acc[i][2] = fma(p, w4.z, acc[i][2]);
+                        acc[i][3] = fma(p, w4.w, acc[i][3]);
+                    }
+                }
+            }
+            if (ngroups > 1) {
+#pragma unroll
+                for (int i = 0; i < NPW; i++) {
+                    const int m = m0 + nw * i;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const double v = warp_sum(acc[i][k]);
+                        if (lane == 0 && m < Nn) sm.pacc[m * 4 + k] += v;
+                        acc[i][k] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (ngroups == 1) {
+#pragma unroll
+        for (int i = 0; i < NPW; i++) {
+            const int m = warp + nw * i;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double v = warp_sum(acc[i][k]);
+                if (lane == 0 && m < Nn) __stcg(part_out + m * 4 + k, v);
+            }
+        }
+    } else {
+        __syncthreads();
+        for (int i = tid; i < 4 * Nn; i += tile) __stcg(part_out + i, sm.pacc[i]);
+    }
+    const double sx = block_sum(sxx, sm.red);
+    if (tid == 0) __stcg(part_out + 4 * Nn, sx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gauss-Jordan elimination with implicit partial (row) pivoting on the augmented system
+// AB = [A | B] (n x (n+3), row stride ld).  Replaces completeOrthogonalDecomposition().solve
+// (trackdlo.cpp:415) for the full-rank A of this path.  Block-cooperative; W -> wsol[n][3].
+// Returns non-zero (uniform) if a zero / non-finite pivot was met.
+// ------------------------------------------------------------------------------------------
+__device__ int gj_solve(double* AB, int n, int ld, int* prow, int* used, double* rpiv_slot, double* wsol) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int ncol = n + 3;
+    for (int i = tid; i < n; i += nt) used[i] = 0;
+    int bad = 0;
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        if (warp == 0) {
+            double best = -1.0;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                if (!used[i]) {
+                    const double v = fabs(AB[(long long)i * ld + k]);
+                    if (v > best || !(v == v)) { best = v; bi = i; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                if (bi == 0x7fffffff) bi = 0;
+                prow[k] = bi;
+                used[bi] = 1;
+                *rpiv_slot = 1.0 / AB[(long long)bi * ld + k];
+            }
+        }
+        __syncthreads();
+        const int p = prow[k];
+        const double rp = *rpiv_slot;
+        if (!(fabs(rp) <= 1.79e308)) bad = 1;          // pivot 0 -> inf, NaN -> NaN
+        const double* __restrict__ prowp = AB + (long long)p * ld;
+        for (int i = warp; i < n; i += nw) {
+            if (i == p) continue;
+            double* __restrict__ row = AB + (long long)i * ld;
+            const double f = row[k] * rp;
+            for (int j = k + 1 + lane; j < ncol; j += 32) row[j] = fma(-f, prowp[j], row[j]);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < 3 * n; i += nt) {
+        const int k = i / 3, d = i - 3 * k;
+        const int p = prow[k];
+        wsol[i] = AB[(long long)p * ld + n + d] / AB[(long long)p * ld + k];
+    }
+    __syncthreads();
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------
+// LLE weights, one node per thread (trackdlo.cpp:92-159).  Mirrors the operation order of
+// oracle/trackdlo_oracle.cpp::lle_weights_node with explicitly rounded mul/add/div so that both
+// produce identical bits (the 6x6 Gram matrices are rank 3; their inverse is rounding noise).
+// Writes row i of E = I - L into E[i*ldE + ...] (row must be pre-zeroed).
+// ------------------------------------------------------------------------------------------
+__device__ int lle_lu6(double* a, int nb, int* piv) {
+    int sign = 1;
+    for (int k = 0; k < nb; k++) {
+        int p = k;
+        double best = fabs(a[k * 6 + k]);
+        for (int i = k + 1; i < nb; i++) {
+            const double v = fabs(a[i * 6 + k]);
+            if (v > best) { best = v; p = i; }
+        }
+        piv[k] = p;
+        if (p != k) {
+            for (int j = 0; j < nb; j++) { const double t = a[k * 6 + j]; a[k * 6 + j] = a[p * 6 + j]; a[p * 6 + j] = t; }
+            sign = -sign;
+        }
+        const double pv = a[k * 6 + k];
+        if (pv != 0.0) {
+            for (int i = k + 1; i < nb; i++) {
+                const double l = __ddiv_rn(a[i * 6 + k], pv);
+                a[i * 6 + k] = l;
+                for (int j = k + 1; j < nb; j++) a[i * 6 + j] = __dsub_rn(a[i * 6 + j], __dmul_rn(l, a[k * 6 + j]));
+            }
+        }
+    }
+    return sign;
+}
+
+__device__ void lle_row(const double* __restrict__ y0 /*[n][3]*/, int M, int i, double* Erow) {
+    int nbr[6];
+    int nb = 0;
+    const int k = 3;
+    if (i - k < 0) { for (int t = 0; t <= i + k && t < M; t++) if (t != i) nbr[nb++] = t; }
+    else if (i + k >= M) { for (int t = i - k; t <= M - 1; t++) if (t != i) nbr[nb++] = t; }
+    else { for (int t = i - k; t <= i + k; t++) if (t != i) nbr[nb++] = t; }
+    double comp[6][3];
+    for (int r = 0; r < nb; r++)
+        for (int d = 0; d < 3; d++) comp[r][d] = __dsub_rn(y0[i * 3 + d], y0[nbr[r] * 3 + d]);
+    double g[36], lu[36];
+    for (int t = 0; t < 36; t++) g[t] = 0.0;
+    for (int a = 0; a < nb; a++)
+        for (int b = 0; b < nb; b++)
+            g[a * 6 + b] = __dadd_rn(__dadd_rn(__dmul_rn(comp[a][0], comp[b][0]), __dmul_rn(comp[a][1], comp[b][1])),
+                                     __dmul_rn(comp[a][2], comp[b][2]));
+    int piv[6];
+    for (int t = 0; t < 36; t++) lu[t] = g[t];
+    const int sign = lle_lu6(lu, nb, piv);
+    double det = (double)sign;
+    for (int t = 0; t < nb; t++) det = __dmul_rn(det, lu[t * 6 + t]);
+    if (!(det != 0.0)) {
+        for (int t = 0; t < nb; t++) g[t * 6 + t] = __dadd_rn(g[t * 6 + t], 0.00001);
+        for (int t = 0; t < 36; t++) lu[t] = g[t];
+        lle_lu6(lu, nb, piv);
+    }
+    double rs[6], tot = 0.0;
+    for (int r = 0; r < nb; r++) rs[r] = 0.0;
+    // explicit inverse column by column; accumulate the row sums (Gi_inv * 1) in column order
+    for (int c = 0; c < nb; c++) {
+        double bcol[6];
+        for (int r = 0; r < nb; r++) bcol[r] = (r == c) ? 1.0 : 0.0;
+        for (int t = 0; t < nb; t++) { const int p = piv[t]; if (p != t) { const double x = bcol[t]; bcol[t] = bcol[p]; bcol[p] = x; } }
+        for (int r = 1; r < nb; r++) {
+            double s = bcol[r];
+            for (int t = 0; t < r; t++) s = __dsub_rn(s, __dmul_rn(lu[r * 6 + t], bcol[t]));
+            bcol[r] = s;
+        }
+        for (int r = nb - 1; r >= 0; r--) {
+            double s = bcol[r];
+            for (int t = r + 1; t < nb; t++) s = __dsub_rn(s, __dmul_rn(lu[r * 6 + t], bcol[t]));
+            bcol[r] = __ddiv_rn(s, lu[r * 6 + r]);
+        }
+        for (int r = 0; r < nb; r++) rs[r] = __dadd_rn(rs[r], bcol[r]);
+    }
+    for (int r = 0; r < nb; r++) tot = __dadd_rn(tot, rs[r]);
+    Erow[i] = 1.0;
+    for (int r = 0; r < nb; r++) Erow[nbr[r]] = __dsub_rn(0.0, __ddiv_rn(rs[r], tot));
+}
+
+// ------------------------------------------------------------------------------------------
+// traverse_euclidean (trackdlo.cpp:584-898) + helpers (utils.cpp:172-241); single thread.
+// Semantics follow oracle/trackdlo_oracle.cpp (explicit bounds where the reference has UB).
+// ------------------------------------------------------------------------------------------
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 ld3(const double* g, int i) { return {g[i * 3], g[i * 3 + 1], g[i * 3 + 2]}; }
+__device__ __forceinline__ double vdist(V3 a, V3 b) { return sqrt(dist2(a.x, a.y, a.z, b.x, b.y, b.z)); }
+
+__device__ bool is_between(V3 x, V3 a, V3 b) {
+    const double xs[3] = {x.x, x.y, x.z}, as[3] = {a.x, a.y, a.z}, bs[3] = {b.x, b.y, b.z};
+    bool in_bound = true;
+    for (int i = 0; i < 3; i++) {
+        if (!(as[i] - 0.0001 <= xs[i] && xs[i] <= bs[i] + 0.0001) &&
+            !(bs[i] - 0.0001 <= xs[i] && xs[i] <= as[i] + 0.0001)) in_bound = false;
+    }
+    return in_bound;
+}
+
+__device__ int line_sphere(V3 A, V3 B, V3 C, double radius, V3* out) {
+    const double a = dist2(A.x, A.y, A.z, B.x, B.y, B.z);
+    const double b = 2 * ((B.x - A.x) * (A.x - C.x) + (B.y - A.y) * (A.y - C.y) + (B.z - A.z) * (A.z - C.z));
+    const double c = dist2(A.x, A.y, A.z, C.x, C.y, C.z) - radius * radius;
+    const double delta = b * b - 4 * a * c;
+    int cnt = 0;
+    if (delta < 0) return 0;
+    if (delta > 0) {
+        const double sq = sqrt(delta);
+        const double d1 = (-b + sq) / (2 * a), d2 = (-b - sq) / (2 * a);
+        const V3 p1 = {A.x + d1 * (B.x - A.x), A.y + d1 * (B.y - A.y), A.z + d1 * (B.z - A.z)};
+        const V3 p2 = {A.x + d2 * (B.x - A.x), A.y + d2 * (B.y - A.y), A.z + d2 * (B.z - A.z)};
+        if (is_between(p1, A, B)) out[cnt++] = p1;
+        if (is_between(p2, A, B)) out[cnt++] = p2;
+    } else {
+        const double d1 = -b / (2 * a);
+        const V3 p1 = {A.x + d1 * (B.x - A.x), A.y + d1 * (B.y - A.y), A.z + d1 * (B.z - A.z)};
+        if (is_between(p1, A, B)) out[cnt++] = p1;
+    }
+    return cnt;
+}
+
+// scans segments i = from, from+dir, ... while (dir>0 ? i+1 <= bound : i >= bound); returns yielding i or -1
+__device__ int pursue(const double* guide, int from, int dir, int bound, V3& centre, double look) {
+    for (int i = from; dir > 0 ? (i + 1 <= bound) : (i >= bound); i += dir) {
+        const V3 A = ld3(guide, i), B = ld3(guide, i + dir);
+        V3 xs[2];
+        const int n = line_sphere(A, B, centre, look, xs);
+        if (n == 0) continue;
+        if (n == 1 && vdist(xs[0], B) > vdist(centre, B)) continue;
+        V3 pick = xs[0];
+        if (n == 2 && !(vdist(xs[0], B) <= vdist(xs[1], B))) pick = xs[1];
+        centre = pick;
+        return i;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void emit4(double* out, int& cnt, double idx, V3 p) {
+    out[cnt * 4] = idx; out[cnt * 4 + 1] = p.x; out[cnt * 4 + 2] = p.y; out[cnt * 4 + 3] = p.z;
+    cnt++;
+}
+
+// returns number of pairs written to out ([<= G+1][4]); *err |= bits on reference-UB paths
+__device__ int traverse_euclidean(const double* geo, int G, const double* guide, int R, const int* vis, int V,
+                                  int alignment, int align_idx, double* out, int* err) {
+    int cnt = 0;
+    if (R == 1) { emit4(out, cnt, vis[0], ld3(guide, 0)); return cnt; }
+    if (alignment == 0) {
+        emit4(out, cnt, vis[0], ld3(guide, 0));
+        int cs = 0;
+        for (int i = 0; i < V; i++) { if (i == vis[i]) cs++; else break; }
+        if (cs == 0) { *err |= 1; return cnt; }
+        int last = 0, k = 0;
+        V3 centre = ld3(guide, 0);
+        while (last + 1 <= cs - 1 && k + 1 <= G - 1) {
+            const double look = fabs(geo[k + 1] - geo[k]);
+            const int got = pursue(guide, last, +1, cs - 1, centre, look);
+            if (got < 0) break;
+            last = got;
+            emit4(out, cnt, k + 1, centre);
+            k++;
+        }
+    } else if (alignment == 1) {
+        emit4(out, cnt, vis[V - 1], ld3(guide, R - 1));
+        int cs = 0;
+        for (int i = 1; i <= V; i++) { if (vis[V - i] == G - i) cs++; else break; }
+        int last = R - 1, k = G - 1;
+        V3 centre = ld3(guide, R - 1);
+        const int lowest = R - cs;
+        while (last - 1 >= lowest && k - 1 >= 0) {
+            const double look = fabs(geo[k] - geo[k - 1]);
+            const int got = pursue(guide, last, -1, lowest + 1, centre, look);
+            if (got < 0) break;
+            last = got;
+            emit4(out, cnt, k - 1, centre);
+            k--;
+        }
+    } else {
+        if (align_idx < 0 || align_idx >= V || align_idx >= R) { *err |= 2; return cnt; }
+        emit4(out, cnt, vis[align_idx], ld3(guide, align_idx));
+        int cs2 = 1;
+        for (int i = align_idx + 1; i < V; i++) { if (vis[i] - vis[i - 1] == 1) cs2++; else break; }
+        int last = align_idx, k = vis[align_idx];
+        V3 centre = ld3(guide, align_idx);
+        while (last + 1 <= align_idx + cs2 - 1 && k + 1 <= G - 1) {
+            const double look = fabs(geo[k + 1] - geo[k]);
+            const int got = pursue(guide, last, +1, align_idx + cs2 - 1, centre, look);
+            if (got < 0) break;
+            last = got;
+            emit4(out, cnt, k + 1, centre);
+            k++;
+        }
+        int cs1 = 1;
+        if (align_idx - 1 >= 0)
+            for (int i = align_idx - 1; i >= 0 && i + 1 < V; i++) { if (vis[i + 1] - vis[i] == 1) cs1++; else break; }
+        last = align_idx; k = vis[align_idx];
+        centre = ld3(guide, align_idx);
+        while ((unsigned long long)(long long)(last - 1) >= (unsigned long long)(long long)align_idx - (unsigned long long)cs1
+               && k - 1 >= 0) {
+            const double look = fabs(geo[k] - geo[k - 1]);
+            const int got = pursue(guide, last, -1, 1, centre, look);
+            if (got < 0) break;
+            last = got;
+            emit4(out, cnt, k - 1, centre);
+            k--;
+        }
+    }
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// One cpd_lle call executed by the whole cluster (trackdlo.cpp:161-441).
+// All CTAs execute the same sequence of cluster barriers.  Returns the status mask (uniform).
+// Yio: global [Nn][3] in/out.  sigma2_out / Wout / iters_out may be null.
+// ------------------------------------------------------------------------------------------
+template <int NPW>
+__device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& a, double* cscr,
+                       const double* __restrict__ Xraw, long long m0, double* __restrict__ Xc,
+                       double* Yio, int Nn, double sigma2_in, double* sigma2_out, const CpdP& p,
+                       const double* priors, int n_priors, int n_visible, const double* Hext, int hstride,
+                       double* Wout, int* iters_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int rank = (int)cluster.block_rank();
+    const int C = (int)cluster.num_blocks();
+    const Scr sc = scr_layout(a.scr_nodes);
+    double* gG = cscr + sc.G;
+    double* gHG = cscr + sc.HG;
+    double* gH = cscr + sc.H;
+    double* gPART = cscr + sc.PART;
+    double* gDMIN = cscr + sc.DMIN;
+    double* gGATH = cscr + sc.GATH;
+    double* gSTATE = cscr + sc.STATE;
+    const int ld = Nn + 3;
+    const bool ab_in_smem = (Nn + 3) <= a.tile;
+    double* AB = ab_in_smem ? sm.ptile : (cscr + sc.AB);
+
+    if (Nn < 4) {                         // reference indexes rows 2 and Nn-3 (trackdlo.cpp:313-321)
+        if (rank == 0 && tid == 0) { if (iters_out) *iters_out = 0; }
+        return ST_TOO_FEW_NODES;
+    }
+
+    // ---- Y -> shared (Y0 and current Y), arc-length coordinates s (trackdlo.cpp:203, 216-223)
+    for (int i = tid; i < 3 * Nn; i += nt) sm.y0[i] = Yio[i];
+    __syncthreads();
+    for (int j = tid; j < Nn; j += nt) sm.node4[j] = make_double4(sm.y0[3 * j], sm.y0[3 * j + 1], sm.y0[3 * j + 2], 0.0);
+    if (tid == 0) {
+        double cur = 0.0;
+        sm.s[0] = 0.0;
+        for (int i = 0; i < Nn - 1; i++) {
+            cur += sqrt(dist2(sm.y0[3 * i + 3], sm.y0[3 * i + 4], sm.y0[3 * i + 5], sm.y0[3 * i], sm.y0[3 * i + 1], sm.y0[3 * i + 2]));
+            sm.s[i + 1] = cur;
+        }
+    }
+    __syncthreads();
+
+    // ---- prune + compaction of this CTA's slice (trackdlo.cpp:177-195)
+    const long long per = (m0 + C - 1) / C;
+    long long r0 = per * rank, r1 = r0 + per;
+    if (r0 > m0) r0 = m0;
+    if (r1 > m0) r1 = m0;
+    double sum_local;
+    const int n_local = prune_slice(sm, Xraw, r0, r1, Xc, Nn, p.prune_radius, &sum_local);
+    if (tid == 0) { __stcg(gGATH + 2 * rank, (double)n_local); __stcg(gGATH + 2 * rank + 1, sum_local); }
+    const double* Xloc = Xc + r0 * 3;
+
+    // ---- rank 0: G, LLE products, priors (trackdlo.cpp:225-260)
+    if (rank == 0) {
+        const double beta = p.beta;
+        for (int idx = tid; idx < Nn * Nn; idx += nt) {
+            const int i = idx / Nn, j = idx - i * Nn;
+            const double dd = fabs(sm.s[i] - sm.s[j]);
+            gG[idx] = 1 / (2 * beta * 2 * beta) * exp(-sqrt(2.0) * dd / beta) * (2 * dd + sqrt(2.0) * beta);
+        }
+        for (int i = tid; i < Nn; i += nt) sm.jd[i] = 0.0;
+        for (int i = tid; i < 3 * Nn; i += nt) sm.yext[i] = sm.y0[i];
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < n_priors; k++) {
+                const int idx = (int)priors[k * 4];
+                if (idx < 0 || idx >= Nn) continue;
+                sm.jd[idx] = 1.0;
+                sm.yext[idx * 3] = priors[k * 4 + 1]; sm.yext[idx * 3 + 1] = priors[k * 4 + 2]; sm.yext[idx * 3 + 2] = priors[k * 4 + 3];
+            }
+        }
+        if (p.include_lle) {
+            if (Hext) {
+                for (int idx = tid; idx < Nn * Nn; idx += nt) { const int i = idx / Nn, j = idx - i * Nn; gH[idx] = Hext[(long long)i * hstride + j]; }
+            } else {
+                double* E = cscr + sc.AB;                              // dense E = I - L
+                for (int idx = tid; idx < Nn * Nn; idx += nt) E[idx] = 0.0;
+                __syncthreads();
+                for (int i = tid; i < Nn; i += nt) lle_row(sm.y0, Nn, i, E + (long long)i * Nn);
+                __syncthreads();
+                for (int idx = tid; idx < Nn * Nn; idx += nt) {        // H = E^T E, k ascending, band only
+                    const int r = idx / Nn, c = idx - r * Nn;
+                    double s = 0.0;
+                    int klo = (r > c ? r : c) - 3, khi = (r < c ? r : c) + 3;
+                    if (klo < 0) klo = 0;
+                    if (khi > Nn - 1) khi = Nn - 1;
+                    for (int k = klo; k <= khi; k++) s = __dadd_rn(s, __dmul_rn(E[(long long)k * Nn + r], E[(long long)k * Nn + c]));
+                    gH[idx] = s;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < Nn * Nn; idx += nt) {            // HG = H G
+                const int i = idx / Nn, j = idx - i * Nn;
+                double s = 0.0;
+                for (int k = 0; k < Nn; k++) s = fma(gH[(long long)i * Nn + k], gG[(long long)k * Nn + j], s);
+                gHG[idx] = s;
+            }
+            for (int idx = tid; idx < 3 * Nn; idx += nt) {             // H Y0
+                const int i = idx / 3, d = idx - 3 * i;
+                double s = 0.0;
+                for (int k = 0; k < Nn; k++) s = fma(gH[(long long)i * Nn + k], sm.y0[3 * k + d], s);
+                sm.hy0[idx] = s;
+            }
+        }
+        __syncthreads();
+    }
+
+    cluster.sync();                                                    // (S) gather prune results
+    long long Mp = 0;
+    double sumd2 = 0.0;
+    for (int r = 0; r < C; r++) { Mp += (long long)__ldcg(gGATH + 2 * r); sumd2 += __ldcg(gGATH + 2 * r + 1); }
+    if (Mp == 0) {
+        if (rank == 0 && tid == 0) { if (iters_out) *iters_out = 0; }
+        cluster.sync();
+        return ST_EMPTY;
+    }
+    double sigma2 = sigma2_in;
+    if (sigma2 == 0) sigma2 = sumd2 / (3.0 * (double)Nn * (double)Mp);   // trackdlo.cpp:271-273
+    const bool use_vis = (n_visible != Nn) && (n_visible > 0) && (p.k_vis != 0);   // trackdlo.cpp:358
+    const bool have_priors = n_priors > 0;
+
+    int status = 0, iters = 0;
+    for (int it = 0; it < p.max_iter; it++) {
+        iters = it + 1;
+        const double rscale = sqrt(0.5 / sigma2);
+        for (int j = tid; j < Nn; j += nt) sm.node4[j].w = sm.s[j] * rscale;
+        const double c_gauss = pow(2 * M_PI * sigma2, 1.5) * p.mu / (1 - p.mu);
+        double c_norm = c_gauss * (double)Nn / (double)Mp;             // trackdlo.cpp:300
+        __syncthreads();
+        if (use_vis) {
+            dmin_slice(sm, Xloc, n_local, Nn, gDMIN + rank * Nn);
+            cluster.sync();                                            // (V)
+            for (int j = tid; j < Nn; j += nt) {
+                double m = __ldcg(gDMIN + j);
+                for (int r = 1; r < C; r++) m = fmin(m, __ldcg(gDMIN + r * Nn + j));
+                double dm = sqrt(m);
+                if (dm <= p.tau) dm = 0.0;                              // trackdlo.cpp:291-293
+                sm.vw[j] = exp(-p.k_vis * dm);                          // trackdlo.cpp:365
+            }
+            __syncthreads();
+            if (tid == 0) { double t = 0.0; for (int j = 0; j < Nn; j++) t += sm.vw[j]; sm.red[40] = t; }
+            __syncthreads();
+            const double tot = sm.red[40];
+            for (int j = tid; j < Nn; j += nt) sm.vw[j] = sm.vw[j] / tot;   // trackdlo.cpp:372
+            c_norm = c_gauss / (double)Mp;                              // trackdlo.cpp:378
+            __syncthreads();
+            estep_slice<NPW, true>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+        } else {
+            estep_slice<NPW, false>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+        }
+        cluster.sync();                                                // (1) partial sums visible
+
+        if (rank == 0) {
+            // ---- gather partials in rank order
+            for (int i = tid; i < 4 * Nn; i += nt) {
+                double v = 0.0;
+                for (int r = 0; r < C; r++) v += __ldcg(gPART + r * (4 * Nn + 4) + i);
+                const int m = i >> 2, k = i & 3;
+                if (k == 0) sm.p1[m] = v; else sm.px[3 * m + k - 1] = v;
+            }
+            double sxx = 0.0;
+            for (int r = 0; r < C; r++) sxx += __ldcg(gPART + r * (4 * Nn + 4) + 4 * Nn);
+            __syncthreads();
+            // ---- assemble [A | B] (trackdlo.cpp:392-413)
+            const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
+            for (int idx = tid; idx < Nn * Nn; idx += nt) {
+                const int i = idx / Nn, j = idx - i * Nn;
+                const double g = gG[idx];
+                double v = sm.p1[i] * g + (i == j ? ls : 0.0);
+                if (p.include_lle) v += sg * gHG[idx];
+                if (have_priors) v += p.alpha * sm.jd[i] * g;
+                AB[(long long)i * ld + j] = v;
+            }
+            for (int idx = tid; idx < 3 * Nn; idx += nt) {
+                const int i = idx / 3, d = idx - 3 * i;
+                double v = sm.px[idx] - sm.p1[i] * sm.y0[idx];
+                if (p.include_lle) v -= sg * sm.hy0[idx];
+                if (have_priors) v += p.alpha * (sm.yext[idx] - sm.y0[idx]);
+                AB[(long long)i * ld + Nn + d] = v;
+            }
+            __syncthreads();
+            if (gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol)) status |= ST_SINGULAR;
+            // ---- T = Y0 + G W (trackdlo.cpp:417)
+            for (int i = warp; i < Nn; i += nw) {
+                double ax = 0.0, ay = 0.0, az = 0.0;
+                for (int k = lane; k < Nn; k += 32) {
+                    const double g = gG[(long long)i * Nn + k];
+                    ax = fma(g, sm.wsol[3 * k], ax); ay = fma(g, sm.wsol[3 * k + 1], ay); az = fma(g, sm.wsol[3 * k + 2], az);
+                }
+                ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+                if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
+            }
+            __syncthreads();
+            // ---- sigma2 update and convergence test (trackdlo.cpp:418-431)
+            if (warp == 0) {
+                double np = 0.0, trPXT = 0.0, trTPT = 0.0, moved = 0.0;
+                for (int m = lane; m < Nn; m += 32) {
+                    const double tx = sm.tnew[3 * m], ty = sm.tnew[3 * m + 1], tz = sm.tnew[3 * m + 2];
+                    const double p1 = sm.p1[m];
+                    np += p1;
+                    trPXT += sm.px[3 * m] * tx + sm.px[3 * m + 1] * ty + sm.px[3 * m + 2] * tz;
+                    trTPT += p1 * (tx * tx + ty * ty + tz * tz);
+                    const double4 yc = sm.node4[m];
+                    moved += sqrt(dist2(yc.x, yc.y, yc.z, tx, ty, tz));
+                }
+                np = warp_sum(np); trPXT = warp_sum(trPXT); trTPT = warp_sum(trTPT); moved = warp_sum(moved);
+                if (lane == 0) {
+                    const double s2new = (sxx - 2 * trPXT + trTPT) / (np * 3);
+                    const bool done = (moved / Nn) < p.tol;
+                    int fin = 0;
+                    if (done) fin = 1;
+                    else if (it == p.max_iter - 1) { fin = 1; status |= ST_NOT_CONVERGED; }
+                    __stcg(gSTATE + 3 * Nn, s2new);
+                    __stcg(gSTATE + 3 * Nn + 1, (double)fin);
+                    __stcg(gSTATE + 3 * Nn + 2, (double)status);
+                }
+            }
+            for (int i = tid; i < 3 * Nn; i += nt) __stcg(gSTATE + i, sm.tnew[i]);
+        }
+        cluster.sync();                                                // (2) new state visible
+        for (int j = tid; j < Nn; j += nt) {
+            const double s = sm.node4[j].w;
+            sm.node4[j] = make_double4(__ldcg(gSTATE + 3 * j), __ldcg(gSTATE + 3 * j + 1), __ldcg(gSTATE + 3 * j + 2), s);
+        }
+        sigma2 = __ldcg(gSTATE + 3 * Nn);
+        const int fin = (int)__ldcg(gSTATE + 3 * Nn + 1);
+        status = (int)__ldcg(gSTATE + 3 * Nn + 2);
+        __syncthreads();
+        if (fin) break;
+    }
+
+    // ---- results (rank 0)
+    if (rank == 0) {
+        for (int j = tid; j < Nn; j += nt) {
+            const double4 q = sm.node4[j];
+            Yio[3 * j] = q.x; Yio[3 * j + 1] = q.y; Yio[3 * j + 2] = q.z;
+        }
+        if (Wout && p.max_iter > 0) for (int i = tid; i < 3 * Nn; i += nt) Wout[i] = sm.wsol[i];
+        if (tid == 0) {
+            if (sigma2_out) *sigma2_out = sigma2;
+            if (iters_out) *iters_out = iters;
+        }
+    }
+    // make Yio visible to the whole cluster (tracking mode reads it back) and protect scratch reuse
+    __threadfence();
+    cluster.sync();
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------
+// The persistent kernel.
+// ------------------------------------------------------------------------------------------
+template <int NPW, int MINB>
+__global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int rank = (int)cluster.block_rank();
+    const int C = (int)cluster.num_blocks();
+    const int cluster_id = blockIdx.x / C;
+
+    const SmemL L = smem_layout(a.nmax, a.tile);
+    Smem sm;
+    sm.tab = reinterpret_cast<double*>(smem_raw + L.tab);
+    sm.node4 = reinterpret_cast<double4*>(smem_raw + L.node4);
+    sm.wbuf = reinterpret_cast<double4*>(smem_raw + L.wbuf);
+    sm.y0 = reinterpret_cast<double*>(smem_raw + L.y0);
+    sm.s = reinterpret_cast<double*>(smem_raw + L.s);
+    sm.vw = reinterpret_cast<double*>(smem_raw + L.vw);
+    sm.yext = reinterpret_cast<double*>(smem_raw + L.yext);
+    sm.jd = reinterpret_cast<double*>(smem_raw + L.jd);
+    sm.hy0 = reinterpret_cast<double*>(smem_raw + L.hy0);
+    sm.p1 = reinterpret_cast<double*>(smem_raw + L.p1);
+    sm.px = reinterpret_cast<double*>(smem_raw + L.px);
+    sm.wsol = reinterpret_cast<double*>(smem_raw + L.wsol);
+    sm.tnew = reinterpret_cast<double*>(smem_raw + L.tnew);
+    sm.pacc = reinterpret_cast<double*>(smem_raw + L.pacc);
+    sm.red = reinterpret_cast<double*>(smem_raw + L.red);
+    sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
+    sm.used = reinterpret_cast<int*>(smem_raw + L.used);
+    sm.ptile = reinterpret_cast<double*>(smem_raw + L.ptile);
+
+    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];
+    __syncthreads();
+
+    double* cscr = a.scratch + (long long)cluster_id * a.scratch_stride;
+    const Scr sc = scr_layout(a.scr_nodes);
+    int* ctl = reinterpret_cast<int*>(cscr + sc.CTL);
+
+    for (;;) {
+        if (rank == 0 && tid == 0) __stcg(ctl, atomicAdd(a.queue, 1));
+        cluster.sync();
+        const int f = __ldcg(ctl);
+        cluster.sync();
+        if (f >= a.n_frames) break;
+
+        const long long x0 = a.x_off[f], m0 = a.x_off[f + 1] - x0;
+        const double* Xraw = a.X + x0 * 3;
+        double* Xc = a.Xc + x0 * 3;
+
+        if (a.mode == 0) {
+            const int Nn = a.n_nodes ? a.n_nodes[f] : a.node_stride;
+            const long long ys = (long long)f * a.node_stride;
+            const int st = cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
+                                        a.priors ? a.priors + ys * 4 : nullptr,
+                                        (a.priors && a.n_priors) ? a.n_priors[f] : 0,
+                                        a.n_visible ? a.n_visible[f] : 0,
+                                        a.H ? a.H + ys * a.node_stride : nullptr, a.node_stride,
+                                        a.W ? a.W + ys * 3 : nullptr, a.iters ? a.iters + f : nullptr);
+            if (rank == 0 && tid == 0 && a.status) a.status[f] = st;
+        } else {
+            // ---------------- tracking_step (trackdlo.cpp:900-999)
+            const int Nn = a.node_stride;
+            double* Yf = a.Y + (long long)f * Nn * 3;
+            const int* vis = a.vis + a.vis_off[f];
+            const int nvis = (int)(a.vis_off[f + 1] - a.vis_off[f]);
+            const int* ext = a.ext + a.ext_off[f];
+            const int V = (int)(a.ext_off[f + 1] - a.ext_off[f]);
+            double* guide = a.guide_out ? a.guide_out + (long long)f * Nn * 3 : cscr + sc.GUIDE;
+            double* pri = a.priors_out ? a.priors_out + (long long)f * 2 * Nn * 4 : cscr + sc.PRI;
+            const double* geo = a.rest + (long long)f * Nn;
+            int st = 0;
+            // guide nodes (trackdlo.cpp:913-921)
+            if (rank == 0) {
+                for (int i = tid; i < 3 * V; i += nt) {
+                    const int r = i / 3, d = i - 3 * r;
+                    guide[i] = (V != Nn) ? Yf[ext[r] * 3 + d] : Yf[i];
+                }
+                __threadfence();
+            }
+            cluster.sync();
+            // pre-processing registration (trackdlo.cpp:925-927); sigma2 copy is discarded
+            const int st_pre = cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
+                                            nullptr, 0, 0, a.H ? a.H + (long long)f * Nn * Nn : nullptr, Nn,
+                                            nullptr, a.iters ? a.iters + 2 * f : nullptr);
+            if (st_pre & ST_NOT_CONVERGED) st |= ST_PRE_NOT_CONVERGED;
+            st |= st_pre & ~ST_NOT_CONVERGED;
+            int* ictl = ctl + 2;
+            if (rank == 0 && tid == 0) {
+                int err = 0, state = 0, np = 0;
+                double* trv = cscr + sc.TRV;
+                if (st_pre & (ST_TOO_FEW_NODES | ST_EMPTY)) {
+                    state = -1;
+                } else if (V == Nn) {
+                    state = 0;
+                    double* v1 = trv;
+                    double* v2 = trv + (Nn + 2) * 4;
+                    const int n1 = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, v1, &err);
+                    const int n2 = traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, v2, &err);
+                    // v2 is emitted tail -> head; the reference reverses it (trackdlo.cpp:942): v2r[j] = v2[n2-1-j]
+                    for (int i = 0; i < Nn; i++) {
+                        const int j2 = i - (Nn - n2);
+                        const double* first2 = v2 + (n2 - 1) * 4;
+                        if (i < first2[0] && i < n1) { for (int t = 0; t < 4; t++) pri[np * 4 + t] = v1[i * 4 + t]; np++; }
+                        else if (i > v1[(n1 - 1) * 4] && j2 >= 0 && j2 < n2) {
+                            const double* s2 = v2 + (n2 - 1 - j2) * 4;
+                            for (int t = 0; t < 4; t++) pri[np * 4 + t] = s2[t];
+                            np++;
+                        } else if (i < n1 && j2 >= 0 && j2 < n2) {
+                            const double* s2 = v2 + (n2 - 1 - j2) * 4;
+                            for (int t = 0; t < 4; t++) pri[np * 4 + t] = (v1[i * 4 + t] + s2[t]) / 2.0;
+                            np++;
+                        } else err |= 4;
+                    }
+                } else if (ext[0] == 0 && ext[V - 1] == Nn - 1) {
+                    state = 1;
+                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, pri, &err);
+                    np += traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, pri + np * 4, &err);
+                } else if (ext[0] == 0) {
+                    state = 2;
+                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, pri, &err);
+                } else if (ext[V - 1] == Nn - 1) {
+                    state = 3;
+                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, pri, &err);
+                } else {
+                    state = 4;
+                    int align = -1;
+                    double moved = 999999;
+                    for (int i = 0; i < nvis; i++) {
+                        if (i >= V) { err |= 8; break; }
+                        const double dd = vdist(ld3(Yf, vis[i]), ld3(guide, i));
+                        if (dd < moved) { moved = dd; align = i; }
+                    }
+                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 2, align, pri, &err);
+                }
+                if (a.state_out) a.state_out[f] = state;
+                if (a.n_priors_out) a.n_priors_out[f] = np;
+                __stcg(ictl, np);
+                __stcg(ictl + 1, err);
+                __threadfence();
+            }
+            cluster.sync();
+            const int np = __ldcg(ictl);
+            if (__ldcg(ictl + 1)) st |= ST_TRAVERSE_UB;
+            if (!(st & (ST_TOO_FEW_NODES | ST_EMPTY))) {
+                // main registration (trackdlo.cpp:998)
+                st |= cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
+                                   pri, np, V, nullptr, Nn, a.W ? a.W + (long long)f * Nn * 3 : nullptr,
+                                   a.iters ? a.iters + 2 * f + 1 : nullptr);
+            }
+            if (rank == 0 && tid == 0 && a.status) a.status[f] = st;
+        }
+    }
+}
+
+}  // namespace tdlo
