@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed goldens (tests/golden, minted by scripts/make_golden.py).
+
+Tolerances: BASELINE.json north_star asks for <= 1e-5 relative on W and node positions; the fp64
+CUDA path is held to 1e-7 on the include_lle=false path and on tracking_step (LLE weights are
+bit-mirrored between oracle and device, but everything downstream of them is still chaotic
+amplification) -- both far inside the gate.  Integer outputs (iteration counts,
+states, status, prior indices) must match exactly.
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from trackdlo_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+GATE = 1e-5          # north_star tolerance
+TIGHT = 1e-7         # what we actually hold the fp64 path to
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(max_frames=64, max_nodes=64, max_points_total=64 * 20000 + 1000)
+    yield c
+    c.close()
+
+
+def _params_pair(arr):
+    kw = dict(beta=arr[0], lambda_=arr[1], lle_weight=arr[2], mu=arr[3], tol=arr[4], alpha=arr[5], k_vis=arr[6],
+              visibility_threshold=arr[7], max_iter=int(arr[8]), include_lle=bool(arr[9]))
+    return oracle.CpdParams(**kw), api.CpdParams(**kw)
+
+
+def _batch(frames):
+    F = len(frames)
+    xo = np.zeros(F + 1, np.int64); xo[1:] = np.cumsum([f["X"].shape[0] for f in frames])
+    return np.concatenate([f["X"] for f in frames]), xo, np.stack([f["Y"] for f in frames])
+
+
+@pytest.mark.parametrize("name", ["c1_fixed20", "c1_converge", "c1_lle_preproc", "occl_vis_priors", "n64_sigma_given"])
+@pytest.mark.parametrize("cluster", [0, 1, 4])
+def test_cpd_against_golden(ctx, golden_dir, name, cluster):
+    g = np.load(os.path.join(golden_dir, f"cpd_{name}.npz"))
+    _, pg = _params_pair(g["params"])
+    X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
+    pri = npr = nv = None
+    if len(g["priors"]):
+        pri = np.zeros((1, Nn, 4)); pri[0, :len(g["priors"])] = g["priors"]; npr = np.array([len(g["priors"])], np.int32)
+    if int(g["n_visible"]) >= 0:
+        nv = np.array([int(g["n_visible"])], np.int32)
+    ctx.set_cluster_size(cluster)
+    r = ctx.cpd_lle_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.array([float(g["sigma2_in"])]), pg,
+                            priors=pri, n_priors=npr, n_visible=nv)
+    ctx.set_cluster_size(0)
+    assert r["iters"][0] == int(g["iters"])
+    assert bool(r["status"][0] & api.ST_NOT_CONVERGED) == (not bool(g["converged"]))
+    assert r["status"][0] & ~api.ST_NOT_CONVERGED == 0
+    tol = TIGHT if not pg.include_lle else 1e-6
+    assert rel(r["Y"][0], g["Y"]) < tol < GATE
+    assert rel(r["W"][0], g["W"]) < tol * 10 < GATE
+    assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < tol * 10
+
+
+@pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
+def test_tracking_step_against_golden(ctx, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
+    vis, ext = g["vis"].astype(np.int32), g["vis_ext"].astype(np.int32)
+    r = ctx.tracking_step_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.zeros(1), g["rest"][None],
+                                  vis, np.array([0, len(vis)], np.int64), ext, np.array([0, len(ext)], np.int64),
+                                  api.TrackParams())
+    assert r["state"][0] == int(g["state"])
+    assert list(r["iters"][0]) == list(g["iters"])
+    assert r["status"][0] == 0 and int(g["err"]) == 0
+    npri = len(g["priors"])
+    assert r["n_priors"][0] == npri
+    assert np.array_equal(r["priors"][0, :npri, 0], g["priors"][:, 0])           # node indices: exact
+    assert rel(r["priors"][0, :npri, 1:], g["priors"][:, 1:]) < 1e-6
+    assert rel(r["guide"][0, :len(ext)], g["guide"]) < 1e-6
+    assert rel(r["Y"][0], g["Y"]) < 1e-6 < GATE
+    assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
+
+
+def test_ragged_batch_matches_per_frame_oracle(ctx):
+    """Frames of different point counts AND node counts in one call; results must equal the oracle run
+    frame by frame (frames are independent problems)."""
+    specs = [(30, 2000, 0.0), (50, 5000, 0.4), (40, 700, 0.0), (50, 3000, 0.2), (12, 300, 0.0)]
+    frames = [synth.make_frame(10 + i, n_nodes=n, n_points=m, occlusion=p) for i, (n, m, p) in enumerate(specs)]
+    F, S = len(frames), 50
+    xo = np.zeros(F + 1, np.int64); xo[1:] = np.cumsum([f["X"].shape[0] for f in frames])
+    X = np.concatenate([f["X"] for f in frames])
+    Y = np.zeros((F, S, 3)); nn = np.zeros(F, np.int32)
+    for i, f in enumerate(frames):
+        Y[i, :f["Y"].shape[0]] = f["Y"]; nn[i] = f["Y"].shape[0]
+    po, pg = oracle.CpdParams(max_iter=30), api.CpdParams(max_iter=30)
+    r = ctx.cpd_lle_batched(X, xo, Y, np.zeros(F), pg, n_nodes=nn)
+    for i, f in enumerate(frames):
+        o = oracle.cpd_lle(f["X"], f["Y"], 0.0, po)
+        n = nn[i]
+        assert r["iters"][i] == o["iters"], i
+        assert bool(r["status"][i] & 1) == (not o["converged"])
+        assert rel(r["Y"][i, :n], o["Y"]) < TIGHT
+        assert rel(r["W"][i, :n], o["W"]) < TIGHT * 10
+        assert np.array_equal(r["Y"][i, n:], Y[i, n:])           # padding rows untouched
+
+
+def test_edge_cases_status_words(ctx):
+    f = synth.make_frame(0, n_nodes=30, n_points=500)
+    far = f["X"] + 10.0                                          # every point pruned
+    X = np.concatenate([f["X"], far, f["X"][:0], f["X"]])
+    xo = np.array([0, 500, 1000, 1000, 1500], np.int64)          # frame 2 is empty
+    Y = np.stack([f["Y"]] * 4)
+    nn = np.array([30, 30, 30, 3], np.int32)                     # frame 3 has too few nodes
+    r = ctx.cpd_lle_batched(X, xo, Y, np.zeros(4), api.CpdParams(max_iter=5, tol=0.0), n_nodes=nn)
+    assert r["status"][0] == api.ST_NOT_CONVERGED and r["iters"][0] == 5
+    assert r["status"][1] == api.ST_EMPTY_CLOUD and r["iters"][1] == 0
+    assert r["status"][2] == api.ST_EMPTY_CLOUD
+    assert r["status"][3] == api.ST_TOO_FEW_NODES
+    assert np.array_equal(r["Y"][1], f["Y"]) and np.array_equal(r["Y"][2], f["Y"])
+    # max_iter = 0: Y untouched, sigma2 initialised (trackdlo.cpp:197,271-275,440)
+    r0 = ctx.cpd_lle_batched(f["X"], np.array([0, 500], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=0))
+    o0 = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(max_iter=0))
+    assert r0["status"][0] == 0 and r0["iters"][0] == 0 and np.array_equal(r0["Y"][0], f["Y"])
+    assert abs(r0["sigma2"][0] - o0["sigma2"]) / o0["sigma2"] < 1e-12
+
+
+def test_end_quirk_and_far_points_match_oracle(ctx):
+    Y = np.array([[0.0, 0, 0], [0.03, 0.03, 0], [0.001, 0.004, 0], [0.0, 0.06, 0], [0.0, 0.09, 0], [0.0, 0.12, 0]])
+    rng = np.random.default_rng(5)
+    X = np.concatenate([rng.normal(0, 0.004, (200, 3)) + Y[rng.integers(0, 6, 200)],
+                        np.array([[0.0, -0.001, 0.0], [0.0, 0.0, 0.0995], [0.09, 0.0, 0.0]])])
+    for s2 in (0.0, 1e-4, 1e-7):
+        po, pg = oracle.CpdParams(max_iter=3, tol=0.0), api.CpdParams(max_iter=3, tol=0.0)
+        o = oracle.cpd_lle(X, Y, s2, po)
+        r = ctx.cpd_lle_batched(X, np.array([0, len(X)], np.int64), Y[None], np.array([s2]), pg)
+        assert rel(r["Y"][0], o["Y"]) < 1e-6, s2
+        assert abs(r["sigma2"][0] - o["sigma2"]) / o["sigma2"] < 1e-6
+
+
+def test_supplied_H_overrides_device_lle(ctx):
+    f = synth.make_frame(2, n_nodes=30, n_points=2000)
+    H = oracle.lle_H(f["Y"])
+    po = oracle.CpdParams(beta=3.0, lambda_=1.0, include_lle=True, max_iter=15, tol=0.0)
+    pg = api.CpdParams(beta=3.0, lambda_=1.0, include_lle=True, max_iter=15, tol=0.0)
+    o = oracle.cpd_lle(f["X"], f["Y"], 0.0, po, H=H)
+    r = ctx.cpd_lle_batched(f["X"], np.array([0, 2000], np.int64), f["Y"][None], np.zeros(1), pg, H=H[None])
+    assert rel(r["Y"][0], o["Y"]) < TIGHT
+    r2 = ctx.cpd_lle_batched(f["X"], np.array([0, 2000], np.int64), f["Y"][None], np.zeros(1), pg)   # device LLE
+    o2 = oracle.cpd_lle(f["X"], f["Y"], 0.0, po)
+    assert rel(r2["Y"][0], o2["Y"]) < 1e-6
+
+
+def test_full_size_c2_frame_and_invariances(ctx):
+    """BASELINE configs[1] size (Nn=50, Mp=20000, 50 fixed iterations): one frame against the oracle, plus
+    size-independent properties on a batch: batch-order independence (bit-exact), point-permutation
+    invariance and rigid-translation equivariance (to rounding)."""
+    frames = [synth.make_frame(i, n_nodes=50, n_points=20000) for i in range(4)]
+    X, xo, Y = _batch(frames)
+    pg = api.CpdParams(max_iter=50, tol=0.0)
+    r = ctx.cpd_lle_batched(X, xo, Y, np.zeros(4), pg)
+    o = oracle.cpd_lle(frames[0]["X"], frames[0]["Y"], 0.0, oracle.CpdParams(max_iter=50, tol=0.0))
+    assert r["iters"][0] == 50
+    assert rel(r["Y"][0], o["Y"]) < TIGHT and rel(r["W"][0], o["W"]) < TIGHT * 10
+    # batch order
+    rev = frames[::-1]
+    Xr, xor_, Yr = _batch(rev)
+    rr = ctx.cpd_lle_batched(Xr, xor_, Yr, np.zeros(4), pg)
+    assert np.array_equal(rr["Y"][::-1], r["Y"]) and np.array_equal(rr["sigma2"][::-1], r["sigma2"])
+    # permutation of the points of frame 1
+    perm = np.random.default_rng(0).permutation(20000)
+    f1 = dict(frames[1]); f1["X"] = frames[1]["X"][perm]
+    Xp, xop, Yp = _batch([f1])
+    rp = ctx.cpd_lle_batched(Xp, xop, Yp, np.zeros(1), pg)
+    assert rel(rp["Y"][0], r["Y"][1]) < 1e-9
+    # translation by t: result translates by t, W unchanged
+    t = np.array([0.125, -0.25, 0.0625])
+    f2 = dict(frames[2]); f2["X"] = frames[2]["X"] + t; f2["Y"] = frames[2]["Y"] + t
+    Xt, xot, Yt = _batch([f2])
+    rt = ctx.cpd_lle_batched(Xt, xot, Yt, np.zeros(1), pg)
+    assert rel(rt["Y"][0] - t, r["Y"][2]) < 1e-8
+    assert rel(rt["W"][0], r["W"][2]) < 1e-5
+
+
+def test_device_pointer_entry_matches_host_entry(ctx):
+    import torch
+    frames = [synth.make_frame(20 + i, n_nodes=50, n_points=3000) for i in range(3)]
+    X, xo, Y = _batch(frames)
+    pg = api.CpdParams(max_iter=12, tol=0.0)
+    host = ctx.cpd_lle_batched(X, xo, Y, np.zeros(3), pg)
+    dev = torch.device("cuda:0")
+    dX = torch.from_numpy(X).to(dev); dxo = torch.from_numpy(xo).to(dev); dY = torch.from_numpy(Y.copy()).to(dev)
+    ds2 = torch.zeros(3, dtype=torch.float64, device=dev); dW = torch.zeros(3, 50, 3, dtype=torch.float64, device=dev)
+    dit = torch.zeros(3, dtype=torch.int32, device=dev); dst = torch.zeros(3, dtype=torch.int32, device=dev)
+    b = api.CpdBatchC(3, 50, dX.data_ptr(), dxo.data_ptr(), None, dY.data_ptr(), ds2.data_ptr(), None, None, None, None,
+                      dW.data_ptr(), dit.data_ptr(), dst.data_ptr())
+    stream = torch.cuda.current_stream()
+    ctx.cpd_lle_batched_raw(b, pg.to_c(), device=True, stream=stream.cuda_stream)
+    stream.synchronize()
+    assert np.array_equal(dY.cpu().numpy(), host["Y"]) and np.array_equal(ds2.cpu().numpy(), host["sigma2"])
+    assert np.array_equal(dit.cpu().numpy(), host["iters"])
+
+
+def test_bad_arguments_are_rejected(ctx):
+    f = synth.make_frame(0, n_nodes=30, n_points=100)
+    with pytest.raises(api.TdloError):
+        ctx.cpd_lle_batched(f["X"], np.array([0, 100], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(mu=0.0))
+    with pytest.raises(api.TdloError):
+        ctx.cpd_lle_batched(f["X"], np.array([5, 100], np.int64), f["Y"][None], np.zeros(1), api.CpdParams())
+    with pytest.raises(api.TdloError):
+        big = np.zeros((200, 100, 3))
+        ctx.cpd_lle_batched(f["X"], np.zeros(201, np.int64), big, np.zeros(200), api.CpdParams())
+
+
+def test_larger_node_counts(ctx):
+    """Nn = 100 and 200 take the other kernel variants (16 nodes/warp, global-memory solve workspace)."""
+    c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)
+    try:
+        for Nn, Mp in ((100, 6000), (200, 8000)):
+            f = synth.make_frame(1, n_nodes=Nn, n_points=Mp)
+            o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(max_iter=8, tol=0.0))
+            r = c.cpd_lle_batched(f["X"], np.array([0, Mp], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=8, tol=0.0))
+            assert r["iters"][0] == 8
+            assert rel(r["Y"][0], o["Y"]) < 1e-6 and rel(r["W"][0], o["W"]) < GATE
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("name", ["track_c1", "track_occl_mid"])
+def test_adapter_class_matches_golden(golden_dir, name):
+    """The Eigen-facing drop-in `class trackdlo` (include/trackdlo_adapter.hpp), compiled against the
+    MatrixXd stand-in and linked to the C-ABI library, reproduces the golden tracking_step."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    tp = api.TrackParams()
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "adapter_run")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                               os.path.join(ROOT, "tests", "cpp", "adapter_run.cpp"), "-o", exe,
+                               "-L", os.path.join(ROOT, "trackdlo_b200"), "-ltrackdlo_b200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "trackdlo_b200")])
+        X = g["X"].astype(np.float64); Y = g["Y_in"]; Nn = Y.shape[0]
+        vis, ext = g["vis"].astype(np.int32), g["vis_ext"].astype(np.int32)
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as fh:
+            np.array([Nn, len(X), len(vis), len(ext)], np.int64).tofile(fh)
+            np.array([tp.visibility_threshold, tp.beta, tp.lambda_, tp.alpha, tp.k_vis, tp.mu, tp.max_iter, tp.tol,
+                      tp.beta_pre_proc, tp.lambda_pre_proc, tp.lle_weight, 0.0], np.float64).tofile(fh)
+            Y.astype(np.float64).tofile(fh); g["rest"].astype(np.float64).tofile(fh); X.tofile(fh)
+            vis.tofile(fh); ext.tofile(fh)
+        rc = subprocess.call([exe, fin, fout])
+        assert rc == 0
+        out = np.fromfile(fout, np.float64)
+    Yo = out[:Nn * 3].reshape(Nn, 3); s2 = out[Nn * 3]
+    guide = out[Nn * 3 + 1: Nn * 3 + 1 + len(ext) * 3].reshape(-1, 3)
+    npri = int(out[Nn * 3 + 1 + len(ext) * 3])
+    pri = out[Nn * 3 + 2 + len(ext) * 3:].reshape(-1, 4)
+    assert npri == len(g["priors"]) == len(pri)
+    assert rel(Yo, g["Y"]) < 1e-6 and rel(guide, g["guide"]) < 1e-6 and rel(pri, g["priors"]) < 1e-6
+    assert abs(s2 - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
