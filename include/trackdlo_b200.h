@@ -144,6 +144,11 @@ int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* bat
  * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */
 int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]);
 
+/* Development aid: enables/disables the kernel's per-phase cycle counters and returns + resets the
+ * totals accumulated since the previous call.  cycles[0..5] (cluster rank 0) = {set-up, visibility
+ * pre-pass, E-step, wait, M-step, wait}; cycles[8..13] = the same for the other ranks.  Synchronises. */
+int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
+
 /* Overrides the automatic cluster-size choice (0 = automatic; 1,2,4,8,16). */
 int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t cluster_size);
 

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "tdlo_create", "tdlo_destroy", "tdlo_last_error", "tdlo_version",
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
-    "tdlo_last_launch_info", "tdlo_set_cluster_size",
+    "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library():
         lib.tdlo_tracking_step_batched_device.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC), C.c_void_p]
         lib.tdlo_last_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
+        lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         _lib = lib
     return _lib
 
@@ -163,6 +164,14 @@ class Context:
 
     def set_cluster_size(self, c):
         self._check(self.lib.tdlo_set_cluster_size(self.h, c), "tdlo_set_cluster_size")
+
+    def profile_phases(self, enable=True):
+        """Returns and resets the kernel's phase cycle counters; see tdlo_profile_phases."""
+        cyc = (C.c_uint64 * 16)()
+        self._check(self.lib.tdlo_profile_phases(self.h, int(enable), cyc), "tdlo_profile_phases")
+        names = ("setup", "dmin", "estep", "wait1", "assemble", "wait2", "solve", "update")
+        v = list(cyc)
+        return {"rank0": dict(zip(names, v[:8])), "others": dict(zip(names, v[8:16]))}
 
     def launch_info(self):
         info = (C.c_int32 * 8)()

@@ -31,6 +31,8 @@ struct tdlo_ctx {
     long long scratch_stride = 0;
     int scratch_clusters = 0;
     int* d_queue = nullptr;
+    unsigned long long* d_prof = nullptr;   // phase cycle counters (enabled by tdlo_profile_phases)
+    unsigned long long* d_prof_buf = nullptr;
     int cluster_override = 0;
     long long points_hint = 0;      // points per frame of the current host call (0 = unknown)
     int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -67,7 +69,7 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
     void* ptrs[] = {ctx->d_X, ctx->d_Y, ctx->d_sigma2, ctx->d_priors, ctx->d_H, ctx->d_W, ctx->d_rest, ctx->d_guide,
                     ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
-                    ctx->d_Xc, ctx->d_scratch, ctx->d_queue};
+                    ctx->d_Xc, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -137,6 +139,7 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(dalloc(&ctx->d_state, F));
     CKC(dalloc(&ctx->d_scratch, (size_t)ctx->scratch_stride * ctx->scratch_clusters));
     CKC(dalloc(&ctx->d_queue, 1));
+    CKC(dalloc(&ctx->d_prof_buf, 16));
     // exp table 2^(j/64)
     double tab[64];
     for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
@@ -174,20 +177,17 @@ static int pick_tile(int nmax, int budget) {
 static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points_per_frame_hint) {
     CK(cudaSetDevice(ctx->device));
     const int nmax = a.nmax;
-    // ---- kernel variant + tile
+    // ---- kernel variant + tile: <224,2> two CTAs/SM (Nn <= ~50), <256,1> one CTA/SM, <0,1> generic (runtime tile)
     const int budget2 = 113 * 1024, budget1 = 227 * 1024;
     kern_t kern;
-    int tile, occ, npw;
-    const int t2 = pick_tile(nmax, budget2);
-    if (nmax <= 64 && t2 >= 192 && (t2 / 32) * 8 >= nmax) { kern = tdlo_em_kernel<8, 2>; tile = t2; occ = 2; npw = 8; }
+    int tile, occ;
+    if (smem_layout(nmax, 224).total <= budget2 && nmax <= 224) { kern = tdlo_em_kernel<224, 2>; tile = 224; occ = 2; }
+    else if (smem_layout(nmax, 256).total <= budget1) { kern = tdlo_em_kernel<256, 1>; tile = 256; occ = 1; }
     else {
+        kern = tdlo_em_kernel<0, 1>; occ = 1;
         tile = pick_tile(nmax, budget1);
-        occ = 1;
         if (tile < 32) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
-        if ((tile / 32) * 8 >= nmax) { kern = tdlo_em_kernel<8, 1>; npw = 8; }
-        else { kern = tdlo_em_kernel<16, 1>; npw = 16; }
     }
-    (void)npw;
     const int smem = smem_layout(nmax, tile).total;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -225,11 +225,13 @@ static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points
     if (n_clusters < 1) n_clusters = 1;
     cfg.gridDim = dim3(n_clusters * C, 1, 1);
     a.tile = tile;
+    a.L = smem_layout(nmax, tile);
     a.Xc = ctx->d_Xc;
     a.scratch = ctx->d_scratch;
     a.scratch_stride = ctx->scratch_stride;
     a.queue = ctx->d_queue;
     a.scr_nodes = ctx->max_nodes;
+    a.prof = ctx->d_prof;
     CK(cudaMemsetAsync(ctx->d_queue, 0, sizeof(int), stream));
     CK(cudaLaunchKernelEx(&cfg, kern, a));
     ctx->info[0] = C; ctx->info[1] = n_clusters * C; ctx->info[2] = tile; ctx->info[3] = smem; ctx->info[4] = tile;
@@ -418,5 +420,20 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
     if (b->state) D2H(b->state, ctx->d_state, F * sizeof(int));
     CK(cudaStreamSynchronize(ctx->stream));
+    return TDLO_OK;
+}
+
+// Development aid: enable (and read back / reset) the per-phase cycle counters of the kernel.
+// cycles[0..7]: cluster rank 0 {setup, dmin pre-pass, E-step, wait, M-step, wait}; [8..15]: other ranks.
+extern "C" int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if (cycles) {
+        if (ctx->d_prof) CK(cudaMemcpy(cycles, ctx->d_prof_buf, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        else memset(cycles, 0, 16 * sizeof(uint64_t));
+    }
+    CK(cudaMemset(ctx->d_prof_buf, 0, 16 * sizeof(uint64_t)));
+    ctx->d_prof = enable ? ctx->d_prof_buf : nullptr;
     return TDLO_OK;
 }

@@ -34,6 +34,39 @@ struct CpdP {
     int max_iter, include_lle;
 };
 
+// ------------------------------------------------------------------------------------------
+// shared memory layout (bytes)
+// ------------------------------------------------------------------------------------------
+struct SmemL {
+    int tab, node4, wbuf, y0, s, vw, yext, jd, hy0, p1, px, wsol, tnew, pacc, red, gjbuf, prow, used, ptile, total;
+};
+__host__ __device__ inline SmemL smem_layout(int N, int tile) {
+    SmemL l;
+    int o = 0;
+    l.tab = o; o += 64 * 8;
+    l.node4 = o; o += N * 32;
+    l.wbuf = o; o += tile * 32;
+    l.y0 = o; o += 3 * N * 8;
+    l.s = o; o += N * 8;
+    l.vw = o; o += N * 8;
+    l.yext = o; o += 3 * N * 8;
+    l.jd = o; o += N * 8;
+    l.hy0 = o; o += 3 * N * 8;
+    l.p1 = o; o += N * 8;
+    l.px = o; o += 3 * N * 8;
+    l.wsol = o; o += 3 * N * 8;
+    l.tnew = o; o += 3 * N * 8;
+    l.pacc = o; o += 4 * N * 8;
+    l.red = o; o += 64 * 8;
+    l.gjbuf = o; o += 132 * 8;
+    l.prow = o; o += N * 4;
+    l.used = o; o += N * 4;
+    o = (o + 31) & ~31;
+    l.ptile = o; o += N * (tile + 1) * 8;
+    l.total = o;
+    return l;
+}
+
 struct KArgs {
     int mode;            // 0 = batched cpd_lle, 1 = batched tracking_step
     int n_frames;
@@ -60,6 +93,8 @@ struct KArgs {
     long long scratch_stride;   // doubles per cluster
     int* queue;          // frame queue counter
     int scr_nodes;       // node capacity the scratch layout was sized for
+    unsigned long long* prof;   // optional [16] phase cycle counters (rank 0: 0..7, other ranks: 8..15)
+    SmemL L;             // shared-memory layout, computed by the host (keeps address arithmetic out of the kernel)
 };
 
 __constant__ double c_exp_tab[64];   // 2^(j/64), filled by the host
@@ -89,41 +124,9 @@ __host__ __device__ inline Scr scr_layout(int N) {
     return s;
 }
 
-// ------------------------------------------------------------------------------------------
-// shared memory layout (bytes)
-// ------------------------------------------------------------------------------------------
-struct SmemL {
-    int tab, node4, wbuf, y0, s, vw, yext, jd, hy0, p1, px, wsol, tnew, pacc, red, prow, used, ptile, total;
-};
-__host__ __device__ inline SmemL smem_layout(int N, int tile) {
-    SmemL l;
-    int o = 0;
-    l.tab = o; o += 64 * 8;
-    l.node4 = o; o += N * 32;
-    l.wbuf = o; o += tile * 32;
-    l.y0 = o; o += 3 * N * 8;
-    l.s = o; o += N * 8;
-    l.vw = o; o += N * 8;
-    l.yext = o; o += 3 * N * 8;
-    l.jd = o; o += N * 8;
-    l.hy0 = o; o += 3 * N * 8;
-    l.p1 = o; o += N * 8;
-    l.px = o; o += 3 * N * 8;
-    l.wsol = o; o += 3 * N * 8;
-    l.tnew = o; o += 3 * N * 8;
-    l.pacc = o; o += 4 * N * 8;
-    l.red = o; o += 64 * 8;
-    l.prow = o; o += N * 4;
-    l.used = o; o += N * 4;
-    o = (o + 31) & ~31;
-    l.ptile = o; o += N * tile * 8;
-    l.total = o;
-    return l;
-}
-
 struct Smem {
     double* tab; double4* node4; double4* wbuf;
-    double *y0, *s, *vw, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *pacc, *red;
+    double *y0, *s, *vw, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *pacc, *red, *gjbuf;
     int *prow, *used;
     double* ptile;
 };
@@ -149,29 +152,28 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
-// exp(-z) for z >= 0, fp64, ~1 ulp: 64-entry table + degree-5 polynomial.
-// Results below 2.4e-307 flush to zero (the reference keeps denormals down to 4.9e-324; those
-// terms are > 290 orders of magnitude below the outlier constant c they are added to).
+// exp(-z) for z >= 0, fp64: 64-entry table 2^(j/64) + degree-5 polynomial, relative error
+// <= 3e-16 + |z| * 5e-17 (the ln2/64 reduction constant is a single double).
+// z is clamped to [0, ~706]: entries that the reference would compute as < 2.4e-307 (down to
+// denormals / exact 0) come out as ~2.4e-307 here -- 290 orders of magnitude below the outlier
+// constant c they are added to, i.e. no effect on any result bit that survives the division.
 __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ tab) {
     const double L = 92.33248261689366;           // 64 / ln 2
-    const double C_HI = 0.010830424696249145;     // ln 2 / 64 (hi)
-    const double C_LO = 3.623510646634843e-19;    // ln 2 / 64 (lo)
+    const double C_HI = 0.010830424696249145;     // ln 2 / 64
     const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52
-    double t = fma(z, -L, MAGIC);
+    z = __hiloint2double(min(__double2hiint(z), 0x40861000), __double2loint(z));   // NaN also lands here
+    const double t = fma(z, -L, MAGIC);
     const int n = __double2loint(t);
     const double nf = t - MAGIC;
-    double r = fma(nf, -C_HI, -z);
-    r = fma(nf, -C_LO, r);
+    const double r = fma(nf, -C_HI, -z);
     const double tj = tab[n & 63];
-    const int k = n >> 6;
     const double r2 = r * r;
     double q = fma(r, 8.3333333333333332e-3, 4.1666666666666664e-2);
     q = fma(q, r, 1.6666666666666666e-1);
     q = fma(q, r, 0.5);
     const double p = fma(q, r2, r);
-    double e = fma(tj, p, tj);
-    e = __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
-    return (__double2hiint(z) >= 0x40861000) ? 0.0 : e;     // z >= 706 (or NaN) -> 0
+    const double e = fma(tj, p, tj);
+    return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
 }
 
 __device__ __forceinline__ double dist2(double ax, double ay, double az, double bx, double by, double bz) {
@@ -262,27 +264,33 @@ __device__ void dmin_slice(const Smem& sm, const double* __restrict__ Xc, int n_
 // ------------------------------------------------------------------------------------------
 // Fused E-step over this CTA's slice (trackdlo.cpp:278-389): distances -> arg-max node ->
 // geodesic distances -> P -> (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.
-// Phase A is thread-per-point (P column into the shared-memory tile); phase B is
-// warp-per-node with lanes over the tile's points and register accumulators.
+// Phase A is thread-per-point: the point's P column goes into the shared-memory tile
+// ptile[node][point] (row stride TILE+1 doubles).  Phase B maps threads to (node m, slice q):
+// lanes of a warp hold consecutive nodes (conflict-free reads of the padded tile, broadcast reads
+// of the per-point weights) and keep the four sums of their node in registers across all tiles.
 // part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
+// TILE_CT != 0 fixes the tile size at compile time (immediate smem offsets in the hot loops).
 // ------------------------------------------------------------------------------------------
-template <int NPW, bool VIS>
-__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn,
+template <int TILE_CT, bool VIS>
+__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn, int tile_rt,
                             double sigma2, double c_norm, double rscale, double* part_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
-    const int per_group = nw * NPW;
-    const int ngroups = (Nn + per_group - 1) / per_group;
-    double acc[NPW][4];
-#pragma unroll
-    for (int i = 0; i < NPW; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0; }
-    if (ngroups > 1) {
-        for (int i = tid; i < 4 * Nn; i += tile) sm.pacc[i] = 0.0;
+    const int TILE = TILE_CT ? TILE_CT : tile_rt;
+    const int RS = TILE + 1;
+    const int tid = threadIdx.x;
+    const bool regacc = Nn <= TILE;
+    const int Q = regacc ? TILE / Nn : 1;
+    const int bq = tid / Nn, bm = tid - bq * Nn;
+    const bool actB = regacc && bq < Q;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (!regacc) {
+        for (int i = tid; i < 4 * Nn; i += TILE) sm.pacc[i] = 0.0;
     }
     double sxx = 0.0;
     const double* __restrict__ tab = sm.tab;
     double* __restrict__ pcol = sm.ptile + tid;
+    const double uflow = 1490.2 * sigma2;      // cheap pre-test: below this exp(-0.5*d2/sigma2) cannot underflow to 0
 
-    for (int base = 0; base < n_local; base += tile) {
+    for (int base = 0; base < n_local; base += TILE) {
         const int n = base + tid;
         const bool valid = n < n_local;
         double x = 0, y = 0, z = 0;
@@ -298,7 +306,7 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
             if (d2 < best) { best = d2; a = j; }
         }
         // whole column underflows to 0 in the reference -> maxCoeff returns index 0
-        if ((-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
+        if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
         int q1 = a - 1; if (q1 == -1) q1 = 2;
         int q2 = a + 1; if (q2 == Nn) q2 = Nn - 3;
         double da, d1, d2n;
@@ -316,15 +324,26 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
 
         // ---- P column (trackdlo.cpp:332-354, 358-375)
         double colsum = 0.0;
+        {
+            const double4* __restrict__ nd = sm.node4;
+            const double* __restrict__ vw = sm.vw;
+            double* __restrict__ pc = pcol;
 #pragma unroll 2
-        for (int j = 0; j < Nn; j++) {
-            const double sj = sm.node4[j].w;
-            double t = (j <= lo) ? (alo - sj) : (ahi + sj);
-            if (j > lo && j < hi) t = 0.0;               // rows between lo and hi stay 0 (end quirk)
-            double p = exp_neg(t * t, tab);
-            if (VIS) p *= sm.vw[j];
-            colsum += p;
-            pcol[j * tile] = p;
+            for (int j = 0; j < Nn; j++) {
+                const double sj = nd[j].w;
+                const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
+                double p = exp_neg(t * t, tab);
+                if (VIS) p *= vw[j];
+                colsum += p;
+                *pc = p;
+                pc += RS;
+            }
+        }
+        if (hi - lo == 2) {                              // row strictly between lo and hi keeps geodesic 0 (end quirk)
+            const int jb = lo + 1;
+            const double pn = VIS ? sm.vw[jb] : 1.0;
+            colsum += pn - pcol[jb * RS];
+            pcol[jb * RS] = pn;
         }
         const double den = colsum + c_norm;              // trackdlo.cpp:379 / 382
         const double w = valid ? 1.0 / den : 0.0;
@@ -333,51 +352,44 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         __syncthreads();
 
         // ---- P1 / PX accumulation (trackdlo.cpp:387-389)
-        for (int g = 0; g < ngroups; g++) {
-            const int m0 = g * per_group + warp;
-            for (int cn = lane; cn < tile; cn += 32) {
-                const double4 w4 = sm.wbuf[cn];
-#pragma unroll
-                for (int i = 0; i < NPW; i++) {
-                    const int m = m0 + nw * i;
-                    if (m < Nn) {
-                        const double p = sm.ptile[m * tile + cn];
-                        acc[i][0] = fma(p, w4.x, acc[i][0]);
-                        acc[i][1] = fma(p, w4.y, acc[i][1]);
-                        acc[i][2] = fma(p, w4.z, acc[i][2]);
-                        acc[i][3] = fma(p, w4.w, acc[i][3]);
-                    }
+        if (regacc) {
+            if (actB) {
+                const double* __restrict__ prow = sm.ptile + bm * RS;
+                const double4* __restrict__ wb = sm.wbuf;
+#pragma unroll 4
+                for (int nn = bq; nn < TILE; nn += Q) {
+                    const double p = prow[nn];
+                    const double4 w4 = wb[nn];
+                    a0 = fma(p, w4.x, a0); a1 = fma(p, w4.y, a1); a2 = fma(p, w4.z, a2); a3 = fma(p, w4.w, a3);
                 }
             }
-            if (ngroups > 1) {
-#pragma unroll
-                for (int i = 0; i < NPW; i++) {
-                    const int m = m0 + nw * i;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const double v = warp_sum(acc[i][k]);
-                        if (lane == 0 && m < Nn) sm.pacc[m * 4 + k] += v;
-                        acc[i][k] = 0.0;
-                    }
+        } else {
+            for (int m = tid; m < Nn; m += TILE) {
+                const double* __restrict__ prow = sm.ptile + m * RS;
+                double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                for (int nn = 0; nn < TILE; nn++) {
+                    const double p = prow[nn];
+                    const double4 w4 = sm.wbuf[nn];
+                    b0 = fma(p, w4.x, b0); b1 = fma(p, w4.y, b1); b2 = fma(p, w4.z, b2); b3 = fma(p, w4.w, b3);
                 }
+                sm.pacc[m * 4] += b0; sm.pacc[m * 4 + 1] += b1; sm.pacc[m * 4 + 2] += b2; sm.pacc[m * 4 + 3] += b3;
             }
         }
         __syncthreads();
     }
 
-    if (ngroups == 1) {
-#pragma unroll
-        for (int i = 0; i < NPW; i++) {
-            const int m = warp + nw * i;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const double v = warp_sum(acc[i][k]);
-                if (lane == 0 && m < Nn) __stcg(part_out + m * 4 + k, v);
-            }
+    if (regacc) {
+        sm.wbuf[tid] = actB ? make_double4(a0, a1, a2, a3) : make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncthreads();
+        const double* wflat = reinterpret_cast<const double*>(sm.wbuf);
+        for (int i = tid; i < 4 * Nn; i += TILE) {
+            const int m = i >> 2, k = i & 3;
+            double v = 0.0;
+            for (int q = 0; q < Q; q++) v += wflat[(q * Nn + m) * 4 + k];
+            __stcg(part_out + i, v);
         }
     } else {
-        __syncthreads();
-        for (int i = tid; i < 4 * Nn; i += tile) __stcg(part_out + i, sm.pacc[i]);
+        for (int i = tid; i < 4 * Nn; i += TILE) __stcg(part_out + i, sm.pacc[i]);
     }
     const double sx = block_sum(sxx, sm.red);
     if (tid == 0) __stcg(part_out + 4 * Nn, sx);
@@ -438,6 +450,126 @@ __device__ int gj_solve(double* AB, int n, int ld, int* prow, int* used, double*
     }
     __syncthreads();
     return bad;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path of the solve for n <= 64 with [A | B] in shared memory: same Gauss-Jordan
+// elimination with implicit partial pivoting, but ONE block barrier per elimination step.
+// Warp 0 is the pivot warp: while the other warps apply step k to columns k+2.., it computes
+// the updated column k+1 itself, selects the next pivot with three warp reductions on the bit
+// patterns of |a_ik| (non-negative doubles order like their bits), and publishes the scaled
+// multipliers for step k+1 (double-buffered).  gj: 2*64 multipliers + 1 flag.
+// ------------------------------------------------------------------------------------------
+// Pivot selection among the candidate rows {lane, lane+32}: arg-max of |v| over the warp via two
+// integer reductions on the bit pattern (non-negative doubles order like their bits) + one vote.
+// Ties go to the lowest lane.  NaN has the largest key, is selected, and poisons 1/pivot (-> flagged).
+__device__ __forceinline__ void gj_pick(double v0, double v1, bool ok0, bool ok1, int lane, int& prow_out, double& pval_out) {
+    const bool take1 = ok1 && (!ok0 || !(fabs(v1) <= fabs(v0)));
+    const double val = take1 ? v1 : v0;
+    const bool ok = ok0 || ok1;
+    const int hi = ok ? (__double2hiint(val) & 0x7fffffff) : -1;
+    const int mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = (hi == mh) ? (unsigned)__double2loint(val) : 0u;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+    const unsigned match = __ballot_sync(0xffffffffu, ok && hi == mh && lo == ml);
+    const unsigned t1 = __ballot_sync(0xffffffffu, take1);
+    const int win = __ffs(match) - 1;
+    prow_out = win + (((t1 >> win) & 1u) ? 32 : 0);
+    pval_out = __shfl_sync(0xffffffffu, val, win);
+}
+
+// AB must point into shared memory (pass the __shared__-derived pointer directly so that the
+// compiler emits LDS/STS with 32-bit addresses).
+__device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __restrict__ gj, int* __restrict__ pivs,
+                              double* __restrict__ wsol) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int ncol = n + 3;
+    const int r0 = lane, r1 = lane + 32;
+    const bool in0 = r0 < n, in1 = r1 < n;
+    bool used0 = false, used1 = false;             // pivot warp: rows r0 / r1 already used as pivots
+    int bad = 0;
+    double* const a0p = AB + r0 * ld;              // pivot warp: its two rows
+    double* const a1p = AB + r1 * ld;
+    if (warp == 0) {
+        const double v0 = in0 ? a0p[0] : 0.0, v1 = in1 ? a1p[0] : 0.0;
+        int p; double pv;
+        gj_pick(v0, v1, in0, in1, lane, p, pv);
+        const double rp = __drcp_rn(pv);
+        if (!(fabs(rp) <= 1.79e308)) bad = 1;
+        used0 |= (p == r0); used1 |= (p == r1);
+        if (in0) gj[r0] = (r0 == p) ? 0.0 : v0 * rp;
+        if (in1) gj[r1] = (r1 == p) ? 0.0 : v1 * rp;
+        if (lane == 0) pivs[0] = p;
+    }
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        const double* __restrict__ fk = gj + (k & 1) * 64;
+        const int p = pivs[k];
+        const double* __restrict__ prw = AB + p * ld;
+        if (warp == 0) {
+            // column k+1 belongs to the pivot warp in step k (for k = n-1 it is the first RHS column)
+            const double pj = prw[k + 1];
+            double v0 = 0.0, v1 = 0.0;
+            if (in0) { v0 = fma(-fk[r0], pj, a0p[k + 1]); a0p[k + 1] = v0; }
+            if (in1) { v1 = fma(-fk[r1], pj, a1p[k + 1]); a1p[k + 1] = v1; }
+            if (k + 1 < n) {
+                double* __restrict__ fn = gj + ((k + 1) & 1) * 64;
+                int pn; double pv;
+                gj_pick(v0, v1, in0 && !used0, in1 && !used1, lane, pn, pv);
+                const double rp = __drcp_rn(pv);
+                bad |= !(fabs(rp) <= 1.79e308);
+                used0 |= (pn == r0); used1 |= (pn == r1);
+                // rows >= n hold v = 0; gj has 64 slots per buffer, so the stores need no guard
+                fn[r0] = (r0 == pn) ? 0.0 : v0 * rp;
+                fn[r1] = (r1 == pn) ? 0.0 : v1 * rp;
+                pivs[k + 1] = pn;
+            }
+        } else if (warp <= 6) {
+            // updater warps 1..6.  While more than 32 columns remain: 2 column chunks x 3 row groups,
+            // afterwards 1 chunk x 6 row groups.  thread -> column j, rows g, g+RG, g+2RG, ...
+            // Loads are issued in batches of 6 rows ahead of the FMAs/stores (latency-bound code).
+            const int rem = ncol - (k + 2);
+            const bool two = rem > 32;
+            const int c = two ? ((warp - 1) & 1) : 0;
+            const int g = two ? ((warp - 1) >> 1) : (warp - 1);
+            const int RG = two ? 3 : 6;
+            const int j = k + 2 + 32 * c + lane;
+            if (j < ncol) {
+                const double q = -prw[j];
+                const int sr = RG * ld;
+                double* __restrict__ pp = AB + g * ld + j;
+                const double* __restrict__ fp = fk + g;
+                int cnt = (n - g + RG - 1) / RG;
+                for (; cnt >= 6; cnt -= 6) {
+                    const double x0 = pp[0], x1 = pp[sr], x2 = pp[2 * sr], x3 = pp[3 * sr], x4 = pp[4 * sr], x5 = pp[5 * sr];
+                    const double f0 = fp[0], f1 = fp[RG], f2 = fp[2 * RG], f3 = fp[3 * RG], f4 = fp[4 * RG], f5 = fp[5 * RG];
+                    pp[0] = fma(f0, q, x0); pp[sr] = fma(f1, q, x1); pp[2 * sr] = fma(f2, q, x2);
+                    pp[3 * sr] = fma(f3, q, x3); pp[4 * sr] = fma(f4, q, x4); pp[5 * sr] = fma(f5, q, x5);
+                    pp += 6 * sr; fp += 6 * RG;
+                }
+                if (cnt >= 3) {
+                    const double x0 = pp[0], x1 = pp[sr], x2 = pp[2 * sr];
+                    const double f0 = fp[0], f1 = fp[RG], f2 = fp[2 * RG];
+                    pp[0] = fma(f0, q, x0); pp[sr] = fma(f1, q, x1); pp[2 * sr] = fma(f2, q, x2);
+                    pp += 3 * sr; fp += 3 * RG; cnt -= 3;
+                }
+                for (; cnt > 0; cnt--) { pp[0] = fma(fp[0], q, pp[0]); pp += sr; fp += RG; }
+            }
+            if (n + 3 > 66 && two && c == 1) {           // n = 64: columns beyond k+2+63 (only for k = 0)
+                const int j2 = j + 32;
+                if (j2 < ncol) for (int i = g; i < n; i += 3) AB[i * ld + j2] = fma(-fk[i], prw[j2], AB[i * ld + j2]);
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && lane == 0) gj[128] = (double)bad;
+    for (int i = tid; i < 3 * n; i += nt) {
+        const int k = i / 3, d = i - 3 * k;
+        const int p = pivs[k];
+        wsol[i] = AB[p * ld + n + d] / AB[p * ld + k];
+    }
+    __syncthreads();
+    return gj[128] != 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -656,7 +788,7 @@ __device__ int traverse_euclidean(const double* geo, int G, const double* guide,
 // All CTAs execute the same sequence of cluster barriers.  Returns the status mask (uniform).
 // Yio: global [Nn][3] in/out.  sigma2_out / Wout / iters_out may be null.
 // ------------------------------------------------------------------------------------------
-template <int NPW>
+template <int TILE_CT>
 __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& a, double* cscr,
                        const double* __restrict__ Xraw, long long m0, double* __restrict__ Xc,
                        double* Yio, int Nn, double sigma2_in, double* sigma2_out, const CpdP& p,
@@ -674,7 +806,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
     double* gGATH = cscr + sc.GATH;
     double* gSTATE = cscr + sc.STATE;
     const int ld = Nn + 3;
-    const bool ab_in_smem = (Nn + 3) <= a.tile;
+    const bool ab_in_smem = (Nn + 3) <= a.tile + 1;
     double* AB = ab_in_smem ? sm.ptile : (cscr + sc.AB);
 
     if (Nn < 4) {                         // reference indexes rows 2 and Nn-3 (trackdlo.cpp:313-321)
@@ -776,6 +908,10 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
     const bool have_priors = n_priors > 0;
 
     int status = 0, iters = 0;
+    // optional phase timers (thread 0 of every CTA): 0 setup, 1 dmin, 2 estep, 3 wait after estep, 4 mstep, 5 wait after mstep
+    long long tprev = a.prof ? clock64() : 0;
+#define TDLO_TICK(slot)                                                                                   \
+    if (a.prof && tid == 0) { const long long tn_ = clock64(); atomicAdd(a.prof + (rank ? 8 : 0) + (slot), (unsigned long long)(tn_ - tprev)); tprev = tn_; }
     for (int it = 0; it < p.max_iter; it++) {
         iters = it + 1;
         const double rscale = sqrt(0.5 / sigma2);
@@ -783,6 +919,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
         const double c_gauss = pow(2 * M_PI * sigma2, 1.5) * p.mu / (1 - p.mu);
         double c_norm = c_gauss * (double)Nn / (double)Mp;             // trackdlo.cpp:300
         __syncthreads();
+        TDLO_TICK(0)
         if (use_vis) {
             dmin_slice(sm, Xloc, n_local, Nn, gDMIN + rank * Nn);
             cluster.sync();                                            // (V)
@@ -800,11 +937,14 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
             for (int j = tid; j < Nn; j += nt) sm.vw[j] = sm.vw[j] / tot;   // trackdlo.cpp:372
             c_norm = c_gauss / (double)Mp;                              // trackdlo.cpp:378
             __syncthreads();
-            estep_slice<NPW, true>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+            TDLO_TICK(1)
+            estep_slice<TILE_CT, true>(sm, Xloc, n_local, Nn, a.tile, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
         } else {
-            estep_slice<NPW, false>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+            estep_slice<TILE_CT, false>(sm, Xloc, n_local, Nn, a.tile, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
         }
+        TDLO_TICK(2)
         cluster.sync();                                                // (1) partial sums visible
+        TDLO_TICK(3)
 
         if (rank == 0) {
             // ---- gather partials in rank order
@@ -835,7 +975,11 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
                 AB[(long long)i * ld + Nn + d] = v;
             }
             __syncthreads();
-            if (gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol)) status |= ST_SINGULAR;
+            TDLO_TICK(4)
+            const int sing = (ab_in_smem && Nn <= 64 && nt >= 224) ? gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol)
+                                                                   : gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
+            if (sing) status |= ST_SINGULAR;
+            TDLO_TICK(6)
             // ---- T = Y0 + G W (trackdlo.cpp:417)
             for (int i = warp; i < Nn; i += nw) {
                 double ax = 0.0, ay = 0.0, az = 0.0;
@@ -873,7 +1017,9 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
             }
             for (int i = tid; i < 3 * Nn; i += nt) __stcg(gSTATE + i, sm.tnew[i]);
         }
+        TDLO_TICK(7)
         cluster.sync();                                                // (2) new state visible
+        TDLO_TICK(5)
         for (int j = tid; j < Nn; j += nt) {
             const double s = sm.node4[j].w;
             sm.node4[j] = make_double4(__ldcg(gSTATE + 3 * j), __ldcg(gSTATE + 3 * j + 1), __ldcg(gSTATE + 3 * j + 2), s);
@@ -885,6 +1031,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
         if (fin) break;
     }
 
+#undef TDLO_TICK
     // ---- results (rank 0)
     if (rank == 0) {
         for (int j = tid; j < Nn; j += nt) {
@@ -906,8 +1053,8 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
 // ------------------------------------------------------------------------------------------
 // The persistent kernel.
 // ------------------------------------------------------------------------------------------
-template <int NPW, int MINB>
-__global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
+template <int TILE_CT, int MINB>
+__global__ void __launch_bounds__(TILE_CT ? TILE_CT : kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -915,7 +1062,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs 
     const int C = (int)cluster.num_blocks();
     const int cluster_id = blockIdx.x / C;
 
-    const SmemL L = smem_layout(a.nmax, a.tile);
+    const SmemL& L = a.L;
     Smem sm;
     sm.tab = reinterpret_cast<double*>(smem_raw + L.tab);
     sm.node4 = reinterpret_cast<double4*>(smem_raw + L.node4);
@@ -932,6 +1079,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs 
     sm.tnew = reinterpret_cast<double*>(smem_raw + L.tnew);
     sm.pacc = reinterpret_cast<double*>(smem_raw + L.pacc);
     sm.red = reinterpret_cast<double*>(smem_raw + L.red);
+    sm.gjbuf = reinterpret_cast<double*>(smem_raw + L.gjbuf);
     sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
     sm.used = reinterpret_cast<int*>(smem_raw + L.used);
     sm.ptile = reinterpret_cast<double*>(smem_raw + L.ptile);
@@ -957,7 +1105,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs 
         if (a.mode == 0) {
             const int Nn = a.n_nodes ? a.n_nodes[f] : a.node_stride;
             const long long ys = (long long)f * a.node_stride;
-            const int st = cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
+            const int st = cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
                                         a.priors ? a.priors + ys * 4 : nullptr,
                                         (a.priors && a.n_priors) ? a.n_priors[f] : 0,
                                         a.n_visible ? a.n_visible[f] : 0,
@@ -986,7 +1134,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs 
             }
             cluster.sync();
             // pre-processing registration (trackdlo.cpp:925-927); sigma2 copy is discarded
-            const int st_pre = cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
+            const int st_pre = cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
                                             nullptr, 0, 0, a.H ? a.H + (long long)f * Nn * Nn : nullptr, Nn,
                                             nullptr, a.iters ? a.iters + 2 * f : nullptr);
             if (st_pre & ST_NOT_CONVERGED) st |= ST_PRE_NOT_CONVERGED;
@@ -1050,7 +1198,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs 
             if (__ldcg(ictl + 1)) st |= ST_TRAVERSE_UB;
             if (!(st & (ST_TOO_FEW_NODES | ST_EMPTY))) {
                 // main registration (trackdlo.cpp:998)
-                st |= cpd_run<NPW>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
+                st |= cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
                                    pri, np, V, nullptr, Nn, a.W ? a.W + (long long)f * Nn * 3 : nullptr,
                                    a.iters ? a.iters + 2 * f + 1 : nullptr);
             }
