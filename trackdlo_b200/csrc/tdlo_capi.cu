@@ -177,17 +177,17 @@ static int pick_tile(int nmax, int budget) {
 static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points_per_frame_hint) {
     CK(cudaSetDevice(ctx->device));
     const int nmax = a.nmax;
-    // ---- kernel variant + tile: <224,2> two CTAs/SM (Nn <= ~50), <256,1> one CTA/SM, <0,1> generic (runtime tile)
+    // ---- kernel variant + tile (= threads per CTA, one 32-point P slice per warp):
+    // <2,2>: Nn <= 64, two CTAs/SM; <4,1>: Nn <= 128; <8,1>: Nn <= 256.  Largest tile that fits.
     const int budget2 = 113 * 1024, budget1 = 227 * 1024;
     kern_t kern;
     int tile, occ;
-    if (smem_layout(nmax, 224).total <= budget2 && nmax <= 224) { kern = tdlo_em_kernel<224, 2>; tile = 224; occ = 2; }
-    else if (smem_layout(nmax, 256).total <= budget1) { kern = tdlo_em_kernel<256, 1>; tile = 256; occ = 1; }
-    else {
-        kern = tdlo_em_kernel<0, 1>; occ = 1;
-        tile = pick_tile(nmax, budget1);
-        if (tile < 32) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
-    }
+    if (nmax <= 64) {
+        tile = pick_tile(nmax, budget2); occ = 2; kern = tdlo_em_kernel<2, 2>;
+        if (tile < 128) { tile = pick_tile(nmax, budget1); occ = 1; }
+    } else if (nmax <= 128) { kern = tdlo_em_kernel<4, 1>; tile = pick_tile(nmax, budget1); occ = 1; }
+    else { kern = tdlo_em_kernel<8, 1>; tile = pick_tile(nmax, budget1); occ = 1; }
+    if (tile < 64) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
     const int smem = smem_layout(nmax, tile).total;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

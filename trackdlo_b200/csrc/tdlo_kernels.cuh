@@ -62,7 +62,7 @@ __host__ __device__ inline SmemL smem_layout(int N, int tile) {
     l.prow = o; o += N * 4;
     l.used = o; o += N * 4;
     o = (o + 31) & ~31;
-    l.ptile = o; o += N * (tile + 1) * 8;
+    l.ptile = o; o += (tile / 32) * N * 33 * 8;      // one [N][33] P slice per warp
     l.total = o;
     return l;
 }
@@ -264,34 +264,30 @@ __device__ void dmin_slice(const Smem& sm, const double* __restrict__ Xc, int n_
 // ------------------------------------------------------------------------------------------
 // Fused E-step over this CTA's slice (trackdlo.cpp:278-389): distances -> arg-max node ->
 // geodesic distances -> P -> (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.
-// Phase A is thread-per-point: the point's P column goes into the shared-memory tile
-// ptile[node][point] (row stride TILE+1 doubles).  Phase B maps threads to (node m, slice q):
-// lanes of a warp hold consecutive nodes (conflict-free reads of the padded tile, broadcast reads
-// of the per-point weights) and keep the four sums of their node in registers across all tiles.
+// Every WARP is autonomous: it takes 32 points at a time (lane = point), writes their P columns
+// into its private shared-memory slice pt[node][33] (phase A), then switches to lane = node and
+// accumulates P1/PX for its nodes over those 32 points in registers (phase B).  Only __syncwarp
+// separates the phases, so the warps of a CTA overlap their phases freely and no block barrier
+// sits in the hot loop.  NPASS = ceil(Nn / 32) node passes in phase B (compile time).
 // part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
-// TILE_CT != 0 fixes the tile size at compile time (immediate smem offsets in the hot loops).
 // ------------------------------------------------------------------------------------------
-template <int TILE_CT, bool VIS>
-__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn, int tile_rt,
+template <int NPASS, bool VIS>
+__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn,
                             double sigma2, double c_norm, double rscale, double* part_out) {
-    const int TILE = TILE_CT ? TILE_CT : tile_rt;
-    const int RS = TILE + 1;
-    const int tid = threadIdx.x;
-    const bool regacc = Nn <= TILE;
-    const int Q = regacc ? TILE / Nn : 1;
-    const int bq = tid / Nn, bm = tid - bq * Nn;
-    const bool actB = regacc && bq < Q;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (!regacc) {
-        for (int i = tid; i < 4 * Nn; i += TILE) sm.pacc[i] = 0.0;
-    }
-    double sxx = 0.0;
+    constexpr int RS = 33;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    double* __restrict__ pt = sm.ptile + warp * (Nn * RS);
+    double4* __restrict__ wb = sm.wbuf + warp * 32;
+    double* __restrict__ pcol = pt + lane;
     const double* __restrict__ tab = sm.tab;
-    double* __restrict__ pcol = sm.ptile + tid;
+    double acc[NPASS][4];
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
+    double sxx = 0.0;
     const double uflow = 1490.2 * sigma2;      // cheap pre-test: below this exp(-0.5*d2/sigma2) cannot underflow to 0
 
-    for (int base = 0; base < n_local; base += TILE) {
-        const int n = base + tid;
+    for (int base = warp * 32; base < n_local; base += nw * 32) {
+        const int n = base + lane;
         const bool valid = n < n_local;
         double x = 0, y = 0, z = 0;
         if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
@@ -322,14 +318,29 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         const double alo = sm.node4[lo].w + dlo * rscale;        //  s'_lo + d'_lo  (minus s'_j)
         const double ahi = dhi * rscale - sm.node4[hi].w;        //  d'_hi - s'_hi  (plus  s'_j)
 
-        // ---- P column (trackdlo.cpp:332-354, 358-375)
+        // ---- phase A: P column (trackdlo.cpp:332-354, 358-375).  Four nodes per trip: all shared-memory
+        // loads of a trip precede its stores, so the four exp chains are independent and interleave.
         double colsum = 0.0;
         {
-            const double4* __restrict__ nd = sm.node4;
-            const double* __restrict__ vw = sm.vw;
-            double* __restrict__ pc = pcol;
-#pragma unroll 2
-            for (int j = 0; j < Nn; j++) {
+            const double4* nd = sm.node4;
+            const double* vw = sm.vw;
+            double* pc = pcol;
+            int j = 0;
+            for (; j + 4 <= Nn; j += 4) {
+                const double s0 = nd[j].w, s1 = nd[j + 1].w, s2 = nd[j + 2].w, s3 = nd[j + 3].w;
+                double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
+                if (VIS) { v0 = vw[j]; v1 = vw[j + 1]; v2 = vw[j + 2]; v3 = vw[j + 3]; }
+                const double t0 = (j <= lo) ? (alo - s0) : (ahi + s0);
+                const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
+                const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
+                const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
+                double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
+                if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
+                colsum += (p0 + p1) + (p2 + p3);
+                pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3;
+                pc += 4 * RS;
+            }
+            for (; j < Nn; j++) {
                 const double sj = nd[j].w;
                 const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
                 double p = exp_neg(t * t, tab);
@@ -348,51 +359,46 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         const double den = colsum + c_norm;              // trackdlo.cpp:379 / 382
         const double w = valid ? 1.0 / den : 0.0;
         sxx = fma(colsum * w, x * x + y * y + z * z, sxx);   // Pt1_n * |x_n|^2 (trackdlo.cpp:418)
-        sm.wbuf[tid] = make_double4(w, w * x, w * y, w * z);
-        __syncthreads();
+        wb[lane] = make_double4(w, w * x, w * y, w * z);
+        __syncwarp();
 
-        // ---- P1 / PX accumulation (trackdlo.cpp:387-389)
-        if (regacc) {
-            if (actB) {
-                const double* __restrict__ prow = sm.ptile + bm * RS;
-                const double4* __restrict__ wb = sm.wbuf;
-#pragma unroll 4
-                for (int nn = bq; nn < TILE; nn += Q) {
-                    const double p = prow[nn];
-                    const double4 w4 = wb[nn];
-                    a0 = fma(p, w4.x, a0); a1 = fma(p, w4.y, a1); a2 = fma(p, w4.z, a2); a3 = fma(p, w4.w, a3);
-                }
-            }
-        } else {
-            for (int m = tid; m < Nn; m += TILE) {
-                const double* __restrict__ prow = sm.ptile + m * RS;
-                double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                for (int nn = 0; nn < TILE; nn++) {
-                    const double p = prow[nn];
-                    const double4 w4 = sm.wbuf[nn];
-                    b0 = fma(p, w4.x, b0); b1 = fma(p, w4.y, b1); b2 = fma(p, w4.z, b2); b3 = fma(p, w4.w, b3);
-                }
-                sm.pacc[m * 4] += b0; sm.pacc[m * 4 + 1] += b1; sm.pacc[m * 4 + 2] += b2; sm.pacc[m * 4 + 3] += b3;
+        // ---- phase B: lane = node; P1 / PX over this warp's 32 points (trackdlo.cpp:387-389)
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ps++) {
+            int m = lane + 32 * ps;
+            m = m < Nn ? m : Nn - 1;                      // surplus lanes recompute the last node; discarded below
+            const double* __restrict__ prow = pt + m * RS;
+#pragma unroll 8
+            for (int nn = 0; nn < 32; nn++) {
+                const double p = prow[nn];
+                const double4 w4 = wb[nn];
+                acc[ps][0] = fma(p, w4.x, acc[ps][0]); acc[ps][1] = fma(p, w4.y, acc[ps][1]);
+                acc[ps][2] = fma(p, w4.z, acc[ps][2]); acc[ps][3] = fma(p, w4.w, acc[ps][3]);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    if (regacc) {
-        sm.wbuf[tid] = actB ? make_double4(a0, a1, a2, a3) : make_double4(0.0, 0.0, 0.0, 0.0);
-        __syncthreads();
-        const double* wflat = reinterpret_cast<const double*>(sm.wbuf);
-        for (int i = tid; i < 4 * Nn; i += TILE) {
-            const int m = i >> 2, k = i & 3;
-            double v = 0.0;
-            for (int q = 0; q < Q; q++) v += wflat[(q * Nn + m) * 4 + k];
-            __stcg(part_out + i, v);
+    // ---- cross-warp reduction in a fixed order (deterministic)
+    __syncthreads();
+    double* __restrict__ racc = sm.ptile;                 // [nw][Nn][4]; the P slices are dead now
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) {
+        const int m = lane + 32 * ps;
+        if (m < Nn) {
+            double* dst = racc + ((long long)warp * Nn + m) * 4;
+            dst[0] = acc[ps][0]; dst[1] = acc[ps][1]; dst[2] = acc[ps][2]; dst[3] = acc[ps][3];
         }
-    } else {
-        for (int i = tid; i < 4 * Nn; i += TILE) __stcg(part_out + i, sm.pacc[i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * Nn; i += nt) {
+        double v = 0.0;
+        for (int w = 0; w < nw; w++) v += racc[w * 4 * Nn + i];
+        __stcg(part_out + i, v);
     }
     const double sx = block_sum(sxx, sm.red);
     if (tid == 0) __stcg(part_out + 4 * Nn, sx);
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,16 +530,17 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
                 fn[r1] = (r1 == pn) ? 0.0 : v1 * rp;
                 pivs[k + 1] = pn;
             }
-        } else if (warp <= 6) {
-            // updater warps 1..6.  While more than 32 columns remain: 2 column chunks x 3 row groups,
-            // afterwards 1 chunk x 6 row groups.  thread -> column j, rows g, g+RG, g+2RG, ...
+        } else {
+            // updater warps 1..nw-1.  While more than 32 columns remain: 2 column chunks x (U/2) row groups,
+            // afterwards 1 chunk x U row groups (U = nw-1 updater warps).  thread -> column j, rows g, g+RG, ...
             // Loads are issued in batches of 6 rows ahead of the FMAs/stores (latency-bound code).
+            const int U = nw - 1;
             const int rem = ncol - (k + 2);
-            const bool two = rem > 32;
-            const int c = two ? ((warp - 1) & 1) : 0;
-            const int g = two ? ((warp - 1) >> 1) : (warp - 1);
-            const int RG = two ? 3 : 6;
-            const int j = k + 2 + 32 * c + lane;
+            const bool two = rem > 32 && U >= 2;
+            const int RG = two ? (U >> 1) : U;
+            const int c = two ? ((warp - 1) / RG) : 0;
+            const int g = two ? ((warp - 1) - c * RG) : (warp - 1);
+            const int j = (c > 1) ? ncol : k + 2 + 32 * c + lane;   // odd U: the last warp sits out the two-chunk phase
             if (j < ncol) {
                 const double q = -prw[j];
                 const int sr = RG * ld;
@@ -555,9 +562,9 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
                 }
                 for (; cnt > 0; cnt--) { pp[0] = fma(fp[0], q, pp[0]); pp += sr; fp += RG; }
             }
-            if (n + 3 > 66 && two && c == 1) {           // n = 64: columns beyond k+2+63 (only for k = 0)
-                const int j2 = j + 32;
-                if (j2 < ncol) for (int i = g; i < n; i += 3) AB[i * ld + j2] = fma(-fk[i], prw[j2], AB[i * ld + j2]);
+            if (n + 3 > 66 && c == (two ? 1 : 0)) {     // columns beyond the chunks above (n = 64, k = 0; or a single updater chunk)
+                for (int j2 = k + 2 + (two ? 64 : 32) + lane; j2 < ncol; j2 += 32)
+                    for (int i = g; i < n; i += RG) AB[i * ld + j2] = fma(-fk[i], prw[j2], AB[i * ld + j2]);
             }
         }
         __syncthreads();
@@ -788,7 +795,7 @@ __device__ int traverse_euclidean(const double* geo, int G, const double* guide,
 // All CTAs execute the same sequence of cluster barriers.  Returns the status mask (uniform).
 // Yio: global [Nn][3] in/out.  sigma2_out / Wout / iters_out may be null.
 // ------------------------------------------------------------------------------------------
-template <int TILE_CT>
+template <int NPASS>
 __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& a, double* cscr,
                        const double* __restrict__ Xraw, long long m0, double* __restrict__ Xc,
                        double* Yio, int Nn, double sigma2_in, double* sigma2_out, const CpdP& p,
@@ -806,7 +813,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
     double* gGATH = cscr + sc.GATH;
     double* gSTATE = cscr + sc.STATE;
     const int ld = Nn + 3;
-    const bool ab_in_smem = (Nn + 3) <= a.tile + 1;
+    const bool ab_in_smem = (long long)Nn * (Nn + 3) <= (long long)(a.tile / 32) * a.nmax * 33;
     double* AB = ab_in_smem ? sm.ptile : (cscr + sc.AB);
 
     if (Nn < 4) {                         // reference indexes rows 2 and Nn-3 (trackdlo.cpp:313-321)
@@ -938,9 +945,9 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
             c_norm = c_gauss / (double)Mp;                              // trackdlo.cpp:378
             __syncthreads();
             TDLO_TICK(1)
-            estep_slice<TILE_CT, true>(sm, Xloc, n_local, Nn, a.tile, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+            estep_slice<NPASS, true>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
         } else {
-            estep_slice<TILE_CT, false>(sm, Xloc, n_local, Nn, a.tile, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
+            estep_slice<NPASS, false>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
         }
         TDLO_TICK(2)
         cluster.sync();                                                // (1) partial sums visible
@@ -976,7 +983,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
             }
             __syncthreads();
             TDLO_TICK(4)
-            const int sing = (ab_in_smem && Nn <= 64 && nt >= 224) ? gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol)
+            const int sing = (ab_in_smem && Nn <= 64 && nt >= 64) ? gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol)
                                                                    : gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
             if (sing) status |= ST_SINGULAR;
             TDLO_TICK(6)
@@ -1053,8 +1060,8 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
 // ------------------------------------------------------------------------------------------
 // The persistent kernel.
 // ------------------------------------------------------------------------------------------
-template <int TILE_CT, int MINB>
-__global__ void __launch_bounds__(TILE_CT ? TILE_CT : kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
+template <int NPASS, int MINB>
+__global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -1105,7 +1112,7 @@ __global__ void __launch_bounds__(TILE_CT ? TILE_CT : kMaxThreads, MINB) tdlo_em
         if (a.mode == 0) {
             const int Nn = a.n_nodes ? a.n_nodes[f] : a.node_stride;
             const long long ys = (long long)f * a.node_stride;
-            const int st = cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
+            const int st = cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
                                         a.priors ? a.priors + ys * 4 : nullptr,
                                         (a.priors && a.n_priors) ? a.n_priors[f] : 0,
                                         a.n_visible ? a.n_visible[f] : 0,
@@ -1134,7 +1141,7 @@ __global__ void __launch_bounds__(TILE_CT ? TILE_CT : kMaxThreads, MINB) tdlo_em
             }
             cluster.sync();
             // pre-processing registration (trackdlo.cpp:925-927); sigma2 copy is discarded
-            const int st_pre = cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
+            const int st_pre = cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
                                             nullptr, 0, 0, a.H ? a.H + (long long)f * Nn * Nn : nullptr, Nn,
                                             nullptr, a.iters ? a.iters + 2 * f : nullptr);
             if (st_pre & ST_NOT_CONVERGED) st |= ST_PRE_NOT_CONVERGED;
@@ -1198,7 +1205,7 @@ __global__ void __launch_bounds__(TILE_CT ? TILE_CT : kMaxThreads, MINB) tdlo_em
             if (__ldcg(ictl + 1)) st |= ST_TRAVERSE_UB;
             if (!(st & (ST_TOO_FEW_NODES | ST_EMPTY))) {
                 // main registration (trackdlo.cpp:998)
-                st |= cpd_run<TILE_CT>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
+                st |= cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
                                    pri, np, V, nullptr, Nn, a.W ? a.W + (long long)f * Nn * 3 : nullptr,
                                    a.iters ? a.iters + 2 * f + 1 : nullptr);
             }
