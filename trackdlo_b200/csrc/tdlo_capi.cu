@@ -27,6 +27,7 @@ struct tdlo_ctx {
     int *d_vis = nullptr, *d_ext = nullptr, *d_npri_out = nullptr, *d_state = nullptr;
     // workspace
     double* d_Xc = nullptr;
+    unsigned short* d_bkt = nullptr;
     double* d_scratch = nullptr;
     long long scratch_stride = 0;
     int scratch_clusters = 0;
@@ -69,7 +70,7 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
     void* ptrs[] = {ctx->d_X, ctx->d_Y, ctx->d_sigma2, ctx->d_priors, ctx->d_H, ctx->d_W, ctx->d_rest, ctx->d_guide,
                     ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
-                    ctx->d_Xc, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf};
+                    ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -118,6 +119,7 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(dalloc(&ctx->d_X, P * 3));
     CKC(dalloc(&ctx->d_Xc, P * 3));
+    CKC(dalloc(&ctx->d_bkt, P));
     CKC(dalloc(&ctx->d_xoff, F + 1));
     CKC(dalloc(&ctx->d_Y, F * N * 3));
     CKC(dalloc(&ctx->d_sigma2, F));
@@ -227,6 +229,7 @@ static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points
     a.tile = tile;
     a.L = smem_layout(nmax, tile);
     a.Xc = ctx->d_Xc;
+    a.bkt = ctx->d_bkt;
     a.scratch = ctx->d_scratch;
     a.scratch_stride = ctx->scratch_stride;
     a.queue = ctx->d_queue;

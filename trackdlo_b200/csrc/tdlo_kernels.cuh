@@ -89,6 +89,7 @@ struct KArgs {
     CpdP p1;             // mode 1: main registration
     // workspace
     double* Xc;          // compacted points, same indexing as X
+    unsigned short* bkt; // nearest-node bucket per raw point (sort key), same indexing as X
     double* scratch;     // per-cluster scratch
     long long scratch_stride;   // doubles per cluster
     int* queue;          // frame queue counter
@@ -182,40 +183,70 @@ __device__ __forceinline__ double dist2(double ax, double ay, double az, double 
 }
 
 // ------------------------------------------------------------------------------------------
-// Prune + order-preserving compaction of this CTA's slice of the frame (trackdlo.cpp:177-195)
-// and the sum of squared distances of the kept points to all nodes (sigma2 init, :263-273).
+// Prune this CTA's slice of the frame (trackdlo.cpp:177-195), accumulate the sum of squared
+// distances of the kept points to all nodes (sigma2 init, :263-273), and write the kept points
+// to Xc[r0 ...) STABLY SORTED BY NEAREST NODE (counting sort, deterministic).  Sorting changes only
+// the summation order of the E-step reductions; it makes the points of a warp neighbours along
+// the DLO, which is what lets the E-step skip node ranges whose P entries are exactly 0.
+// bkt: global temp, one uint16 per raw point (nearest node, 0xffff = pruned).
 // Returns the number of kept points (uniform over the block); *sum_out gets the block sum.
 // ------------------------------------------------------------------------------------------
-__device__ int prune_slice(const Smem& sm, const double* __restrict__ Xraw, long long r0, long long r1,
-                           double* __restrict__ Xc, int Nn, double radius, double* sum_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
-    int* wcnt = reinterpret_cast<int*>(sm.red);      // nw ints
-    int count = 0;
+__device__ int prune_sort_slice(const Smem& sm, const double* __restrict__ Xraw, long long r0, long long r1,
+                                double* __restrict__ Xc, unsigned short* __restrict__ bkt, int Nn, double radius,
+                                double* sum_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    int* hist = reinterpret_cast<int*>(sm.ptile);      // [Nn+1] counts, then running bucket offsets
+    int* cnt = hist + 264;                             // [nw][Nn] per-warp counts of the current tile
+    for (int i = tid; i <= Nn; i += nt) hist[i] = 0;
+    for (int i = tid; i < nw * Nn; i += nt) cnt[i] = 0;
+    __syncthreads();
     double sum2 = 0.0;
-    for (long long base = r0; base < r1; base += tile) {
+    for (long long base = r0; base < r1; base += nt) {
         const long long n = base + tid;
         const bool valid = n < r1;
         double x = 0, y = 0, z = 0;
         if (valid) { x = __ldg(Xraw + n * 3); y = __ldg(Xraw + n * 3 + 1); z = __ldg(Xraw + n * 3 + 2); }
         double best = 1e300, tot = 0.0;
+        int a = 0;
         for (int j = 0; j < Nn; j++) {
             const double4 q = sm.node4[j];
             const double d2 = dist2(q.x, q.y, q.z, x, y, z);
             tot += d2;
-            best = fmin(best, d2);
+            if (d2 < best) { best = d2; a = j; }
         }
         const bool keep = valid && (sqrt(best) < radius);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) wcnt[warp] = __popc(bal);
+        if (valid) bkt[n] = keep ? (unsigned short)a : (unsigned short)0xffff;
+        if (keep) { atomicAdd(&hist[a], 1); sum2 += tot; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int bk = 0; bk < Nn; bk++) { const int c = hist[bk]; hist[bk] = run; run += c; }
+        hist[Nn] = run;
+    }
+    __syncthreads();
+    const int count = hist[Nn];
+    for (long long base = r0; base < r1; base += nt) {
+        const long long n = base + tid;
+        const bool valid = n < r1;
+        const unsigned bk = valid ? (unsigned)bkt[n] : 0xffffu;
+        const bool keep = bk != 0xffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, bk);
+        const int rk = __popc(peers & ((1u << lane) - 1u));
+        if (keep && rk == 0) cnt[warp * Nn + bk] = __popc(peers);
         __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < nw; w++) { const int c = wcnt[w]; if (w < warp) before += c; total += c; }
         if (keep) {
-            const long long dst = r0 + count + before + __popc(bal & ((1u << lane) - 1u));
-            Xc[dst * 3] = x; Xc[dst * 3 + 1] = y; Xc[dst * 3 + 2] = z;
-            sum2 += tot;
+            int off = hist[bk] + rk;
+            for (int w = 0; w < warp; w++) off += cnt[w * Nn + bk];
+            const long long dst = r0 + off;
+            Xc[dst * 3] = __ldg(Xraw + n * 3); Xc[dst * 3 + 1] = __ldg(Xraw + n * 3 + 1); Xc[dst * 3 + 2] = __ldg(Xraw + n * 3 + 2);
         }
-        count += total;
+        __syncthreads();
+        for (int bb = tid; bb < Nn; bb += nt) {
+            int sc = 0;
+            for (int w = 0; w < nw; w++) { sc += cnt[w * Nn + bb]; cnt[w * Nn + bb] = 0; }
+            hist[bb] += sc;
+        }
         __syncthreads();
     }
     *sum_out = block_sum(sum2, sm.red);
@@ -318,15 +349,44 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         const double alo = sm.node4[lo].w + dlo * rscale;        //  s'_lo + d'_lo  (minus s'_j)
         const double ahi = dhi * rscale - sm.node4[hi].w;        //  d'_hi - s'_hi  (plus  s'_j)
 
+        // ---- node window of this warp: outside [jlo, jhi] every P entry of these 32 points is EXACTLY 0 in
+        // the reference (exp underflows for -0.5*geo/sigma2 < -745.13), so those rows are skipped.  A lane
+        // needs j <= lo while s'_j > alo - T and j >= hi while s'_j < T - ahi (T^2 = 745.2); [lo, hi] itself
+        // is always kept (the end quirk puts P = 1 between them).  The points are sorted by nearest node,
+        // so the union over the warp stays narrow once sigma2 is small.
+        int jlo, jhi;
+        {
+            const double T = 27.298351598585583;              // sqrt(745.2)
+            double mlo = valid ? alo : 1e300, mhi = valid ? ahi : 1e300;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+                mhi = fmin(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+            }
+            const int lomin = __reduce_min_sync(0xffffffffu, valid ? lo : Nn);
+            const int himax = __reduce_max_sync(0xffffffffu, valid ? hi : -1);
+            const double thr_lo = mlo - T, thr_hi = T - mhi;
+            jlo = Nn; jhi = -1;
+            for (int c = 0; c < Nn; c += 32) {
+                const int j = c + lane;
+                const double sj = j < Nn ? sm.node4[j].w : 0.0;
+                const unsigned m1 = __ballot_sync(0xffffffffu, j < Nn && sj > thr_lo);
+                const unsigned m2 = __ballot_sync(0xffffffffu, j < Nn && sj < thr_hi);
+                if (m1 && jlo == Nn) jlo = c + __ffs(m1) - 1;
+                if (m2) jhi = c + 31 - __clz(m2);
+            }
+            jlo = min(jlo, lomin); jhi = max(jhi, himax);
+        }
+
         // ---- phase A: P column (trackdlo.cpp:332-354, 358-375).  Four nodes per trip: all shared-memory
         // loads of a trip precede its stores, so the four exp chains are independent and interleave.
         double colsum = 0.0;
         {
             const double4* nd = sm.node4;
             const double* vw = sm.vw;
-            double* pc = pcol;
-            int j = 0;
-            for (; j + 4 <= Nn; j += 4) {
+            double* pc = pcol + jlo * RS;
+            int j = jlo;
+            for (; j + 3 <= jhi; j += 4) {
                 const double s0 = nd[j].w, s1 = nd[j + 1].w, s2 = nd[j + 2].w, s3 = nd[j + 3].w;
                 double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
                 if (VIS) { v0 = vw[j]; v1 = vw[j + 1]; v2 = vw[j + 2]; v3 = vw[j + 3]; }
@@ -340,7 +400,7 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
                 pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3;
                 pc += 4 * RS;
             }
-            for (; j < Nn; j++) {
+            for (; j <= jhi; j++) {
                 const double sj = nd[j].w;
                 const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
                 double p = exp_neg(t * t, tab);
@@ -362,18 +422,20 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         wb[lane] = make_double4(w, w * x, w * y, w * z);
         __syncwarp();
 
-        // ---- phase B: lane = node; P1 / PX over this warp's 32 points (trackdlo.cpp:387-389)
+        // ---- phase B: lane = node; P1 / PX over this warp's 32 points (trackdlo.cpp:387-389).
+        // Lanes whose node lies outside the window are masked off; a pass with no node inside is skipped.
 #pragma unroll
         for (int ps = 0; ps < NPASS; ps++) {
-            int m = lane + 32 * ps;
-            m = m < Nn ? m : Nn - 1;                      // surplus lanes recompute the last node; discarded below
-            const double* __restrict__ prow = pt + m * RS;
+            const int m = lane + 32 * ps;
+            if (m >= jlo && m <= jhi) {
+                const double* __restrict__ prow = pt + m * RS;
 #pragma unroll 8
-            for (int nn = 0; nn < 32; nn++) {
-                const double p = prow[nn];
-                const double4 w4 = wb[nn];
-                acc[ps][0] = fma(p, w4.x, acc[ps][0]); acc[ps][1] = fma(p, w4.y, acc[ps][1]);
-                acc[ps][2] = fma(p, w4.z, acc[ps][2]); acc[ps][3] = fma(p, w4.w, acc[ps][3]);
+                for (int nn = 0; nn < 32; nn++) {
+                    const double p = prow[nn];
+                    const double4 w4 = wb[nn];
+                    acc[ps][0] = fma(p, w4.x, acc[ps][0]); acc[ps][1] = fma(p, w4.y, acc[ps][1]);
+                    acc[ps][2] = fma(p, w4.z, acc[ps][2]); acc[ps][3] = fma(p, w4.w, acc[ps][3]);
+                }
             }
         }
         __syncwarp();
@@ -841,7 +903,7 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
     if (r0 > m0) r0 = m0;
     if (r1 > m0) r1 = m0;
     double sum_local;
-    const int n_local = prune_slice(sm, Xraw, r0, r1, Xc, Nn, p.prune_radius, &sum_local);
+    const int n_local = prune_sort_slice(sm, Xraw, r0, r1, Xc, a.bkt + (Xraw - a.X) / 3, Nn, p.prune_radius, &sum_local);
     if (tid == 0) { __stcg(gGATH + 2 * rank, (double)n_local); __stcg(gGATH + 2 * rank + 1, sum_local); }
     const double* Xloc = Xc + r0 * 3;
 
