@@ -169,9 +169,9 @@ class Context:
         """Returns and resets the kernel's phase cycle counters; see tdlo_profile_phases."""
         cyc = (C.c_uint64 * 16)()
         self._check(self.lib.tdlo_profile_phases(self.h, int(enable), cyc), "tdlo_profile_phases")
-        names = ("setup", "dmin", "estep", "wait1", "assemble", "wait2", "solve", "update")
+        names = ("setup", "dmin", "estep", "wait1", "assemble", "wait2", "solve", "update")  # others[x6]/[x7]: solver warp0 / warp1 busy cycles
         v = list(cyc)
-        return {"rank0": dict(zip(names, v[:8])), "others": dict(zip(names, v[8:16]))}
+        return {"rank0": dict(zip(names, v[:8])), "others": dict(zip(names[:6] + ("solver_warp0_busy", "solver_warp1_busy"), v[8:16]))}
 
     def launch_info(self):
         info = (C.c_int32 * 8)()

@@ -323,14 +323,56 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
         double x = 0, y = 0, z = 0;
         if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
 
-        // ---- nearest node (== arg-max of the Gaussian P of trackdlo.cpp:298-310)
+        // ---- nearest node (== arg-max of the Gaussian P of trackdlo.cpp:298-310).
+        // Exact pruning of the search range: with c = the point of lane 0 and rho = max_lane |x - c|, a node m
+        // with |Y_m - c| > min_m' |Y_m' - c| + 2 rho is strictly farther from EVERY point of this warp than the
+        // node nearest to c (triangle inequality), so it can be neither the arg-min nor tie with it.  The scan
+        // covers the contiguous index range [ja, jb] spanned by the surviving nodes -> same first-minimum as
+        // the full scan.  The points are sorted by nearest node, so the range is a handful of nodes.
+        int ja, jb;
+        {
+            const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
+            const double r2 = valid ? dist2(x, y, z, cx, cy, cz) : 0.0;
+            const unsigned rh = __reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(r2));
+            const unsigned rl = __reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(r2) == rh ? (unsigned)__double2loint(r2) : 0u);
+            const double rho = sqrt(__hiloint2double((int)rh, (int)rl));
+            double dc[NPASS];
+            double dloc = 1e300;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ps++) {
+                const int m = lane + 32 * ps;
+                dc[ps] = 1e300;
+                if (m < Nn) { const double4 q = sm.node4[m]; dc[ps] = sqrt(dist2(q.x, q.y, q.z, cx, cy, cz)); }
+                dloc = fmin(dloc, dc[ps]);
+            }
+            const unsigned dh = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(dloc));
+            const unsigned dl = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(dloc) == dh ? (unsigned)__double2loint(dloc) : 0xffffffffu);
+            const double lim = (__hiloint2double((int)dh, (int)dl) + 2.0 * rho) * (1.0 + 1e-12) + 1e-300;
+            ja = Nn; jb = -1;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ps++) {
+                const unsigned mk = __ballot_sync(0xffffffffu, dc[ps] <= lim);
+                if (mk) { if (ja == Nn) ja = 32 * ps + __ffs(mk) - 1; jb = 32 * ps + 31 - __clz(mk); }
+            }
+        }
         double best = 1e300;
-        int a = 0;
-#pragma unroll 4
-        for (int j = 0; j < Nn; j++) {
-            const double4 q = sm.node4[j];
-            const double d2 = dist2(q.x, q.y, q.z, x, y, z);
-            if (d2 < best) { best = d2; a = j; }
+        int a = ja;
+        {
+            int j = ja;
+            for (; j + 3 <= jb; j += 4) {
+                const double4 q0 = sm.node4[j], q1 = sm.node4[j + 1], q2 = sm.node4[j + 2], q3 = sm.node4[j + 3];
+                const double e0 = dist2(q0.x, q0.y, q0.z, x, y, z), e1 = dist2(q1.x, q1.y, q1.z, x, y, z);
+                const double e2 = dist2(q2.x, q2.y, q2.z, x, y, z), e3 = dist2(q3.x, q3.y, q3.z, x, y, z);
+                if (e0 < best) { best = e0; a = j; }
+                if (e1 < best) { best = e1; a = j + 1; }
+                if (e2 < best) { best = e2; a = j + 2; }
+                if (e3 < best) { best = e3; a = j + 3; }
+            }
+            for (; j <= jb; j++) {
+                const double4 q = sm.node4[j];
+                const double d2 = dist2(q.x, q.y, q.z, x, y, z);
+                if (d2 < best) { best = d2; a = j; }
+            }
         }
         // whole column underflows to 0 in the reference -> maxCoeff returns index 0
         if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
@@ -548,8 +590,10 @@ __device__ __forceinline__ void gj_pick(double v0, double v1, bool ok0, bool ok1
 
 // AB must point into shared memory (pass the __shared__-derived pointer directly so that the
 // compiler emits LDS/STS with 32-bit addresses).
+// pivot == false: the caller guarantees a symmetric positive definite A (elimination in natural order is
+// stable, every pivot is positive); the search is skipped and the pivot warp's chain is ~3x shorter.
 __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __restrict__ gj, int* __restrict__ pivs,
-                              double* __restrict__ wsol) {
+                              double* __restrict__ wsol, const bool pivot, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int ncol = n + 3;
     const int r0 = lane, r1 = lane + 32;
@@ -561,7 +605,8 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
     if (warp == 0) {
         const double v0 = in0 ? a0p[0] : 0.0, v1 = in1 ? a1p[0] : 0.0;
         int p; double pv;
-        gj_pick(v0, v1, in0, in1, lane, p, pv);
+        if (pivot) gj_pick(v0, v1, in0, in1, lane, p, pv);
+        else { p = 0; pv = __shfl_sync(0xffffffffu, v0, 0); }
         const double rp = __drcp_rn(pv);
         if (!(fabs(rp) <= 1.79e308)) bad = 1;
         used0 |= (p == r0); used1 |= (p == r1);
@@ -570,7 +615,21 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
         if (lane == 0) pivs[0] = p;
     }
     __syncthreads();
+    // updater-warp geometry, hoisted out of the elimination loop (every instruction inside it is on the
+    // critical path of a ~50-step dependent chain).  Phase "two" (more than 32 columns left): 2 column chunks x
+    // RG2 row groups; phase "one": 1 chunk x RG1 row groups.
+    const int U = nw - 1;
+    const int RG2 = U >> 1, c2 = RG2 ? (warp - 1) / RG2 : 2, g2 = (warp - 1) - c2 * RG2;
+    const int cnt2 = (warp >= 1 && RG2 && c2 <= 1 && g2 < n) ? (n - g2 + RG2 - 1) / RG2 : 0;
+    const int RG1 = U > 0 ? U : 1, g1 = warp - 1;
+    const int cnt1 = (g1 >= 0 && g1 < n) ? (n - g1 + RG1 - 1) / RG1 : 0;
+    const int ktwo = (U >= 2) ? ncol - 34 : 0;                 // k < ktwo  <=>  ncol - (k + 2) > 32
+    double* const pp2 = AB + g2 * ld + 2 + 32 * (c2 & 1) + lane;  // + k at step k
+    double* const pp1 = AB + (g1 > 0 ? g1 : 0) * ld + 2 + lane;
+    const int sr2 = RG2 * ld, sr1 = RG1 * ld;
+    const int jo2 = 2 + 32 * (c2 & 1) + lane, jo1 = 2 + lane;   // column of this lane = k + jo
     for (int k = 0; k < n; k++) {
+        const long long dbg_t0 = dbg ? clock64() : 0;
         const double* __restrict__ fk = gj + (k & 1) * 64;
         const int p = pivs[k];
         const double* __restrict__ prw = AB + p * ld;
@@ -583,7 +642,8 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
             if (k + 1 < n) {
                 double* __restrict__ fn = gj + ((k + 1) & 1) * 64;
                 int pn; double pv;
-                gj_pick(v0, v1, in0 && !used0, in1 && !used1, lane, pn, pv);
+                if (pivot) gj_pick(v0, v1, in0 && !used0, in1 && !used1, lane, pn, pv);
+                else { pn = k + 1; pv = __shfl_sync(0xffffffffu, pn < 32 ? v0 : v1, pn & 31); }
                 const double rp = __drcp_rn(pv);
                 bad |= !(fabs(rp) <= 1.79e308);
                 used0 |= (pn == r0); used1 |= (pn == r1);
@@ -596,19 +656,17 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
             // updater warps 1..nw-1.  While more than 32 columns remain: 2 column chunks x (U/2) row groups,
             // afterwards 1 chunk x U row groups (U = nw-1 updater warps).  thread -> column j, rows g, g+RG, ...
             // Loads are issued in batches of 6 rows ahead of the FMAs/stores (latency-bound code).
-            const int U = nw - 1;
-            const int rem = ncol - (k + 2);
-            const bool two = rem > 32 && U >= 2;
-            const int RG = two ? (U >> 1) : U;
-            const int c = two ? ((warp - 1) / RG) : 0;
-            const int g = two ? ((warp - 1) - c * RG) : (warp - 1);
-            const int j = (c > 1) ? ncol : k + 2 + 32 * c + lane;   // odd U: the last warp sits out the two-chunk phase
-            if (j < ncol) {
+            const bool two = k < ktwo;
+            const int RG = two ? RG2 : RG1;
+            const int c = two ? c2 : 0;
+            const int g = two ? g2 : g1;
+            const int sr = two ? sr2 : sr1;
+            const int j = k + (two ? jo2 : jo1);
+            int cnt = two ? cnt2 : cnt1;
+            if (j < ncol && cnt > 0) {
                 const double q = -prw[j];
-                const int sr = RG * ld;
-                double* __restrict__ pp = AB + g * ld + j;
+                double* __restrict__ pp = (two ? pp2 : pp1) + k;
                 const double* __restrict__ fp = fk + g;
-                int cnt = (n - g + RG - 1) / RG;
                 for (; cnt >= 6; cnt -= 6) {
                     const double x0 = pp[0], x1 = pp[sr], x2 = pp[2 * sr], x3 = pp[3 * sr], x4 = pp[4 * sr], x5 = pp[5 * sr];
                     const double f0 = fp[0], f1 = fp[RG], f2 = fp[2 * RG], f3 = fp[3 * RG], f4 = fp[4 * RG], f5 = fp[5 * RG];
@@ -629,6 +687,7 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
                     for (int i = g; i < n; i += RG) AB[i * ld + j2] = fma(-fk[i], prw[j2], AB[i * ld + j2]);
             }
         }
+        if (dbg && lane == 0 && warp <= 1) atomicAdd(dbg + 14 + warp, (unsigned long long)(clock64() - dbg_t0));
         __syncthreads();
     }
     if (warp == 0 && lane == 0) gj[128] = (double)bad;
@@ -1028,12 +1087,25 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
             __syncthreads();
             // ---- assemble [A | B] (trackdlo.cpp:392-413)
             const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
+            // Without LLE, A = D G + ls I with D = diag(P1 + alpha J) is similar to the SPD matrix
+            // D^1/2 G D^1/2 + ls I (G is a Matern-3/2 kernel of the arc length): solve that one without
+            // pivoting, (D^1/2 G D^1/2 + ls I) Z = D^-1/2 B, W = D^1/2 Z.  Rows with D_i = 0 have B_i = 0 and give
+            // W_i = 0 in both forms.  Same conditioning as A.
+            const bool spd = !p.include_lle && ab_in_smem && Nn <= 64 && nt >= 64;
+            if (spd) {
+                for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
+                __syncthreads();
+            }
             for (int idx = tid; idx < Nn * Nn; idx += nt) {
                 const int i = idx / Nn, j = idx - i * Nn;
                 const double g = gG[idx];
-                double v = sm.p1[i] * g + (i == j ? ls : 0.0);
-                if (p.include_lle) v += sg * gHG[idx];
-                if (have_priors) v += p.alpha * sm.jd[i] * g;
+                double v;
+                if (spd) v = sm.tnew[i] * g * sm.tnew[j] + (i == j ? ls : 0.0);
+                else {
+                    v = sm.p1[i] * g + (i == j ? ls : 0.0);
+                    if (p.include_lle) v += sg * gHG[idx];
+                    if (have_priors) v += p.alpha * sm.jd[i] * g;
+                }
                 AB[(long long)i * ld + j] = v;
             }
             for (int idx = tid; idx < 3 * Nn; idx += nt) {
@@ -1041,12 +1113,21 @@ __device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& 
                 double v = sm.px[idx] - sm.p1[i] * sm.y0[idx];
                 if (p.include_lle) v -= sg * sm.hy0[idx];
                 if (have_priors) v += p.alpha * (sm.yext[idx] - sm.y0[idx]);
+                if (spd) { const double sd = sm.tnew[i]; v = sd > 0.0 ? v / sd : 0.0; }
                 AB[(long long)i * ld + Nn + d] = v;
             }
             __syncthreads();
             TDLO_TICK(4)
-            const int sing = (ab_in_smem && Nn <= 64 && nt >= 64) ? gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol)
-                                                                   : gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
+            int sing;
+            if (ab_in_smem && Nn <= 64 && nt >= 64) {
+                double sdreg[3];
+                if (spd) for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sdreg[t] = sm.tnew[i / 3];   // tnew is reused below
+                sing = gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol, !spd, a.prof);
+                if (spd) {
+                    for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
+                    __syncthreads();
+                }
+            } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
             if (sing) status |= ST_SINGULAR;
             TDLO_TICK(6)
             // ---- T = Y0 + G W (trackdlo.cpp:417)
