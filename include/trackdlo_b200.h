@@ -149,7 +149,24 @@ int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]);
  * pre-pass, E-step, wait, M-step, wait}; cycles[8..13] = the same for the other ranks.  Synchronises. */
 int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 
-/* Overrides the automatic cluster-size choice (0 = automatic; 1,2,4,8,16). */
+/* Engine options.
+ *  TDLO_OPT_ENGINE        1 (default) = task-queue engine: one persistent launch, the E-step of every frame is
+ *                         cut into chunk tasks that any SM may run, the CTA finishing a frame's last chunk runs
+ *                         its M-step; 0 = cluster-per-frame engine.
+ *  TDLO_OPT_CHUNK_POINTS  raw points per chunk task (default 1024).
+ *  TDLO_OPT_TRUNCATION    z_cut: affinity entries exp(-z) with z > z_cut are skipped.  745.2 skips only entries
+ *                         that are exactly 0 in the reference (double underflow); the default 100 skips entries
+ *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.
+ *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
+ *  TDLO_OPT_THREADS       threads per CTA of the task-queue engine (default 224). */
+#define TDLO_OPT_ENGINE 1
+#define TDLO_OPT_CHUNK_POINTS 2
+#define TDLO_OPT_TRUNCATION 3
+#define TDLO_OPT_INFLIGHT 4
+#define TDLO_OPT_THREADS 5
+int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value);
+
+/* Overrides the automatic cluster-size choice of the cluster engine (0 = automatic; 1,2,4,8,16). */
 int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t cluster_size);
 
 #ifdef __cplusplus

@@ -41,6 +41,13 @@ def run():
     return e0.elapsed_time(e1)
 
 
+engine = os.environ.get("TDLO_ENGINE", "tq")
+for k in ("chunk_points", "truncation", "inflight", "threads"):
+    if os.environ.get("TDLO_" + k.upper()):
+        ctx.set_option(k, float(os.environ["TDLO_" + k.upper()]))
+ctx.set_option("engine", 1 if engine == "tq" else 0)
+if engine == "tq":
+    clusters = [0]
 for c in clusters:
     ctx.set_cluster_size(c)
     run(); run()

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "tdlo_create", "tdlo_destroy", "tdlo_last_error", "tdlo_version",
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
-    "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases",
+    "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases", "tdlo_set_option",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library():
         lib.tdlo_tracking_step_batched_device.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC), C.c_void_p]
         lib.tdlo_last_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
+        lib.tdlo_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         _lib = lib
     return _lib
@@ -164,6 +165,12 @@ class Context:
 
     def set_cluster_size(self, c):
         self._check(self.lib.tdlo_set_cluster_size(self.h, c), "tdlo_set_cluster_size")
+
+    OPTIONS = {"engine": 1, "chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5}
+
+    def set_option(self, name, value):
+        """tdlo_set_option: engine (1 task queue / 0 cluster), chunk_points, truncation, inflight, threads."""
+        self._check(self.lib.tdlo_set_option(self.h, self.OPTIONS[name], float(value)), f"tdlo_set_option({name})")
 
     def profile_phases(self, enable=True):
         """Returns and resets the kernel's phase cycle counters; see tdlo_profile_phases."""

@@ -3,6 +3,7 @@
 // (trackdlo/include/trackdlo.h:81-102) for batches of independent frames.
 #include "../../include/trackdlo_b200.h"
 #include "tdlo_kernels.cuh"
+#include "tdlo_taskq.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -35,6 +36,15 @@ struct tdlo_ctx {
     unsigned long long* d_prof = nullptr;   // phase cycle counters (enabled by tdlo_profile_phases)
     unsigned long long* d_prof_buf = nullptr;
     int cluster_override = 0;
+    // task-queue engine (tdlo_taskq.cuh)
+    int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
+    int tq_chunk = 1024;            // raw points per chunk task
+    int tq_threads = 224;           // threads per CTA
+    int tq_inflight = 0;            // frames in flight (0 = automatic)
+    double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
+    double* d_fscratch = nullptr; long long fstride = 0;
+    double *d_part = nullptr, *d_dminp = nullptr, *d_gath = nullptr; int* d_nkept = nullptr;
+    unsigned long long* d_q = nullptr; unsigned qcap = 0; long long tq_chunks_cap = 0; int tq_alloc_chunk = 0;
     long long points_hint = 0;      // points per frame of the current host call (0 = unknown)
     int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     char err[512] = {0};
@@ -70,7 +80,8 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
     void* ptrs[] = {ctx->d_X, ctx->d_Y, ctx->d_sigma2, ctx->d_priors, ctx->d_H, ctx->d_W, ctx->d_rest, ctx->d_guide,
                     ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
-                    ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf};
+                    ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf,
+                    ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -176,7 +187,75 @@ static int pick_tile(int nmax, int budget) {
     return best;
 }
 
+typedef void (*tq_kern_t)(const TqArgs);
+
+// Task-queue engine: one persistent launch, grid = SMs x resident CTAs, no clusters.
+static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
+    CK(cudaSetDevice(ctx->device));
+    const int nmax = a.nmax;
+    const int threads = ctx->tq_threads;
+    const int nw = threads / 32;
+    // ---- workspace (allocated on first use / when the chunk size changes)
+    const int chunk = ctx->tq_chunk;
+    if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {
+        void* old[] = {ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q};
+        CK(cudaDeviceSynchronize());
+        for (void* p : old) if (p) cudaFree(p);
+        ctx->d_fscratch = nullptr; ctx->d_part = ctx->d_dminp = ctx->d_gath = nullptr; ctx->d_nkept = nullptr; ctx->d_q = nullptr;
+        const TqScr sc = tq_scr_layout(ctx->max_nodes);
+        ctx->fstride = sc.total;
+        ctx->tq_chunks_cap = ctx->max_points / chunk + ctx->max_frames + 2;
+        unsigned cap = 1024;
+        while ((long long)cap < 2 * (ctx->tq_chunks_cap + 4LL * ctx->sm_count + ctx->max_frames + 64)) cap <<= 1;
+        ctx->qcap = cap;
+#define CKA(call)                                                                                   \
+        do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) return fail(ctx, e2_ == cudaErrorMemoryAllocation ? TDLO_ERR_NOMEM : TDLO_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2_)); } while (0)
+        CKA(dalloc(&ctx->d_fscratch, (size_t)ctx->fstride * ctx->max_frames));
+        CKA(dalloc(&ctx->d_part, (size_t)ctx->tq_chunks_cap * (4 * ctx->max_nodes + 4)));
+        CKA(dalloc(&ctx->d_dminp, (size_t)ctx->tq_chunks_cap * ctx->max_nodes));
+        CKA(dalloc(&ctx->d_gath, (size_t)ctx->tq_chunks_cap));
+        CKA(dalloc(&ctx->d_nkept, (size_t)ctx->tq_chunks_cap));
+        CKA(dalloc(&ctx->d_q, (size_t)cap + 8));
+#undef CKA
+        ctx->tq_alloc_chunk = chunk;
+    }
+    tq_kern_t kern;
+    const TqSmemL L = tq_smem_layout(nmax, nw);
+    int minb;
+    if (nmax <= 64) { kern = tdlo_tq_kernel<2, 3>; minb = 3; }
+    else if (nmax <= 128) { kern = tdlo_tq_kernel<4, 2>; minb = 2; }
+    else { kern = tdlo_tq_kernel<8, 2>; minb = 2; }
+    if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, L.total));
+    if (occ < 1) return fail(ctx, TDLO_ERR_CUDA, "task-queue kernel does not fit (smem %d B, %d threads)", L.total, threads);
+    (void)minb;
+    const int grid = ctx->sm_count * occ;
+    TqArgs t;
+    memset(&t, 0, sizeof(t));
+    a.Xc = ctx->d_Xc; a.bkt = ctx->d_bkt; a.scr_nodes = ctx->max_nodes; a.prof = nullptr;
+    t.k = a;
+    t.chunk = chunk;
+    t.inflight = ctx->tq_inflight > 0 ? ctx->tq_inflight : std::max(grid / 2, 64);
+    t.inflight = std::min(std::min(t.inflight, grid), a.n_frames);
+    t.zcut = ctx->tq_zcut;
+    t.qctl = ctx->d_q; t.qslots = ctx->d_q + 8; t.qmask = ctx->qcap - 1;
+    t.fscratch = ctx->d_fscratch; t.fstride = ctx->fstride;
+    t.part = ctx->d_part; t.dminp = ctx->d_dminp; t.gath = ctx->d_gath; t.nkept = ctx->d_nkept;
+    t.part_stride = 4 * ctx->max_nodes + 4;
+    t.L = L;
+    CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));
+    CK(cudaMemcpyAsync(reinterpret_cast<int*>(ctx->d_q + 2), &t.inflight, sizeof(int), cudaMemcpyHostToDevice, stream));
+    kern<<<grid, threads, L.total, stream>>>(t);
+    CK(cudaGetLastError());
+    ctx->info[0] = 1; ctx->info[1] = grid; ctx->info[2] = threads; ctx->info[3] = L.total; ctx->info[4] = chunk;
+    ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
+    return TDLO_OK;
+}
+
 static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points_per_frame_hint) {
+    if (ctx->engine == 1) return launch_tq(ctx, a, stream);
     CK(cudaSetDevice(ctx->device));
     const int nmax = a.nmax;
     // ---- kernel variant + tile (= threads per CTA, one 32-point P slice per warp):
@@ -424,6 +503,32 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (b->state) D2H(b->state, ctx->d_state, F * sizeof(int));
     CK(cudaStreamSynchronize(ctx->stream));
     return TDLO_OK;
+}
+
+extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    switch (option) {
+        case TDLO_OPT_ENGINE:
+            if (value != 0.0 && value != 1.0) return fail(ctx, TDLO_ERR_INVALID, "engine must be 0 (cluster) or 1 (task queue)");
+            ctx->engine = (int)value; return TDLO_OK;
+        case TDLO_OPT_CHUNK_POINTS: {
+            const int c = (int)value;
+            if (c < 256 || c > (1 << 20) || (c % 32)) return fail(ctx, TDLO_ERR_INVALID, "chunk must be a multiple of 32 in [256, 2^20]");
+            ctx->tq_chunk = c; return TDLO_OK;
+        }
+        case TDLO_OPT_TRUNCATION:
+            if (!(value >= 40.0 && value <= 745.2)) return fail(ctx, TDLO_ERR_INVALID, "truncation exponent must be in [40, 745.2]");
+            ctx->tq_zcut = value; return TDLO_OK;
+        case TDLO_OPT_INFLIGHT:
+            if (value < 0) return fail(ctx, TDLO_ERR_INVALID, "inflight must be >= 0");
+            ctx->tq_inflight = (int)value; return TDLO_OK;
+        case TDLO_OPT_THREADS: {
+            const int t = (int)value;
+            if (t < 64 || t > 256 || (t % 32)) return fail(ctx, TDLO_ERR_INVALID, "threads must be a multiple of 32 in [64, 256]");
+            ctx->tq_threads = t; return TDLO_OK;
+        }
+        default: return fail(ctx, TDLO_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 // Development aid: enable (and read back / reset) the per-phase cycle counters of the kernel.

@@ -1,0 +1,1087 @@
+// Task-queue engine of the B200-native TrackDLO registration path (sm_100a).
+//
+// ONE persistent launch per batch.  Every CTA loops over a global ticket queue of small tasks; a
+// frame's EM iteration (trackdlo/src/trackdlo.cpp:276-438) is a wave of independent CHUNK tasks over the
+// frame's points followed by the M-step, which the CTA that finishes the wave's last chunk runs on the
+// spot ("last arriver continues").  Nothing ever waits on another CTA: while one CTA assembles and solves
+// (diag(P1) G + lambda sigma2 I) W = B for a frame, every other CTA keeps streaming E-step chunks of the
+// other frames, and the SMs stay busy irrespective of how frames x chunks divide the 148 SMs.
+//
+//   start_call ──► PRUNE chunk tasks ─┐ (+ the set-up itself: G, LLE, priors)
+//                                     └► after_prune ─► begin_iter ─► [DMIN chunk tasks ─► after_dmin] ─►
+//                  ESTEP chunk tasks ─► m_step ─► begin_iter ... ─► finish_call ─► (tracking: traverse, main call)
+//
+// Results are bit-deterministic: chunk partials are combined in chunk order whichever CTA computed them.
+// Everything is fp64 (the reference is MatrixXd end to end).
+#pragma once
+
+#include "tdlo_kernels.cuh"
+
+namespace tdlo {
+
+constexpr int TQ_THREADS = 256;            // upper bound of threads per CTA (the host picks 224 or 256)
+constexpr int TQ_ROWS = 32, TQ_RS = 33;    // P tile of a warp: 32 node rows x 32 points (+1 pad)
+
+enum { TK_PRUNE = 1, TK_DMIN = 2, TK_ESTEP = 3, TK_EXIT = 7 };
+enum { A_NONE = 0, A_START_CALL, A_AFTER_PRUNE, A_BEGIN_ITER, A_AFTER_DMIN, A_MSTEP, A_FINISH_CALL, A_FRAME_DONE };
+
+// frame control block (ints)
+enum { FC_PENDING = 0, FC_PHASE, FC_STAGE, FC_ITER, FC_NN, FC_NCHUNK, FC_USEVIS, FC_NPRI, FC_STATUS, FC_NVIS, FC_STPRE,
+       FC_ITPRE, FC_WORDS = 16 };
+// frame scalars (doubles)
+enum { FS_SIGMA2 = 0, FS_RSCALE, FS_CNORM, FS_MP, FS_CGAUSS, FS_WORDS = 8 };
+
+// ---- per-frame scratch (doubles); N = scr_nodes
+struct TqScr {
+    long long G, HG, H, AB, NODE4, VW, Y0, S, YEXT, JD, HY0, WSOL, SCAL, TRV, PRI, GUIDE, CTL, total;
+};
+__host__ __device__ inline TqScr tq_scr_layout(int N) {
+    TqScr s;
+    long long o = 0, n2 = (long long)N * N;
+    s.G = o; o += n2;
+    s.HG = o; o += n2;
+    s.H = o; o += n2;
+    s.AB = o; o += (long long)N * (N + 4);
+    s.NODE4 = o; o += 4 * N;
+    s.VW = o; o += N;
+    s.Y0 = o; o += 3 * N;
+    s.S = o; o += N;
+    s.YEXT = o; o += 3 * N;
+    s.JD = o; o += N;
+    s.HY0 = o; o += 3 * N;
+    s.WSOL = o; o += 3 * N;
+    s.SCAL = o; o += FS_WORDS;
+    s.TRV = o; o += 2LL * (N + 2) * 4;
+    s.PRI = o; o += (2LL * N + 4) * 4;
+    s.GUIDE = o; o += 3 * N;
+    s.CTL = o; o += FC_WORDS / 2;
+    s.total = (o + 15) & ~15LL;
+    return s;
+}
+
+// ---- shared memory layout (bytes).  One fixed head (exp table, node data) + a region that is the E-step's
+// P tiles during chunk tasks and the M-step's [A|B] + vectors during continuations.
+struct TqSmemL {
+    int tab, node4, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, total;
+};
+__host__ __device__ inline TqSmemL tq_smem_layout(int N, int nw) {
+    TqSmemL l;
+    int o = 0;
+    l.tab = o; o += 64 * 8;
+    l.node4 = o; o += N * 32;
+    l.vw = o; o += N * 8;
+    l.bcast = o; o += 64;
+    l.red = o; o += 64 * 8;
+    o = (o + 31) & ~31;
+    const int u = o;
+    // E-step view
+    l.wbuf = o; o += nw * 32 * 32;
+    l.ptile = o; o += nw * TQ_ROWS * TQ_RS * 8;
+    const int e_end = o;
+    // M-step view (aliases the E-step view)
+    o = u;
+    l.y0 = o; o += 3 * N * 8;
+    l.s = o; o += N * 8;
+    l.yext = o; o += 3 * N * 8;
+    l.jd = o; o += N * 8;
+    l.hy0 = o; o += 3 * N * 8;
+    l.p1 = o; o += N * 8;
+    l.px = o; o += 3 * N * 8;
+    l.wsol = o; o += 3 * N * 8;
+    l.tnew = o; o += 3 * N * 8;
+    l.gjbuf = o; o += 136 * 8;
+    l.prow = o; o += N * 4;
+    l.used = o; o += N * 4;
+    o = (o + 31) & ~31;
+    l.ab = o;
+    l.ab_doubles = (e_end - o) / 8;
+    l.total = e_end;
+    return l;
+}
+
+struct TqArgs {
+    KArgs k;                         // frame data + parameters (same meaning as in the cluster engine)
+    int chunk;                       // raw points per chunk task
+    int inflight;                    // frames started at launch; one more starts whenever a frame completes
+    double zcut;                     // Gaussian truncation: entries exp(-z), z > zcut, are skipped (745.2 = exact zeros only)
+    unsigned long long* qctl;        // [0] head ticket, [1] tail, [2] next frame (int), [3] frames done (int)
+    unsigned long long* qslots; unsigned qmask;
+    double* fscratch; long long fstride;   // per-frame scratch
+    double* part; double* dminp; double* gath; int* nkept;   // per global chunk
+    int part_stride;                 // doubles per chunk in `part`
+    TqSmemL L;
+};
+
+struct TqSm {
+    double* tab; double4* node4; double* vw; int* bcast; double* red;
+    double4* wbuf; double* ptile;
+    double *y0, *s, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *gjbuf; int *prow, *used; double* ab;
+};
+
+// 32-byte L2 load (data written by other CTAs during this launch must not come from L1)
+__device__ __forceinline__ double4 ldcg4(const double4* p) {
+    const double2 lo = __ldcg(reinterpret_cast<const double2*>(p)), hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// ------------------------------------------------------------------------------------------
+// queue
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// slot word: lap(24) | type(3) | frame(17) | chunk(20)
+__device__ __forceinline__ unsigned long long tq_word(unsigned long long ticket, unsigned qmask, int type, int frame, int chunk) {
+    const unsigned long long lap = (ticket / ((unsigned long long)qmask + 1ull) + 1ull) & 0xffffffull;
+    return (lap << 40) | ((unsigned long long)type << 37) | ((unsigned long long)frame << 20) | (unsigned long long)chunk;
+}
+// Publishes n tasks (type, frame, chunk 0..n-1).  Called by all threads of the CTA after the data the tasks
+// read has been written; contains the fences and a barrier.
+__device__ void tq_push(const TqArgs& a, TqSm& sm, int type, int frame, int n) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = atomicAdd(a.qctl + 1, (unsigned long long)n);
+    __syncthreads();
+    const unsigned long long base = *reinterpret_cast<unsigned long long*>(sm.bcast + 4);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long t = base + i;
+        st_release_u64(a.qslots + (t & a.qmask), tq_word(t, a.qmask, type, type == TK_EXIT ? 0 : frame, type == TK_EXIT ? 0 : i));
+    }
+    __syncthreads();
+}
+// Takes the next ticket and waits for its task.  Returns the slot word (uniform over the CTA).
+__device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(a.qctl, 1ull);
+        const unsigned long long lap = (t / ((unsigned long long)a.qmask + 1ull) + 1ull) & 0xffffffull;
+        const unsigned long long* slot = a.qslots + (t & a.qmask);
+        unsigned long long v = ld_acquire_u64(slot);
+        unsigned ns = 32;
+        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 1024) ns <<= 1; v = ld_acquire_u64(slot); }
+        *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = v;
+    }
+    __syncthreads();
+    const unsigned long long v = *reinterpret_cast<unsigned long long*>(sm.bcast + 4);
+    __syncthreads();
+    return v;
+}
+// A chunk task (or the set-up) of frame f is complete.  Returns true (uniform) for the LAST arriver of the
+// wave, which then owns the frame until it publishes the next wave.
+__device__ bool tq_arrive(TqSm& sm, int* ctl) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicSub(ctl + FC_PENDING, 1);
+        sm.bcast[0] = (old == 1);
+        if (old == 1) __threadfence();
+    }
+    __syncthreads();
+    const bool last = sm.bcast[0] != 0;
+    __syncthreads();
+    return last;
+}
+
+__device__ __forceinline__ int tq_chunk_base(const TqArgs& a, int f) { return (int)(a.k.x_off[f] / a.chunk) + f; }
+
+// positive doubles order like their bit patterns: warp min / max of the HIGH words gives a bound that is
+// conservative by < 2^-20 relative -- good enough for search ranges and windows, one REDUX instead of a
+// ten-shuffle tree.  (Both return a value <= / >= the true extremum.)
+__device__ __forceinline__ double warp_min_pos_lb(double v) {
+    const unsigned h = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(v));
+    return __hiloint2double((int)h, 0);
+}
+__device__ __forceinline__ double warp_max_pos_ub(double v) {
+    const unsigned h = __reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(v));
+    return __hiloint2double((int)h + 1, 0);
+}
+__device__ __forceinline__ double warp_min_pos_ub(double v) {
+    const unsigned h = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(v));
+    return __hiloint2double((int)h + 1, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// E-step over one chunk (trackdlo.cpp:278-389); see estep_slice in tdlo_kernels.cuh for the maths.
+// Differences: (1) the P tile of a warp has a fixed 32 node rows -- the node WINDOW of the warp's 32 points
+// (everything outside is exactly 0 / below the truncation) is processed in blocks of 32 rows, recomputing
+// the exponentials of later blocks (only the first, wide iterations of a registration need more than one);
+// (2) phase B splits the lanes into (node row, point group) so that a narrow window still uses all 32
+// lanes; (3) window and search bounds use single-REDUX conservative bounds.
+// part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
+// ------------------------------------------------------------------------------------------
+template <int NPASS, bool VIS>
+__device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, int n_local, int Nn,
+                               double sigma2, double c_norm, double rscale, double zcut, double* part_out) {
+    constexpr int RS = TQ_RS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    double* __restrict__ pt = sm.ptile + warp * (TQ_ROWS * RS);
+    double4* __restrict__ wb = sm.wbuf + warp * 32;
+    double* __restrict__ pcol = pt + lane;
+    const double* __restrict__ tab = sm.tab;
+    const double4* __restrict__ nd = sm.node4;
+    const double* __restrict__ vw = sm.vw;
+    double acc[NPASS][4];
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
+    double sxx = 0.0;
+    const double uflow = 1490.2 * sigma2;
+    const double T = sqrt(zcut);
+    const double s_last = nd[Nn - 1].w;
+
+    for (int base = warp * 32; base < n_local; base += nw * 32) {
+        const bool valid = base + lane < n_local;
+        const int n = valid ? base + lane : base;            // idle lanes shadow the tile's first point (weight 0)
+        const double x = __ldcg(Xc + (long long)n * 3), y = __ldcg(Xc + (long long)n * 3 + 1), z = __ldcg(Xc + (long long)n * 3 + 2);
+
+        // ---- nearest node: exact bounding-sphere pruning of the scan range (see estep_slice)
+        int ja, jb;
+        {
+            const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
+            const double rho = sqrt(warp_max_pos_ub(dist2(x, y, z, cx, cy, cz) + 1e-300));
+            double dc[NPASS];
+            double dloc = 1e300;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ps++) {
+                const int m = lane + 32 * ps;
+                dc[ps] = 1e300;
+                if (m < Nn) { const double4 q = nd[m]; dc[ps] = dist2(q.x, q.y, q.z, cx, cy, cz); }
+                dloc = fmin(dloc, dc[ps]);
+            }
+            double lim = (sqrt(warp_min_pos_ub(dloc + 1e-300)) + 2.0 * rho) * (1.0 + 1e-9);
+            lim = lim * lim;
+            ja = Nn; jb = -1;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ps++) {
+                const unsigned mk = __ballot_sync(0xffffffffu, dc[ps] <= lim);
+                if (mk) { if (ja == Nn) ja = 32 * ps + __ffs(mk) - 1; jb = 32 * ps + 31 - __clz(mk); }
+            }
+        }
+        double best = 1e300;
+        int a = ja;
+        {
+            int j = ja;
+            for (; j + 1 <= jb; j += 2) {
+                const double4 q0 = nd[j], q1 = nd[j + 1];
+                const double e0 = dist2(q0.x, q0.y, q0.z, x, y, z), e1 = dist2(q1.x, q1.y, q1.z, x, y, z);
+                if (e0 < best) { best = e0; a = j; }
+                if (e1 < best) { best = e1; a = j + 1; }
+            }
+            if (j <= jb) {
+                const double4 q = nd[j];
+                const double d2 = dist2(q.x, q.y, q.z, x, y, z);
+                if (d2 < best) { best = d2; a = j; }
+            }
+        }
+        // whole column underflows to 0 in the reference -> maxCoeff returns index 0 (trackdlo.cpp:310)
+        if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
+        int q1 = a - 1; if (q1 == -1) q1 = 2;
+        int q2 = a + 1; if (q2 == Nn) q2 = Nn - 3;
+        double da, d1, d2n;
+        { const double4 q = nd[a];  da  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        { const double4 q = nd[q1]; d1  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        { const double4 q = nd[q2]; d2n = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
+        const bool pick1 = d1 < d2n;                     // trackdlo.cpp:324-329
+        const int b = pick1 ? q1 : q2;
+        const double db = pick1 ? d1 : d2n;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const double dlo = a < b ? da : db, dhi = a < b ? db : da;
+        const double alo = nd[lo].w + dlo * rscale;      // t_j = alo - s'_j  for j <= lo
+        const double ahi = dhi * rscale - nd[hi].w;      // t_j = ahi + s'_j  for j >= hi
+
+        // ---- node window [jlo, jhi] of this warp: P entries outside are below exp(-zcut) for all 32 points
+        int jlo, jhi;
+        {
+            const double thr_lo = warp_min_pos_lb(alo) - T;                        // keep j <= lo while s'_j > thr_lo
+            const double thr_hi = T - (warp_min_pos_lb(ahi + s_last) - s_last);    // keep j >= hi while s'_j < thr_hi
+            const int lomin = __reduce_min_sync(0xffffffffu, lo);
+            const int himax = __reduce_max_sync(0xffffffffu, hi);
+            jlo = Nn; jhi = -1;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ps++) {
+                const int j = lane + 32 * ps;
+                const double sj = j < Nn ? nd[j].w : 0.0;
+                const unsigned m1 = __ballot_sync(0xffffffffu, j < Nn && sj > thr_lo);
+                const unsigned m2 = __ballot_sync(0xffffffffu, j < Nn && sj < thr_hi);
+                if (m1 && jlo == Nn) jlo = 32 * ps + __ffs(m1) - 1;
+                if (m2) jhi = 32 * ps + 31 - __clz(m2);
+            }
+            jlo = min(jlo, lomin); jhi = max(jhi, himax);
+        }
+        const bool quirk = (hi - lo == 2);               // the row strictly between lo and hi keeps geodesic 0 -> P = 1 (x vw)
+        const int jq = lo + 1;
+
+        double w = 0.0;
+        for (int j0 = jlo; j0 <= jhi; j0 += TQ_ROWS) {
+            const int j1 = min(j0 + TQ_ROWS - 1, jhi);
+            // ---- phase A (trackdlo.cpp:332-354, 358-375): P column entries of rows [j0, j1] -> tile; the first
+            // block also runs over the rest of the window to complete the column sum.
+            const int jend = (j0 == jlo) ? jhi : j1;
+            double colsum = 0.0;
+            {
+                double* pc = pcol;
+                int j = j0;
+                for (; j + 3 <= jend; j += 4) {
+                    const double s0 = nd[j].w, s1 = nd[j + 1].w, s2 = nd[j + 2].w, s3 = nd[j + 3].w;
+                    double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
+                    if (VIS) { v0 = vw[j]; v1 = vw[j + 1]; v2 = vw[j + 2]; v3 = vw[j + 3]; }
+                    const double t0 = (j <= lo) ? (alo - s0) : (ahi + s0);
+                    const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
+                    const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
+                    const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
+                    double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
+                    if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
+                    colsum += (p0 + p1) + (p2 + p3);
+                    if (j + 3 <= j1) { pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3; }
+                    else {
+                        if (j <= j1) pc[0] = p0;
+                        if (j + 1 <= j1) pc[RS] = p1;
+                        if (j + 2 <= j1) pc[2 * RS] = p2;
+                    }
+                    pc += 4 * RS;
+                }
+                for (; j <= jend; j++) {
+                    const double sj = nd[j].w;
+                    const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
+                    double p = exp_neg(t * t, tab);
+                    if (VIS) p *= vw[j];
+                    colsum += p;
+                    if (j <= j1) *pc = p;
+                    pc += RS;
+                }
+            }
+            if (quirk) {
+                const double pn = VIS ? vw[jq] : 1.0;
+                if (j0 == jlo) {
+                    const double tq = ahi + nd[jq].w;    // what the loop computed for row jq (jq > lo)
+                    double pq = exp_neg(tq * tq, tab);
+                    if (VIS) pq *= vw[jq];
+                    colsum += pn - pq;
+                }
+                if (jq >= j0 && jq <= j1) pcol[(jq - j0) * RS] = pn;
+            }
+            if (j0 == jlo) {
+                const double den = colsum + c_norm;      // trackdlo.cpp:379 / 382
+                w = valid ? 1.0 / den : 0.0;
+                sxx = fma(colsum * w, x * x + y * y + z * z, sxx);   // Pt1_n * |x_n|^2 (trackdlo.cpp:418)
+                wb[lane] = make_double4(w, w * x, w * y, w * z);
+            }
+            __syncwarp();
+
+            // ---- phase B (trackdlo.cpp:387-389): lane = (row r, point group g); P1 / PX of the block's rows over
+            // the warp's 32 points; groups are combined by shuffles and handed to the lanes that own the nodes.
+            const int Wb = j1 - j0 + 1;
+            const int Wp = Wb <= 8 ? 8 : (Wb <= 16 ? 16 : 32);
+            const int r = lane & (Wp - 1);
+            const double* __restrict__ prow = pt + r * RS + (lane - r);       // points [g*Wp, (g+1)*Wp)
+            const double4* __restrict__ wg = wb + (lane - r);
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            if (r < Wb) {
+#pragma unroll 4
+                for (int i = 0; i < Wp; i++) {
+                    const double p = prow[i];
+                    const double4 w4 = wg[i];
+                    b0 = fma(p, w4.x, b0); b1 = fma(p, w4.y, b1); b2 = fma(p, w4.z, b2); b3 = fma(p, w4.w, b3);
+                }
+            }
+            for (int off = Wp; off < 32; off <<= 1) {
+                b0 += __shfl_xor_sync(0xffffffffu, b0, off); b1 += __shfl_xor_sync(0xffffffffu, b1, off);
+                b2 += __shfl_xor_sync(0xffffffffu, b2, off); b3 += __shfl_xor_sync(0xffffffffu, b3, off);
+            }
+            // owner lane l holds nodes l, l+32, ...; at most one of them lies in [j0, j1]
+            const int src = (lane - j0) & 31;             // row index of the owned node inside this block, if any
+            const double o0 = __shfl_sync(0xffffffffu, b0, src), o1 = __shfl_sync(0xffffffffu, b1, src);
+            const double o2 = __shfl_sync(0xffffffffu, b2, src), o3 = __shfl_sync(0xffffffffu, b3, src);
+            const int m = j0 + src;                       // the owned node (m % 32 == lane)
+            if (src < Wb) {
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ps++)
+                    if ((m >> 5) == ps) { acc[ps][0] += o0; acc[ps][1] += o1; acc[ps][2] += o2; acc[ps][3] += o3; }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- cross-warp reduction in a fixed order (deterministic)
+    __syncthreads();
+    double* __restrict__ racc = sm.ptile;                 // [nw][Nn][4]; the P tiles are dead now
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) {
+        const int m = lane + 32 * ps;
+        if (m < Nn) {
+            double* dst = racc + ((long long)warp * Nn + m) * 4;
+            dst[0] = acc[ps][0]; dst[1] = acc[ps][1]; dst[2] = acc[ps][2]; dst[3] = acc[ps][3];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * Nn; i += nt) {
+        double v = 0.0;
+        for (int ww = 0; ww < nw; ww++) v += racc[ww * 4 * Nn + i];
+        __stcg(part_out + i, v);
+    }
+    const double sx = block_sum(sxx, sm.red);
+    if (tid == 0) __stcg(part_out + 4 * Nn, sx);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Visibility pre-pass over one chunk: per-node min squared distance to the chunk's points
+// (trackdlo.cpp:279-296).  Exact, with bounding-sphere pruning: a node whose distance to the tile's
+// sphere already exceeds the best distance found so far cannot improve it.
+// ------------------------------------------------------------------------------------------
+template <int NPASS>
+__device__ void tq_dmin_chunk(const TqSm& sm, const double* __restrict__ Xc, int n_local, int Nn, double* dmin_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const double4* __restrict__ nd = sm.node4;
+    double best[NPASS];                                   // lane owns nodes lane + 32 ps
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) best[ps] = 1e300;
+    // seed: distance to the first point of every tile of this warp (cheap upper bounds)
+    for (int base = warp * 32; base < n_local; base += nw * 32) {
+        const double cx = __ldcg(Xc + (long long)base * 3), cy = __ldcg(Xc + (long long)base * 3 + 1), cz = __ldcg(Xc + (long long)base * 3 + 2);
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ps++) {
+            const int m = lane + 32 * ps;
+            if (m < Nn) { const double4 q = nd[m]; best[ps] = fmin(best[ps], dist2(q.x, q.y, q.z, cx, cy, cz)); }
+        }
+    }
+    for (int base = warp * 32; base < n_local; base += nw * 32) {
+        const bool valid = base + lane < n_local;
+        const int n = valid ? base + lane : base;
+        const double x = __ldcg(Xc + (long long)n * 3), y = __ldcg(Xc + (long long)n * 3 + 1), z = __ldcg(Xc + (long long)n * 3 + 2);
+        const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
+        const double rho = sqrt(warp_max_pos_ub(dist2(x, y, z, cx, cy, cz) + 1e-300)) * (1.0 + 1e-9);
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ps++) {
+            const int m = lane + 32 * ps;
+            bool cand = false;
+            if (m < Nn) {
+                const double4 q = nd[m];
+                const double dcn = sqrt(dist2(q.x, q.y, q.z, cx, cy, cz));
+                const double lb = dcn - rho;                                 // every point of the tile is at least this far
+                cand = !(lb > 0.0 && lb * lb * (1.0 - 1e-9) > best[ps]);
+            }
+            unsigned mk = __ballot_sync(0xffffffffu, cand);
+            while (mk) {
+                const int l = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const double4 q = nd[l + 32 * ps];
+                const double d2 = dist2(q.x, q.y, q.z, x, y, z);            // idle lanes shadow point 0: harmless for a min
+                const unsigned hi = (unsigned)__double2hiint(d2);
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned lw = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
+                const unsigned ml = __reduce_min_sync(0xffffffffu, lw);
+                if (lane == l) best[ps] = fmin(best[ps], __hiloint2double((int)mh, (int)ml));
+            }
+        }
+    }
+    __syncthreads();
+    double* wmin = sm.ptile;                              // [nw][Nn]
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ps++) { const int m = lane + 32 * ps; if (m < Nn) wmin[warp * Nn + m] = best[ps]; }
+    __syncthreads();
+    for (int j = tid; j < Nn; j += nt) {
+        double m = wmin[j];
+        for (int w = 1; w < nw; w++) m = fmin(m, wmin[w * Nn + j]);
+        __stcg(dmin_out + j, m);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// frame helpers
+// ------------------------------------------------------------------------------------------
+struct TqFrame {
+    int f;
+    double* scr; TqScr sc; int* ctl; double* scal;
+    int gbase;               // first global chunk id of the frame
+    const double* Xraw; double* Xc; long long m0;
+};
+__device__ __forceinline__ TqFrame tq_frame(const TqArgs& a, int f) {
+    TqFrame fr;
+    fr.f = f;
+    fr.sc = tq_scr_layout(a.k.scr_nodes);
+    fr.scr = a.fscratch + (long long)f * a.fstride;
+    fr.ctl = reinterpret_cast<int*>(fr.scr + fr.sc.CTL);
+    fr.scal = fr.scr + fr.sc.SCAL;
+    fr.gbase = tq_chunk_base(a, f);
+    const long long x0 = a.k.x_off[f];
+    fr.m0 = a.k.x_off[f + 1] - x0;
+    fr.Xraw = a.k.X + x0 * 3;
+    fr.Xc = a.k.Xc + x0 * 3;
+    return fr;
+}
+__device__ __forceinline__ const CpdP& tq_params(const TqArgs& a, int stage) { return (a.k.mode == 1 && stage == 1) ? a.k.p1 : a.k.p0; }
+
+// global in/out node array of the current call
+__device__ __forceinline__ double* tq_yio(const TqArgs& a, const TqFrame& fr, int stage) {
+    if (a.k.mode == 0) return a.k.Y + (long long)fr.f * a.k.node_stride * 3;
+    if (stage == 0) return a.k.guide_out ? a.k.guide_out + (long long)fr.f * a.k.node_stride * 3 : fr.scr + fr.sc.GUIDE;
+    return a.k.Y + (long long)fr.f * a.k.node_stride * 3;
+}
+__device__ __forceinline__ double* tq_pri(const TqArgs& a, const TqFrame& fr) {
+    return a.k.priors_out ? a.k.priors_out + (long long)fr.f * 2 * a.k.node_stride * 4 : fr.scr + fr.sc.PRI;
+}
+
+// ------------------------------------------------------------------------------------------
+// start_call: set-up of one cpd_lle call (trackdlo.cpp:197-260) + publication of its PRUNE wave.
+// Returns the next action for this CTA.
+// ------------------------------------------------------------------------------------------
+__device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int stage) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const KArgs& k = a.k;
+    const CpdP& p = tq_params(a, stage);
+    const int f = fr.f;
+    double* scr = fr.scr;
+    const TqScr& sc = fr.sc;
+    int Nn, n_priors = 0, n_visible = 0;
+    const double* priors = nullptr;
+    const double* Hext = nullptr;
+    int hstride = k.node_stride;
+    if (k.mode == 0) {
+        Nn = k.n_nodes ? k.n_nodes[f] : k.node_stride;
+        const long long ys = (long long)f * k.node_stride;
+        priors = k.priors ? k.priors + ys * 4 : nullptr;
+        n_priors = (k.priors && k.n_priors) ? k.n_priors[f] : 0;
+        n_visible = k.n_visible ? k.n_visible[f] : 0;
+        Hext = k.H ? k.H + ys * k.node_stride : nullptr;
+    } else {
+        const int V = (int)(k.ext_off[f + 1] - k.ext_off[f]);
+        if (stage == 0) {
+            Nn = V;
+            Hext = k.H ? k.H + (long long)f * k.node_stride * k.node_stride : nullptr;
+            // guide nodes (trackdlo.cpp:913-921)
+            const int* ext = k.ext + k.ext_off[f];
+            const double* Yf = k.Y + (long long)f * k.node_stride * 3;
+            double* guide = tq_yio(a, fr, 0);
+            for (int i = tid; i < 3 * V; i += nt) {
+                const int r = i / 3, d = i - 3 * r;
+                guide[i] = (V != k.node_stride) ? Yf[ext[r] * 3 + d] : Yf[i];
+            }
+            __syncthreads();
+        } else {
+            Nn = k.node_stride;
+            priors = tq_pri(a, fr);
+            n_priors = __ldcg(fr.ctl + FC_NPRI);
+            n_visible = V;
+        }
+    }
+    const double* Yio = tq_yio(a, fr, stage);
+    const int n_chunks = (int)((fr.m0 + a.chunk - 1) / a.chunk);
+    if (tid == 0) {
+        fr.ctl[FC_STAGE] = stage; fr.ctl[FC_ITER] = 0; fr.ctl[FC_NN] = Nn; fr.ctl[FC_NCHUNK] = n_chunks;
+        fr.ctl[FC_USEVIS] = (n_visible != Nn) && (n_visible > 0) && (p.k_vis != 0);    // trackdlo.cpp:358
+        fr.ctl[FC_NPRI] = n_priors; fr.ctl[FC_STATUS] = 0; fr.ctl[FC_NVIS] = n_visible;
+        fr.ctl[FC_PHASE] = TK_PRUNE; fr.ctl[FC_PENDING] = n_chunks + 1;
+        fr.scal[FS_SIGMA2] = k.sigma2[f];
+    }
+    if (Nn < 4) {                          // reference indexes rows 2 and Nn-3 (trackdlo.cpp:313-321)
+        if (tid == 0) fr.ctl[FC_STATUS] = ST_TOO_FEW_NODES;
+        __syncthreads();
+        return A_FINISH_CALL;
+    }
+    // ---- Y0, current Y (node4), arc-length coordinates (trackdlo.cpp:203, 216-223)
+    double* gY0 = scr + sc.Y0;
+    double* gS = scr + sc.S;
+    double* gN4 = scr + sc.NODE4;
+    for (int i = tid; i < 3 * Nn; i += nt) { const double v = Yio[i]; sm.y0[i] = v; gY0[i] = v; }
+    __syncthreads();
+    for (int j = tid; j < Nn; j += nt) { gN4[4 * j] = sm.y0[3 * j]; gN4[4 * j + 1] = sm.y0[3 * j + 1]; gN4[4 * j + 2] = sm.y0[3 * j + 2]; gN4[4 * j + 3] = 0.0; }
+    if (tid == 0) {
+        double cur = 0.0;
+        sm.s[0] = 0.0;
+        for (int i = 0; i < Nn - 1; i++) {
+            cur += sqrt(dist2(sm.y0[3 * i + 3], sm.y0[3 * i + 4], sm.y0[3 * i + 5], sm.y0[3 * i], sm.y0[3 * i + 1], sm.y0[3 * i + 2]));
+            sm.s[i + 1] = cur;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < Nn; j += nt) gS[j] = sm.s[j];
+    // the PRUNE wave only needs node4: publish it now, do the rest of the set-up meanwhile
+    tq_push(a, sm, TK_PRUNE, f, n_chunks);
+
+    // ---- G, priors, LLE products (trackdlo.cpp:225-260)
+    double* gG = scr + sc.G;
+    double* gHG = scr + sc.HG;
+    double* gH = scr + sc.H;
+    const double beta = p.beta;
+    for (int idx = tid; idx < Nn * Nn; idx += nt) {
+        const int i = idx / Nn, j = idx - i * Nn;
+        const double dd = fabs(sm.s[i] - sm.s[j]);
+        gG[idx] = 1 / (2 * beta * 2 * beta) * exp(-sqrt(2.0) * dd / beta) * (2 * dd + sqrt(2.0) * beta);
+    }
+    double* gJD = scr + sc.JD;
+    double* gYE = scr + sc.YEXT;
+    for (int i = tid; i < Nn; i += nt) gJD[i] = 0.0;
+    for (int i = tid; i < 3 * Nn; i += nt) gYE[i] = sm.y0[i];
+    __syncthreads();
+    if (tid == 0) {
+        for (int kk = 0; kk < n_priors; kk++) {
+            const int idx = (int)priors[kk * 4];               // trackdlo.cpp:247
+            if (idx < 0 || idx >= Nn) continue;
+            gJD[idx] = 1.0;
+            gYE[idx * 3] = priors[kk * 4 + 1]; gYE[idx * 3 + 1] = priors[kk * 4 + 2]; gYE[idx * 3 + 2] = priors[kk * 4 + 3];
+        }
+    }
+    if (p.include_lle) {
+        if (Hext) {
+            for (int idx = tid; idx < Nn * Nn; idx += nt) { const int i = idx / Nn, j = idx - i * Nn; gH[idx] = Hext[(long long)i * hstride + j]; }
+        } else {
+            double* E = scr + sc.AB;                              // dense E = I - L
+            for (int idx = tid; idx < Nn * Nn; idx += nt) E[idx] = 0.0;
+            __syncthreads();
+            for (int i = tid; i < Nn; i += nt) lle_row(sm.y0, Nn, i, E + (long long)i * Nn);
+            __syncthreads();
+            for (int idx = tid; idx < Nn * Nn; idx += nt) {        // H = E^T E, k ascending, band only
+                const int r = idx / Nn, c = idx - r * Nn;
+                double s = 0.0;
+                int klo = (r > c ? r : c) - 3, khi = (r < c ? r : c) + 3;
+                if (klo < 0) klo = 0;
+                if (khi > Nn - 1) khi = Nn - 1;
+                for (int kk = klo; kk <= khi; kk++) s = __dadd_rn(s, __dmul_rn(E[(long long)kk * Nn + r], E[(long long)kk * Nn + c]));
+                gH[idx] = s;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < Nn * Nn; idx += nt) {            // HG = H G
+            const int i = idx / Nn, j = idx - i * Nn;
+            double s = 0.0;
+            for (int kk = 0; kk < Nn; kk++) s = fma(gH[(long long)i * Nn + kk], gG[(long long)kk * Nn + j], s);
+            gHG[idx] = s;
+        }
+        double* gHY = scr + sc.HY0;
+        for (int idx = tid; idx < 3 * Nn; idx += nt) {             // H Y0
+            const int i = idx / 3, d = idx - 3 * i;
+            double s = 0.0;
+            for (int kk = 0; kk < Nn; kk++) s = fma(gH[(long long)i * Nn + kk], sm.y0[3 * kk + d], s);
+            gHY[idx] = s;
+        }
+    }
+    return tq_arrive(sm, fr.ctl) ? A_AFTER_PRUNE : A_NONE;
+}
+
+// ------------------------------------------------------------------------------------------
+// after_prune: gather the kept counts, sigma2 init (trackdlo.cpp:263-273)
+// ------------------------------------------------------------------------------------------
+__device__ int tq_after_prune(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+    const int tid = threadIdx.x;
+    const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
+    const CpdP& p = tq_params(a, stage);
+    if (tid == 0) {
+        long long Mp = 0;
+        double sumd2 = 0.0;
+        for (int c = 0; c < n_chunks; c++) { Mp += __ldcg(a.nkept + fr.gbase + c); sumd2 += __ldcg(a.gath + fr.gbase + c); }
+        double sigma2 = __ldcg(fr.scal + FS_SIGMA2);
+        if (Mp > 0 && sigma2 == 0) sigma2 = sumd2 / (3.0 * (double)Nn * (double)Mp);   // trackdlo.cpp:271-273
+        fr.scal[FS_SIGMA2] = sigma2;
+        fr.scal[FS_MP] = (double)Mp;
+        sm.bcast[1] = Mp > 0;
+    }
+    __syncthreads();
+    const bool nonempty = sm.bcast[1] != 0;
+    __syncthreads();
+    if (!nonempty) { if (tid == 0) fr.ctl[FC_STATUS] = ST_EMPTY; __syncthreads(); return A_FINISH_CALL; }
+    if (p.max_iter <= 0) return A_FINISH_CALL;
+    return A_BEGIN_ITER;
+}
+
+// ------------------------------------------------------------------------------------------
+// begin_iter: per-iteration header (scaled arc lengths, outlier constant) and the next wave
+// ------------------------------------------------------------------------------------------
+__device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
+    const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
+    const CpdP& p = tq_params(a, stage);
+    const double sigma2 = __ldcg(fr.scal + FS_SIGMA2), Mp = __ldcg(fr.scal + FS_MP);
+    const double rscale = sqrt(0.5 / sigma2);
+    double* gN4 = fr.scr + fr.sc.NODE4;
+    const double* gS = fr.scr + fr.sc.S;
+    for (int j = tid; j < Nn; j += nt) gN4[4 * j + 3] = __ldcg(gS + j) * rscale;
+    if (tid == 0) {
+        const double c_gauss = pow(2 * M_PI * sigma2, 1.5) * p.mu / (1 - p.mu);
+        fr.scal[FS_RSCALE] = rscale;
+        fr.scal[FS_CGAUSS] = c_gauss;
+        fr.scal[FS_CNORM] = use_vis ? c_gauss / Mp : c_gauss * (double)Nn / Mp;       // trackdlo.cpp:378 / 300
+        fr.ctl[FC_PHASE] = use_vis ? TK_DMIN : TK_ESTEP;
+        fr.ctl[FC_PENDING] = n_chunks;
+    }
+    tq_push(a, sm, use_vis ? TK_DMIN : TK_ESTEP, fr.f, n_chunks);
+    return A_NONE;
+}
+
+// after_dmin: visibility weights (trackdlo.cpp:291-293, 358-375), then the E-step wave
+__device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
+    const CpdP& p = tq_params(a, stage);
+    const int N = a.k.scr_nodes;
+    for (int j = tid; j < Nn; j += nt) {
+        double m = 1e300;
+        for (int c = 0; c < n_chunks; c++) m = fmin(m, __ldcg(a.dminp + (long long)(fr.gbase + c) * N + j));
+        double dm = sqrt(m);
+        if (dm <= p.tau) dm = 0.0;                              // trackdlo.cpp:291-293
+        sm.vw[j] = exp(-p.k_vis * dm);                          // trackdlo.cpp:365
+    }
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int j = 0; j < Nn; j++) t += sm.vw[j]; sm.red[40] = t; }
+    __syncthreads();
+    const double tot = sm.red[40];
+    double* gVW = fr.scr + fr.sc.VW;
+    for (int j = tid; j < Nn; j += nt) gVW[j] = sm.vw[j] / tot;      // trackdlo.cpp:372
+    if (tid == 0) { fr.ctl[FC_PHASE] = TK_ESTEP; fr.ctl[FC_PENDING] = n_chunks; }
+    tq_push(a, sm, TK_ESTEP, fr.f, n_chunks);
+    return A_NONE;
+}
+
+// ------------------------------------------------------------------------------------------
+// m_step (trackdlo.cpp:392-438): run by the CTA that completed the frame's E-step wave.
+// ------------------------------------------------------------------------------------------
+__device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
+    const int it = __ldcg(fr.ctl + FC_ITER);
+    int status = __ldcg(fr.ctl + FC_STATUS);
+    const bool have_priors = __ldcg(fr.ctl + FC_NPRI) > 0;
+    const CpdP& p = tq_params(a, stage);
+    const double sigma2 = __ldcg(fr.scal + FS_SIGMA2);
+    const TqScr& sc = fr.sc;
+    double* scr = fr.scr;
+    const double* gG = scr + sc.G;
+    const double* gHG = scr + sc.HG;
+    const int ld = Nn + 3;
+    const bool ab_in_smem = (long long)Nn * ld <= (long long)a.L.ab_doubles;
+    double* AB = ab_in_smem ? sm.ab : scr + sc.AB;
+
+    // ---- frame vectors -> shared; partial sums in chunk order
+    for (int i = tid; i < 3 * Nn; i += nt) {
+        sm.y0[i] = __ldcg(scr + sc.Y0 + i);
+        if (have_priors) sm.yext[i] = __ldcg(scr + sc.YEXT + i);
+        if (p.include_lle) sm.hy0[i] = __ldcg(scr + sc.HY0 + i);
+    }
+    for (int i = tid; i < Nn; i += nt) {
+        sm.jd[i] = have_priors ? __ldcg(scr + sc.JD + i) : 0.0;
+        const double4 q = ldcg4(reinterpret_cast<const double4*>(scr + sc.NODE4) + i);
+        sm.node4[i] = q;
+    }
+    for (int i = tid; i < 4 * Nn; i += nt) {
+        double v = 0.0;
+        for (int c = 0; c < n_chunks; c++) v += __ldcg(a.part + (long long)(fr.gbase + c) * a.part_stride + i);
+        const int m = i >> 2, kk = i & 3;
+        if (kk == 0) sm.p1[m] = v; else sm.px[3 * m + kk - 1] = v;
+    }
+    double sxx = 0.0;
+    for (int c = 0; c < n_chunks; c++) sxx += __ldcg(a.part + (long long)(fr.gbase + c) * a.part_stride + 4 * Nn);
+    __syncthreads();
+
+    // ---- assemble [A | B] (trackdlo.cpp:392-413); SPD form without LLE (see cpd_run)
+    const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
+    const bool small = ab_in_smem && Nn <= 64;
+    const bool spd = !p.include_lle && small;
+    if (spd) {
+        for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
+        __syncthreads();
+    }
+    for (int idx = tid; idx < Nn * Nn; idx += nt) {
+        const int i = idx / Nn, j = idx - i * Nn;
+        const double g = __ldcg(gG + idx);
+        double v;
+        if (spd) v = sm.tnew[i] * g * sm.tnew[j] + (i == j ? ls : 0.0);
+        else {
+            v = sm.p1[i] * g + (i == j ? ls : 0.0);
+            if (p.include_lle) v += sg * __ldcg(gHG + idx);
+            if (have_priors) v += p.alpha * sm.jd[i] * g;
+        }
+        AB[(long long)i * ld + j] = v;
+    }
+    for (int idx = tid; idx < 3 * Nn; idx += nt) {
+        const int i = idx / 3;
+        double v = sm.px[idx] - sm.p1[i] * sm.y0[idx];
+        if (p.include_lle) v -= sg * sm.hy0[idx];
+        if (have_priors) v += p.alpha * (sm.yext[idx] - sm.y0[idx]);
+        if (spd) { const double sd = sm.tnew[i]; v = sd > 0.0 ? v / sd : 0.0; }
+        AB[(long long)i * ld + Nn + (idx - 3 * i)] = v;
+    }
+    __syncthreads();
+    int sing;
+    if (small) {
+        double sdreg[3];
+        if (spd) for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sdreg[t] = sm.tnew[i / 3];
+        sing = gj_solve_small(sm.ab, Nn, ld, sm.gjbuf, sm.prow, sm.wsol, !spd, nullptr);
+        if (spd) {
+            for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
+            __syncthreads();
+        }
+    } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
+    if (sing) status |= ST_SINGULAR;
+
+    // ---- T = Y0 + G W (trackdlo.cpp:417)
+    for (int i = warp; i < Nn; i += nw) {
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int kk = lane; kk < Nn; kk += 32) {
+            const double g = __ldcg(gG + (long long)i * Nn + kk);
+            ax = fma(g, sm.wsol[3 * kk], ax); ay = fma(g, sm.wsol[3 * kk + 1], ay); az = fma(g, sm.wsol[3 * kk + 2], az);
+        }
+        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+        if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
+    }
+    __syncthreads();
+    // ---- sigma2 update and convergence test (trackdlo.cpp:418-431)
+    if (warp == 0) {
+        double np = 0.0, trPXT = 0.0, trTPT = 0.0, moved = 0.0;
+        for (int m = lane; m < Nn; m += 32) {
+            const double tx = sm.tnew[3 * m], ty = sm.tnew[3 * m + 1], tz = sm.tnew[3 * m + 2];
+            const double p1 = sm.p1[m];
+            np += p1;
+            trPXT += sm.px[3 * m] * tx + sm.px[3 * m + 1] * ty + sm.px[3 * m + 2] * tz;
+            trTPT += p1 * (tx * tx + ty * ty + tz * tz);
+            const double4 yc = sm.node4[m];
+            moved += sqrt(dist2(yc.x, yc.y, yc.z, tx, ty, tz));
+        }
+        np = warp_sum(np); trPXT = warp_sum(trPXT); trTPT = warp_sum(trTPT); moved = warp_sum(moved);
+        if (lane == 0) {
+            const double s2new = (sxx - 2 * trPXT + trTPT) / (np * 3);
+            const bool done = (moved / Nn) < p.tol;
+            int fin = 0;
+            if (done) fin = 1;
+            else if (it == p.max_iter - 1) { fin = 1; status |= ST_NOT_CONVERGED; }
+            fr.scal[FS_SIGMA2] = s2new;
+            fr.ctl[FC_STATUS] = status;
+            fr.ctl[FC_ITER] = it + 1;
+            sm.bcast[1] = fin;
+        }
+    }
+    double* gN4 = scr + sc.NODE4;
+    for (int j = tid; j < Nn; j += nt) { gN4[4 * j] = sm.tnew[3 * j]; gN4[4 * j + 1] = sm.tnew[3 * j + 1]; gN4[4 * j + 2] = sm.tnew[3 * j + 2]; }
+    for (int i = tid; i < 3 * Nn; i += nt) scr[sc.WSOL + i] = sm.wsol[i];
+    __syncthreads();
+    const int fin = sm.bcast[1];
+    __syncthreads();
+    return fin ? A_FINISH_CALL : A_BEGIN_ITER;
+}
+
+// ------------------------------------------------------------------------------------------
+// finish_call: results of one cpd_lle call; in tracking mode the glue between the pre-processing and the
+// main registration (trackdlo.cpp:929-998).
+// ------------------------------------------------------------------------------------------
+__device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int& next_stage) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const KArgs& k = a.k;
+    const int f = fr.f;
+    const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN);
+    const int status = __ldcg(fr.ctl + FC_STATUS), iters = __ldcg(fr.ctl + FC_ITER);
+    const CpdP& p = tq_params(a, stage);
+    const bool ran = !(status & (ST_TOO_FEW_NODES | ST_EMPTY));
+    double* Yio = tq_yio(a, fr, stage);
+    const double* gN4 = fr.scr + fr.sc.NODE4;
+    if (ran) for (int i = tid; i < 3 * Nn; i += nt) Yio[i] = __ldcg(gN4 + 4 * (i / 3) + (i % 3));
+    if (k.mode == 0) {
+        if (ran && k.W && p.max_iter > 0) for (int i = tid; i < 3 * Nn; i += nt) k.W[(long long)f * k.node_stride * 3 + i] = __ldcg(fr.scr + fr.sc.WSOL + i);
+        if (tid == 0) {
+            if (ran) k.sigma2[f] = __ldcg(fr.scal + FS_SIGMA2);
+            if (k.iters) k.iters[f] = ran ? iters : 0;
+            if (k.status) k.status[f] = status;
+        }
+        return A_FRAME_DONE;
+    }
+    const int N = k.node_stride;
+    if (stage == 0) {
+        if (tid == 0 && k.iters) k.iters[2 * f] = ran ? iters : 0;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int st = 0;
+            if (status & ST_NOT_CONVERGED) st |= ST_PRE_NOT_CONVERGED;
+            st |= status & ~ST_NOT_CONVERGED;
+            const int* vis = k.vis + k.vis_off[f];
+            const int nvis = (int)(k.vis_off[f + 1] - k.vis_off[f]);
+            const int* ext = k.ext + k.ext_off[f];
+            const int V = Nn;
+            const double* guide = Yio;
+            const double* Yf = k.Y + (long long)f * N * 3;
+            const double* geo = k.rest + (long long)f * N;
+            double* pri = tq_pri(a, fr);
+            int err = 0, state = 0, np = 0;
+            double* trv = fr.scr + fr.sc.TRV;
+            if (!ran) {
+                state = -1;
+            } else if (V == N) {
+                state = 0;
+                double* v1 = trv;
+                double* v2 = trv + (N + 2) * 4;
+                const int n1 = traverse_euclidean(geo, N, guide, V, ext, V, 0, -1, v1, &err);
+                const int n2 = traverse_euclidean(geo, N, guide, V, ext, V, 1, -1, v2, &err);
+                // v2 is emitted tail -> head; the reference reverses it (trackdlo.cpp:942): v2r[j] = v2[n2-1-j]
+                for (int i = 0; i < N; i++) {
+                    const int j2 = i - (N - n2);
+                    const double* first2 = v2 + (n2 - 1) * 4;
+                    if (i < first2[0] && i < n1) { for (int t = 0; t < 4; t++) pri[np * 4 + t] = v1[i * 4 + t]; np++; }
+                    else if (i > v1[(n1 - 1) * 4] && j2 >= 0 && j2 < n2) {
+                        const double* s2 = v2 + (n2 - 1 - j2) * 4;
+                        for (int t = 0; t < 4; t++) pri[np * 4 + t] = s2[t];
+                        np++;
+                    } else if (i < n1 && j2 >= 0 && j2 < n2) {
+                        const double* s2 = v2 + (n2 - 1 - j2) * 4;
+                        for (int t = 0; t < 4; t++) pri[np * 4 + t] = (v1[i * 4 + t] + s2[t]) / 2.0;
+                        np++;
+                    } else err |= 4;
+                }
+            } else if (ext[0] == 0 && ext[V - 1] == N - 1) {
+                state = 1;
+                np = traverse_euclidean(geo, N, guide, V, ext, V, 0, -1, pri, &err);
+                np += traverse_euclidean(geo, N, guide, V, ext, V, 1, -1, pri + np * 4, &err);
+            } else if (ext[0] == 0) {
+                state = 2;
+                np = traverse_euclidean(geo, N, guide, V, ext, V, 0, -1, pri, &err);
+            } else if (ext[V - 1] == N - 1) {
+                state = 3;
+                np = traverse_euclidean(geo, N, guide, V, ext, V, 1, -1, pri, &err);
+            } else {
+                state = 4;
+                int align = -1;
+                double moved = 999999;
+                for (int i = 0; i < nvis; i++) {
+                    if (i >= V) { err |= 8; break; }
+                    const double dd = vdist(ld3(Yf, vis[i]), ld3(guide, i));
+                    if (dd < moved) { moved = dd; align = i; }
+                }
+                np = traverse_euclidean(geo, N, guide, V, ext, V, 2, align, pri, &err);
+            }
+            if (err) st |= ST_TRAVERSE_UB;
+            if (k.state_out) k.state_out[f] = state;
+            if (k.n_priors_out) k.n_priors_out[f] = np;
+            fr.ctl[FC_NPRI] = np;
+            fr.ctl[FC_STPRE] = st;
+            sm.bcast[1] = ran;
+            __threadfence();
+        }
+        __syncthreads();
+        const bool go = sm.bcast[1] != 0;
+        __syncthreads();
+        if (go) { next_stage = 1; return A_START_CALL; }
+        if (tid == 0) { if (k.status) k.status[f] = __ldcg(fr.ctl + FC_STPRE); if (k.iters) k.iters[2 * f + 1] = 0; }
+        return A_FRAME_DONE;
+    }
+    // stage 1: main registration done
+    if (ran && k.W && p.max_iter > 0) for (int i = tid; i < 3 * Nn; i += nt) k.W[(long long)f * N * 3 + i] = __ldcg(fr.scr + fr.sc.WSOL + i);
+    if (tid == 0) {
+        if (ran) k.sigma2[f] = __ldcg(fr.scal + FS_SIGMA2);
+        if (k.iters) k.iters[2 * f + 1] = ran ? iters : 0;
+        if (k.status) k.status[f] = status | __ldcg(fr.ctl + FC_STPRE);
+    }
+    return A_FRAME_DONE;
+}
+
+// ------------------------------------------------------------------------------------------
+// The persistent kernel
+// ------------------------------------------------------------------------------------------
+template <int NPASS, int MINB>
+__global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(const TqArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const TqSmemL& L = a.L;
+    TqSm sm;
+    sm.tab = reinterpret_cast<double*>(smem_raw + L.tab);
+    sm.node4 = reinterpret_cast<double4*>(smem_raw + L.node4);
+    sm.vw = reinterpret_cast<double*>(smem_raw + L.vw);
+    sm.bcast = reinterpret_cast<int*>(smem_raw + L.bcast);
+    sm.red = reinterpret_cast<double*>(smem_raw + L.red);
+    sm.wbuf = reinterpret_cast<double4*>(smem_raw + L.wbuf);
+    sm.ptile = reinterpret_cast<double*>(smem_raw + L.ptile);
+    sm.y0 = reinterpret_cast<double*>(smem_raw + L.y0);
+    sm.s = reinterpret_cast<double*>(smem_raw + L.s);
+    sm.yext = reinterpret_cast<double*>(smem_raw + L.yext);
+    sm.jd = reinterpret_cast<double*>(smem_raw + L.jd);
+    sm.hy0 = reinterpret_cast<double*>(smem_raw + L.hy0);
+    sm.p1 = reinterpret_cast<double*>(smem_raw + L.p1);
+    sm.px = reinterpret_cast<double*>(smem_raw + L.px);
+    sm.wsol = reinterpret_cast<double*>(smem_raw + L.wsol);
+    sm.tnew = reinterpret_cast<double*>(smem_raw + L.tnew);
+    sm.gjbuf = reinterpret_cast<double*>(smem_raw + L.gjbuf);
+    sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
+    sm.used = reinterpret_cast<int*>(smem_raw + L.used);
+    sm.ab = reinterpret_cast<double*>(smem_raw + L.ab);
+    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];
+    __syncthreads();
+
+    int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [2] frames done
+    int action = A_NONE, af = 0, astage = 0;
+    if ((int)blockIdx.x < a.inflight && (int)blockIdx.x < a.k.n_frames) { action = A_START_CALL; af = blockIdx.x; astage = 0; }
+
+    for (;;) {
+        // ---- continuations owned by this CTA
+        while (action != A_NONE) {
+            const TqFrame fr = tq_frame(a, af);
+            switch (action) {
+                case A_START_CALL: action = tq_start_call(a, sm, fr, astage); break;
+                case A_AFTER_PRUNE: action = tq_after_prune(a, sm, fr); break;
+                case A_BEGIN_ITER: action = tq_begin_iter(a, sm, fr); break;
+                case A_AFTER_DMIN: action = tq_after_dmin(a, sm, fr); break;
+                case A_MSTEP: action = tq_mstep(a, sm, fr); break;
+                case A_FINISH_CALL: action = tq_finish_call(a, sm, fr, astage); break;
+                case A_FRAME_DONE: {
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        const int nf = atomicAdd(qi, 1);
+                        const int done = atomicAdd(qi + 2, 1) + 1;
+                        sm.bcast[1] = nf < a.k.n_frames ? nf : -1;
+                        sm.bcast[2] = done == a.k.n_frames;
+                    }
+                    __syncthreads();
+                    const int nf = sm.bcast[1];
+                    const bool all = sm.bcast[2] != 0;
+                    __syncthreads();
+                    if (all) tq_push(a, sm, TK_EXIT, 0, gridDim.x);
+                    if (nf >= 0) { action = A_START_CALL; af = nf; astage = 0; }
+                    else action = A_NONE;
+                    break;
+                }
+                default: action = A_NONE;
+            }
+        }
+        // ---- next task
+        const unsigned long long wd = tq_pop(a, sm);
+        const int type = (int)((wd >> 37) & 7), f = (int)((wd >> 20) & 0x1ffff), c = (int)(wd & 0xfffff);
+        if (type == TK_EXIT) break;
+        const TqFrame fr = tq_frame(a, f);
+        const int Nn = __ldcg(fr.ctl + FC_NN);
+        const int g = fr.gbase + c;
+        const long long r0 = (long long)c * a.chunk;
+        const long long r1 = r0 + a.chunk < fr.m0 ? r0 + a.chunk : fr.m0;
+        for (int j = tid; j < Nn; j += nt) sm.node4[j] = ldcg4(reinterpret_cast<const double4*>(fr.scr + fr.sc.NODE4) + j);
+        __syncthreads();
+        if (type == TK_PRUNE) {
+            const int stage = __ldcg(fr.ctl + FC_STAGE);
+            Smem os;                                              // view for prune_sort_slice (cluster engine helper)
+            os.node4 = sm.node4; os.ptile = sm.ptile; os.red = sm.red;
+            double sum_local;
+            const int kept = prune_sort_slice(os, fr.Xraw, r0, r1, fr.Xc, a.k.bkt + (fr.Xraw - a.k.X) / 3, Nn,
+                                              tq_params(a, stage).prune_radius, &sum_local);
+            if (tid == 0) { __stcg(a.nkept + g, kept); __stcg(a.gath + g, sum_local); }
+        } else if (type == TK_DMIN) {
+            tq_dmin_chunk<NPASS>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, a.dminp + (long long)g * a.k.scr_nodes);
+        } else {
+            const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
+            const double sigma2 = __ldcg(fr.scal + FS_SIGMA2), c_norm = __ldcg(fr.scal + FS_CNORM), rscale = __ldcg(fr.scal + FS_RSCALE);
+            double* part = a.part + (long long)g * a.part_stride;
+            if (use_vis) {
+                for (int j = tid; j < Nn; j += nt) sm.vw[j] = __ldcg(fr.scr + fr.sc.VW + j);
+                __syncthreads();
+                tq_estep_chunk<NPASS, true>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part);
+            } else {
+                tq_estep_chunk<NPASS, false>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part);
+            }
+        }
+        if (tq_arrive(sm, fr.ctl)) {
+            af = f;
+            action = type == TK_PRUNE ? A_AFTER_PRUNE : (type == TK_DMIN ? A_AFTER_DMIN : A_MSTEP);
+        }
+    }
+}
+
+}  // namespace tdlo
