@@ -34,6 +34,20 @@ METRIC, UNIT = "em_iterations_per_sec", "EM iterations/s"
 WORKLOAD = ("C2: 64 frames/GPU x tracking_step (pre-proc cpd_lle with LLE + traverse_euclidean + main cpd_lle), "
             "Nn=50, Mp=20000, max_iter=50, tol=0 -> 100 EM iterations per frame")
 FP64_PEAK_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz; not in MEASURED_PEAKS.json
+FP64_PEAK_MEASURED_TFLOPS = 33.0    # dependent-free DFMA loop on this pool's B200 (scripts/micro/fp64pipe.cu,
+                                    # profiles/r1_fp64pipe_microbench.txt); DMMA shares the same pipe (37 TF/s alone)
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the persistent kernel from the committed ncu --set full
+    capture of this same command (profiles/ncu_traffic.json), per launch; None if no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
 
 
 def algorithmic_work(n_nodes, mp_raw, mp_kept, iters):
@@ -294,12 +308,17 @@ def run_ours(args):
         fp64 = None
         if kern_s:
             ach = alg_b / kern_s / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src, "kernel": "tdlo_em_kernel<2,2> (one persistent launch per step; E-step = %d%% of its FP64 work)" % 97,
-                    "note": "kernel is FP64-pipe bound (52 flop/B at Nn=50), not HBM bound; see `fp64`"}
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic_bytes(),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_b,
+                    "kernel": "tdlo_tq_kernel<2,3> (one persistent task-queue launch per step: prune, E-step chunks, M-steps, traversal)",
+                    "note": "the path is 52 flop/B at Nn=50 (SURVEY.md §8d): compute-side bound, HBM fraction is tiny by construction; "
+                            "see `fp64` for the FP64-pipe fraction and profiles/ for the shared-memory (MIO) pipe that limits the E-step"}
             tf = alg_f / kern_s / 1e12
-            fp64 = {"achieved": tf, "peak": FP64_PEAK_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_NOMINAL_TFLOPS,
-                    "peak_source": "nominal 148 SM x 64 lanes x 2 x 1.965 GHz", "flop_model": "SURVEY.md §8d: 25*Nn*Mp per frame.iteration"}
+            fp64 = {"achieved": tf, "peak": FP64_PEAK_MEASURED_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_MEASURED_TFLOPS,
+                    "peak_source": "measured DFMA loop (scripts/micro/fp64pipe.cu -> profiles/r1_fp64pipe_microbench.txt)",
+                    "frac_of_nominal": tf / FP64_PEAK_NOMINAL_TFLOPS, "nominal_peak": FP64_PEAK_NOMINAL_TFLOPS,
+                    "flop_model": "ALGORITHMIC flop, SURVEY.md §8d: 25*Nn*Mp per frame.iteration (+18*Nn*Mp0 per call); the kernel "
+                                  "skips affinity entries below exp(-z_cut) (exact zeros / far below one ulp), so executed flop are fewer"}
         cpu = cpu_baseline_single_core(wl["frames"]) if world == 1 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -58,6 +58,15 @@ for c in clusters:
     info = ctx.launch_info()
     print(f"mode={mode} F={F} Nn={NODES} Mp={POINTS} cluster={info['cluster_size']} ctas={info['ctas']} tile={info['tile_points']} occ={info['ctas_per_sm']}: "
           f"{ms:.2f} ms  {iters/ms*1e3:.0f} it/s  {F/ms*1e3:.0f} frames/s")
+    if engine == "tq":
+        v = list(ph["rank0"].values()) + list(ph["others"].values())
+        names = ("wait", "prune", "dmin", "estep", "start_call", "glue", "m_assemble", "m_solve", "m_update", "finish")
+        tot = sum(v[:10]) or 1
+        print("    phases", {n: f"{x/tot*100:.1f}%" for n, x in zip(names, v[:10])}, f"total {tot/3/1e6:.1f} Mcyc/run over {info['ctas']} CTAs")
+        if v[11]:
+            print(f"    estep tasks/run {v[10]/3:.0f}  tiles/run {v[11]/3:.0f}  avg window {v[12]/v[11]:.1f} nodes  blocks/tile {v[13]/v[11]:.2f}"
+                  f"  cycles/estep-task {v[3]/max(v[10],1):.0f}  cycles/msolve {v[7]*1.0/max(iters*3,1):.0f} assemble {v[6]/max(iters*3,1):.0f} update {v[8]/max(iters*3,1):.0f}")
+        continue
     for k in ("rank0", "others"):
         tot = sum(ph[k].values()) or 1
         print("   ", k, {n: f"{v/tot*100:.1f}%" for n, v in ph[k].items()}, f"total {tot/3/1e6:.1f} Mcyc/run")

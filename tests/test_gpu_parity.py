@@ -35,6 +35,25 @@ def ctx():
     c.close()
 
 
+# Engine configurations every golden is run under.  "tq" = task-queue engine (the default), with its default
+# Gaussian truncation (z_cut = 100) and with exact-zero skipping only (z_cut = 745.2), small chunks (many
+# partial sums per frame) and the 256-thread kernel variant; "cluster" = the cluster-per-frame engine.
+ENGINE_CFGS = {
+    "tq": dict(engine=1, chunk_points=1024, truncation=100.0, threads=224),
+    "tq_exact_small_chunks": dict(engine=1, chunk_points=256, truncation=745.2, threads=224),
+    "tq_256thr": dict(engine=1, chunk_points=2048, truncation=100.0, threads=256),
+    "cluster": dict(engine=0),
+    "cluster4": dict(engine=0, cluster=4),
+}
+
+
+def _configure(c, cfg):
+    d = dict(ENGINE_CFGS["tq"]); d.update(ENGINE_CFGS[cfg])
+    c.set_cluster_size(d.pop("cluster", 0))
+    for k, v in d.items():
+        c.set_option(k, v)
+
+
 def _params_pair(arr):
     kw = dict(beta=arr[0], lambda_=arr[1], lle_weight=arr[2], mu=arr[3], tol=arr[4], alpha=arr[5], k_vis=arr[6],
               visibility_threshold=arr[7], max_iter=int(arr[8]), include_lle=bool(arr[9]))
@@ -48,8 +67,8 @@ def _batch(frames):
 
 
 @pytest.mark.parametrize("name", ["c1_fixed20", "c1_converge", "c1_lle_preproc", "occl_vis_priors", "n64_sigma_given"])
-@pytest.mark.parametrize("cluster", [0, 1, 4])
-def test_cpd_against_golden(ctx, golden_dir, name, cluster):
+@pytest.mark.parametrize("cfg", list(ENGINE_CFGS))
+def test_cpd_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"cpd_{name}.npz"))
     _, pg = _params_pair(g["params"])
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
@@ -58,10 +77,12 @@ def test_cpd_against_golden(ctx, golden_dir, name, cluster):
         pri = np.zeros((1, Nn, 4)); pri[0, :len(g["priors"])] = g["priors"]; npr = np.array([len(g["priors"])], np.int32)
     if int(g["n_visible"]) >= 0:
         nv = np.array([int(g["n_visible"])], np.int32)
-    ctx.set_cluster_size(cluster)
-    r = ctx.cpd_lle_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.array([float(g["sigma2_in"])]), pg,
-                            priors=pri, n_priors=npr, n_visible=nv)
-    ctx.set_cluster_size(0)
+    _configure(ctx, cfg)
+    try:
+        r = ctx.cpd_lle_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.array([float(g["sigma2_in"])]), pg,
+                                priors=pri, n_priors=npr, n_visible=nv)
+    finally:
+        _configure(ctx, "tq")
     assert r["iters"][0] == int(g["iters"])
     assert bool(r["status"][0] & api.ST_NOT_CONVERGED) == (not bool(g["converged"]))
     assert r["status"][0] & ~api.ST_NOT_CONVERGED == 0
@@ -72,13 +93,18 @@ def test_cpd_against_golden(ctx, golden_dir, name, cluster):
 
 
 @pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
-def test_tracking_step_against_golden(ctx, golden_dir, name):
+@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "cluster"])
+def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
     vis, ext = g["vis"].astype(np.int32), g["vis_ext"].astype(np.int32)
-    r = ctx.tracking_step_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.zeros(1), g["rest"][None],
-                                  vis, np.array([0, len(vis)], np.int64), ext, np.array([0, len(ext)], np.int64),
-                                  api.TrackParams())
+    _configure(ctx, cfg)
+    try:
+        r = ctx.tracking_step_batched(X, np.array([0, len(X)], np.int64), g["Y_in"][None], np.zeros(1), g["rest"][None],
+                                      vis, np.array([0, len(vis)], np.int64), ext, np.array([0, len(ext)], np.int64),
+                                      api.TrackParams())
+    finally:
+        _configure(ctx, "tq")
     assert r["state"][0] == int(g["state"])
     assert list(r["iters"][0]) == list(g["iters"])
     assert r["status"][0] == 0 and int(g["err"]) == 0
@@ -91,9 +117,18 @@ def test_tracking_step_against_golden(ctx, golden_dir, name):
     assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
 
 
-def test_ragged_batch_matches_per_frame_oracle(ctx):
+@pytest.fixture(params=["tq", "cluster"])
+def ectx(ctx, request):
+    _configure(ctx, request.param)
+    ctx.engine_name = request.param
+    yield ctx
+    _configure(ctx, "tq")
+
+
+def test_ragged_batch_matches_per_frame_oracle(ectx):
     """Frames of different point counts AND node counts in one call; results must equal the oracle run
     frame by frame (frames are independent problems)."""
+    ctx = ectx
     specs = [(30, 2000, 0.0), (50, 5000, 0.4), (40, 700, 0.0), (50, 3000, 0.2), (12, 300, 0.0)]
     frames = [synth.make_frame(10 + i, n_nodes=n, n_points=m, occlusion=p) for i, (n, m, p) in enumerate(specs)]
     F, S = len(frames), 50
@@ -114,7 +149,8 @@ def test_ragged_batch_matches_per_frame_oracle(ctx):
         assert np.array_equal(r["Y"][i, n:], Y[i, n:])           # padding rows untouched
 
 
-def test_edge_cases_status_words(ctx):
+def test_edge_cases_status_words(ectx):
+    ctx = ectx
     f = synth.make_frame(0, n_nodes=30, n_points=500)
     far = f["X"] + 10.0                                          # every point pruned
     X = np.concatenate([f["X"], far, f["X"][:0], f["X"]])
@@ -134,7 +170,8 @@ def test_edge_cases_status_words(ctx):
     assert abs(r0["sigma2"][0] - o0["sigma2"]) / o0["sigma2"] < 1e-12
 
 
-def test_end_quirk_and_far_points_match_oracle(ctx):
+def test_end_quirk_and_far_points_match_oracle(ectx):
+    ctx = ectx
     Y = np.array([[0.0, 0, 0], [0.03, 0.03, 0], [0.001, 0.004, 0], [0.0, 0.06, 0], [0.0, 0.09, 0], [0.0, 0.12, 0]])
     rng = np.random.default_rng(5)
     X = np.concatenate([rng.normal(0, 0.004, (200, 3)) + Y[rng.integers(0, 6, 200)],
@@ -147,7 +184,8 @@ def test_end_quirk_and_far_points_match_oracle(ctx):
         assert abs(r["sigma2"][0] - o["sigma2"]) / o["sigma2"] < 1e-6
 
 
-def test_supplied_H_overrides_device_lle(ctx):
+def test_supplied_H_overrides_device_lle(ectx):
+    ctx = ectx
     f = synth.make_frame(2, n_nodes=30, n_points=2000)
     H = oracle.lle_H(f["Y"])
     po = oracle.CpdParams(beta=3.0, lambda_=1.0, include_lle=True, max_iter=15, tol=0.0)
@@ -160,10 +198,11 @@ def test_supplied_H_overrides_device_lle(ctx):
     assert rel(r2["Y"][0], o2["Y"]) < 1e-6
 
 
-def test_full_size_c2_frame_and_invariances(ctx):
+def test_full_size_c2_frame_and_invariances(ectx):
     """BASELINE configs[1] size (Nn=50, Mp=20000, 50 fixed iterations): one frame against the oracle, plus
     size-independent properties on a batch: batch-order independence (bit-exact), point-permutation
     invariance and rigid-translation equivariance (to rounding)."""
+    ctx = ectx
     frames = [synth.make_frame(i, n_nodes=50, n_points=20000) for i in range(4)]
     X, xo, Y = _batch(frames)
     pg = api.CpdParams(max_iter=50, tol=0.0)
@@ -191,12 +230,14 @@ def test_full_size_c2_frame_and_invariances(ctx):
     assert rel(rt["W"][0], r["W"][2]) < 1e-5
 
 
-def test_device_pointer_entry_matches_host_entry(ctx):
+def test_device_pointer_entry_matches_host_entry(ectx):
     import torch
+    ctx = ectx
     frames = [synth.make_frame(20 + i, n_nodes=50, n_points=3000) for i in range(3)]
     X, xo, Y = _batch(frames)
     pg = api.CpdParams(max_iter=12, tol=0.0)
-    ctx.set_cluster_size(4)          # same split of the points on both entries => bit-identical sums
+    if ectx.engine_name == "cluster":
+        ctx.set_cluster_size(4)      # same split of the points on both entries => bit-identical sums
     host = ctx.cpd_lle_batched(X, xo, Y, np.zeros(3), pg)
     dev = torch.device("cuda:0")
     dX = torch.from_numpy(X).to(dev); dxo = torch.from_numpy(xo).to(dev); dY = torch.from_numpy(Y.copy()).to(dev)
@@ -207,7 +248,6 @@ def test_device_pointer_entry_matches_host_entry(ctx):
     stream = torch.cuda.current_stream()
     ctx.cpd_lle_batched_raw(b, pg.to_c(), device=True, stream=stream.cuda_stream)
     stream.synchronize()
-    ctx.set_cluster_size(0)
     assert np.array_equal(dY.cpu().numpy(), host["Y"]) and np.array_equal(ds2.cpu().numpy(), host["sigma2"])
     assert np.array_equal(dit.cpu().numpy(), host["iters"])
 
@@ -223,9 +263,11 @@ def test_bad_arguments_are_rejected(ctx):
         ctx.cpd_lle_batched(f["X"], np.zeros(201, np.int64), big, np.zeros(200), api.CpdParams())
 
 
-def test_larger_node_counts(ctx):
-    """Nn = 100 and 200 take the other kernel variants (16 nodes/warp, global-memory solve workspace)."""
+@pytest.mark.parametrize("engine", [1, 0])
+def test_larger_node_counts(engine):
+    """Nn = 100 and 200 take the other kernel variants (more node passes per lane, global-memory solve workspace)."""
     c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)
+    c.set_option("engine", engine)
     try:
         for Nn, Mp in ((100, 6000), (200, 8000)):
             f = synth.make_frame(1, n_nodes=Nn, n_points=Mp)

@@ -43,7 +43,7 @@ struct tdlo_ctx {
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
     double* d_fscratch = nullptr; long long fstride = 0;
-    double *d_part = nullptr, *d_dminp = nullptr, *d_gath = nullptr; int* d_nkept = nullptr;
+    double *d_part = nullptr, *d_dminp = nullptr, *d_gath = nullptr; int* d_nkept = nullptr; double4* d_tsph = nullptr;
     unsigned long long* d_q = nullptr; unsigned qcap = 0; long long tq_chunks_cap = 0; int tq_alloc_chunk = 0;
     long long points_hint = 0;      // points per frame of the current host call (0 = unknown)
     int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -81,7 +81,7 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
                     ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
                     ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf,
-                    ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q};
+                    ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -198,10 +198,10 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     // ---- workspace (allocated on first use / when the chunk size changes)
     const int chunk = ctx->tq_chunk;
     if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {
-        void* old[] = {ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q};
+        void* old[] = {ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph};
         CK(cudaDeviceSynchronize());
         for (void* p : old) if (p) cudaFree(p);
-        ctx->d_fscratch = nullptr; ctx->d_part = ctx->d_dminp = ctx->d_gath = nullptr; ctx->d_nkept = nullptr; ctx->d_q = nullptr;
+        ctx->d_fscratch = nullptr; ctx->d_part = ctx->d_dminp = ctx->d_gath = nullptr; ctx->d_nkept = nullptr; ctx->d_q = nullptr; ctx->d_tsph = nullptr;
         const TqScr sc = tq_scr_layout(ctx->max_nodes);
         ctx->fstride = sc.total;
         ctx->tq_chunks_cap = ctx->max_points / chunk + ctx->max_frames + 2;
@@ -216,13 +216,14 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
         CKA(dalloc(&ctx->d_gath, (size_t)ctx->tq_chunks_cap));
         CKA(dalloc(&ctx->d_nkept, (size_t)ctx->tq_chunks_cap));
         CKA(dalloc(&ctx->d_q, (size_t)cap + 8));
+        CKA(dalloc(&ctx->d_tsph, (size_t)ctx->tq_chunks_cap * (chunk / 32)));
 #undef CKA
         ctx->tq_alloc_chunk = chunk;
     }
     tq_kern_t kern;
     const TqSmemL L = tq_smem_layout(nmax, nw);
     int minb;
-    if (nmax <= 64) { kern = tdlo_tq_kernel<2, 3>; minb = 3; }
+    if (nmax <= 64) { if (threads <= 224) { kern = tdlo_tq_kernel<2, 3>; minb = 3; } else { kern = tdlo_tq_kernel<2, 2>; minb = 2; } }
     else if (nmax <= 128) { kern = tdlo_tq_kernel<4, 2>; minb = 2; }
     else { kern = tdlo_tq_kernel<8, 2>; minb = 2; }
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
@@ -234,7 +235,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     const int grid = ctx->sm_count * occ;
     TqArgs t;
     memset(&t, 0, sizeof(t));
-    a.Xc = ctx->d_Xc; a.bkt = ctx->d_bkt; a.scr_nodes = ctx->max_nodes; a.prof = nullptr;
+    a.Xc = ctx->d_Xc; a.bkt = ctx->d_bkt; a.scr_nodes = ctx->max_nodes; a.prof = ctx->d_prof;
     t.k = a;
     t.chunk = chunk;
     t.inflight = ctx->tq_inflight > 0 ? ctx->tq_inflight : std::max(grid / 2, 64);
@@ -242,7 +243,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.zcut = ctx->tq_zcut;
     t.qctl = ctx->d_q; t.qslots = ctx->d_q + 8; t.qmask = ctx->qcap - 1;
     t.fscratch = ctx->d_fscratch; t.fstride = ctx->fstride;
-    t.part = ctx->d_part; t.dminp = ctx->d_dminp; t.gath = ctx->d_gath; t.nkept = ctx->d_nkept;
+    t.part = ctx->d_part; t.dminp = ctx->d_dminp; t.gath = ctx->d_gath; t.nkept = ctx->d_nkept; t.tsph = ctx->d_tsph;
     t.part_stride = 4 * ctx->max_nodes + 4;
     t.L = L;
     CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));

@@ -701,6 +701,131 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
 }
 
 // ------------------------------------------------------------------------------------------
+// Register-resident Gauss-Jordan for n <= 64: [A | B] never lives in shared memory during the elimination
+// (the shared-memory version above is bound by shared-memory bandwidth: every step re-reads and re-writes the
+// whole matrix).  Thread (warp w, lane l) owns rows {l, l+32} x columns [w*CW, (w+1)*CW) in registers
+// (needs nwarps * CW >= n + 3).  Per elimination step the owner warp of column k+1 updates that column first
+// and publishes it (raw entries + the next pivot row / value) to a double-buffered shared array; everything
+// else a thread needs is its own two multipliers (two LDS) and the pivot-row entries of its columns (warp
+// shuffles from the lane that owns the pivot row).  ONE block barrier per step, no shared-memory matrix traffic.
+// Implicit partial pivoting (PIVOT) or natural order (SPD systems).  Solution -> wsol[n][3].
+// buf (doubles): mcol[2][64] @0 | pvv[2] @128 | pivots[64] @130 | out[64][3] @194 | ints: pivi[2], prow[64], flag @386
+// ------------------------------------------------------------------------------------------
+constexpr int GJR_BUF_DOUBLES = 386 + 40;
+
+__device__ __forceinline__ double rcp_fast(double x) {          // ~1 ulp reciprocal, no slow path (callers flag non-finite results)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);          // |e| <= 2^-20
+    return fma(r, fma(e, e, e), r);            // r (1 + e + e^2): relative error e^3 <= 2^-60
+}
+
+template <int CW, bool PIVOT>
+__device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, double* wsol) {   // no __restrict__: buf is written by other threads
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nt = blockDim.x, nwarp = nt >> 5;
+    const int ncol = n + 3;
+    double* mcol = buf;                 // [2][64]
+    double* pvv = buf + 128;            // [2]
+    double* pivots = buf + 130;         // [64]
+    double* out = buf + 194;            // [64][3]
+    int* ibuf = reinterpret_cast<int*>(buf + 386);
+    int* pivi = ibuf;                   // [2]
+    int* prow = ibuf + 2;               // [64]
+    int* flag = ibuf + 66;
+    const int r0 = lane, r1 = lane + 32;
+    const int cbase = w * CW;
+    double a0[CW], a1[CW];
+#pragma unroll
+    for (int c = 0; c < CW; c++) {
+        const int col = cbase + c;
+        a0[c] = (r0 < n && col < ncol) ? AB[r0 * ld + col] : 0.0;
+        a1[c] = (r1 < n && col < ncol) ? AB[r1 * ld + col] : 0.0;
+    }
+    bool used0 = r0 >= n, used1 = r1 >= n;
+    int bad = 0;
+    if (tid == 0) *flag = 0;
+    if (w == 0) {                       // publish column 0
+        int pn; double pvn;
+        if (PIVOT) gj_pick(a0[0], a1[0], !used0, !used1, lane, pn, pvn);
+        else { pn = 0; pvn = __shfl_sync(0xffffffffu, a0[0], 0); }
+        mcol[r0] = a0[0]; mcol[r1] = a1[0];
+        if (lane == 0) { pivi[0] = pn; pvv[0] = pvn; pivots[0] = pvn; prow[0] = pn; }
+    }
+    __syncthreads();
+    const int nkb = (n + CW - 1) / CW;
+    for (int kb = 0; kb < nkb; kb++) {
+#pragma unroll
+        for (int kk = 0; kk < CW; kk++) {
+            const int k = kb * CW + kk;
+            if (k >= n) break;
+            const int cur = k & 1, nxt = cur ^ 1;
+            const int p = pivi[cur];
+            const double pv = pvv[cur];
+            double m0 = mcol[cur * 64 + r0], m1 = mcol[cur * 64 + r1];
+            if (p == r0) { used0 = true; m0 = 0.0; }
+            if (p == r1) { used1 = true; m1 = 0.0; }
+            const double rd = -rcp_fast(pv);
+            bad |= !(fabs(rd) <= 1.79e308);
+            const int pl = p & 31;
+            const bool ph = p >= 32;
+            // owner of column k+1: update it first and publish
+            constexpr bool same = true;
+            (void)same;
+            const int co = (kk + 1 < CW) ? kk + 1 : 0;            // static
+            const int wo = (kk + 1 < CW) ? kb : kb + 1;
+            if (w == wo && k + 1 < n) {
+                const double rj = __shfl_sync(0xffffffffu, ph ? a1[co] : a0[co], pl);
+                const double q = rj * rd;
+                a0[co] = fma(m0, q, a0[co]); a1[co] = fma(m1, q, a1[co]);
+                int pn; double pvn;
+                if (PIVOT) gj_pick(a0[co], a1[co], !used0, !used1, lane, pn, pvn);
+                else { pn = k + 1; pvn = __shfl_sync(0xffffffffu, pn < 32 ? a0[co] : a1[co], pn & 31); }
+                mcol[nxt * 64 + r0] = a0[co]; mcol[nxt * 64 + r1] = a1[co];
+                if (lane == 0) { pivi[nxt] = pn; pvv[nxt] = pvn; pivots[k + 1] = pvn; prow[k + 1] = pn; }
+            }
+            // the remaining columns > k of this warp
+            if (w > kb) {
+#pragma unroll
+                for (int c = 0; c < CW; c++) {
+                    if (w == wo && c == co && k + 1 < n) continue;     // done above (only when kk == CW-1: co == 0)
+                    const double rj = __shfl_sync(0xffffffffu, ph ? a1[c] : a0[c], pl);
+                    const double q = rj * rd;
+                    a0[c] = fma(m0, q, a0[c]); a1[c] = fma(m1, q, a1[c]);
+                }
+            } else if (w == kb) {
+#pragma unroll
+                for (int c = 0; c < CW; c++) {
+                    if (c <= kk) continue;                             // static: columns <= k are finished
+                    if (c == co && kk + 1 < CW && k + 1 < n) continue; // done above
+                    const double rj = __shfl_sync(0xffffffffu, ph ? a1[c] : a0[c], pl);
+                    const double q = rj * rd;
+                    a0[c] = fma(m0, q, a0[c]); a1[c] = fma(m1, q, a1[c]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // right-hand sides -> shared, solution off the pivot rows
+#pragma unroll
+    for (int c = 0; c < CW; c++) {
+        const int col = cbase + c;
+        if (col >= n && col < ncol) {
+            if (r0 < n) out[r0 * 3 + (col - n)] = a0[c];
+            if (r1 < n) out[r1 * 3 + (col - n)] = a1[c];
+        }
+    }
+    if (bad) *flag = 1;
+    __syncthreads();
+    for (int i = tid; i < 3 * n; i += nt) {
+        const int k = i / 3, d = i - 3 * k;
+        wsol[i] = out[prow[k] * 3 + d] / pivots[k];
+    }
+    (void)nwarp;
+    __syncthreads();
+    return *flag;
+}
+
+// ------------------------------------------------------------------------------------------
 // LLE weights, one node per thread (trackdlo.cpp:92-159).  Mirrors the operation order of
 // oracle/trackdlo_oracle.cpp::lle_weights_node with explicitly rounded mul/add/div so that both
 // produce identical bits (the 6x6 Gram matrices are rank 3; their inverse is rounding noise).

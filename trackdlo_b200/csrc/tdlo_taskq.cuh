@@ -89,7 +89,7 @@ __host__ __device__ inline TqSmemL tq_smem_layout(int N, int nw) {
     l.px = o; o += 3 * N * 8;
     l.wsol = o; o += 3 * N * 8;
     l.tnew = o; o += 3 * N * 8;
-    l.gjbuf = o; o += 136 * 8;
+    l.gjbuf = o; o += GJR_BUF_DOUBLES * 8;
     l.prow = o; o += N * 4;
     l.used = o; o += N * 4;
     o = (o + 31) & ~31;
@@ -108,6 +108,7 @@ struct TqArgs {
     unsigned long long* qslots; unsigned qmask;
     double* fscratch; long long fstride;   // per-frame scratch
     double* part; double* dminp; double* gath; int* nkept;   // per global chunk
+    double4* tsph;                   // per tile of 32 sorted points: bounding sphere {centre = first point, radius}; [chunk id][chunk/32]
     int part_stride;                 // doubles per chunk in `part`
     TqSmemL L;
 };
@@ -117,6 +118,12 @@ struct TqSm {
     double4* wbuf; double* ptile;
     double *y0, *s, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *gjbuf; int *prow, *used; double* ab;
 };
+
+// optional cycle counters (thread 0 of every CTA): 0 queue wait, 1 prune, 2 dmin, 3 E-step, 4 start_call, 5 wave glue
+// (after_prune / begin_iter / after_dmin), 6 M-step gather+assemble, 7 solve, 8 update, 9 finish_call (+traversal),
+// 10 E-step tasks, 11 tiles, 12 sum of window widths, 13 row blocks
+#define TQ_TICK(slot)                                                                                   \
+    if (prof && threadIdx.x == 0) { const long long tn_ = clock64(); atomicAdd(prof + (slot), (unsigned long long)(tn_ - tprev)); tprev = tn_; }
 
 // 32-byte L2 load (data written by other CTAs during this launch must not come from L1)
 __device__ __forceinline__ double4 ldcg4(const double4* p) {
@@ -162,8 +169,8 @@ __device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
         const unsigned long long lap = (t / ((unsigned long long)a.qmask + 1ull) + 1ull) & 0xffffffull;
         const unsigned long long* slot = a.qslots + (t & a.qmask);
         unsigned long long v = ld_acquire_u64(slot);
-        unsigned ns = 32;
-        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 1024) ns <<= 1; v = ld_acquire_u64(slot); }
+        unsigned ns = 128;
+        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 2048) ns <<= 1; v = ld_acquire_u64(slot); }
         *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = v;
     }
     __syncthreads();
@@ -205,6 +212,20 @@ __device__ __forceinline__ double warp_min_pos_ub(double v) {
     return __hiloint2double((int)h + 1, 0);
 }
 
+// Bounding spheres of the chunk's tiles (32 consecutive sorted points): centre = the tile's first point,
+// radius = an upper bound of the largest distance to it.  The points do not move during a registration,
+// so this is done once per call, right after the prune/sort; the E-step uses it to prune its node searches.
+__device__ void tq_tile_spheres(const double* __restrict__ Xc, int n_local, double4* __restrict__ sph) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = warp * 32; base < n_local; base += nw * 32) {
+        const int n = base + lane < n_local ? base + lane : base;
+        const double x = Xc[(long long)n * 3], y = Xc[(long long)n * 3 + 1], z = Xc[(long long)n * 3 + 2];   // written by this CTA
+        const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
+        const double rho = sqrt(warp_max_pos_ub(dist2(x, y, z, cx, cy, cz) + 1e-300)) * (1.0 + 1e-9);
+        if (lane == 0) sph[base >> 5] = make_double4(cx, cy, cz, rho);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // E-step over one chunk (trackdlo.cpp:278-389); see estep_slice in tdlo_kernels.cuh for the maths.
 // Differences: (1) the P tile of a warp has a fixed 32 node rows -- the node WINDOW of the warp's 32 points
@@ -215,8 +236,9 @@ __device__ __forceinline__ double warp_min_pos_ub(double v) {
 // part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
 // ------------------------------------------------------------------------------------------
 template <int NPASS, bool VIS>
-__device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, int n_local, int Nn,
-                               double sigma2, double c_norm, double rscale, double zcut, double* part_out) {
+__device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, const double4* __restrict__ sph, int n_local, int Nn,
+                               double sigma2, double c_norm, double rscale, double zcut, double* part_out,
+                               unsigned long long* prof) {
     constexpr int RS = TQ_RS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     double* __restrict__ pt = sm.ptile + warp * (TQ_ROWS * RS);
@@ -233,16 +255,32 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, in
     const double T = sqrt(zcut);
     const double s_last = nd[Nn - 1].w;
 
+    // software prefetch: the next tile's point and sphere are requested before the current tile is processed
+    double xn = 0.0, yn = 0.0, zn = 0.0;
+    double4 sn = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (warp * 32 < n_local) {
+        const int b0 = warp * 32;
+        const int n = b0 + lane < n_local ? b0 + lane : b0;
+        xn = __ldcg(Xc + (long long)n * 3); yn = __ldcg(Xc + (long long)n * 3 + 1); zn = __ldcg(Xc + (long long)n * 3 + 2);
+        sn = ldcg4(sph + (b0 >> 5));
+    }
     for (int base = warp * 32; base < n_local; base += nw * 32) {
-        const bool valid = base + lane < n_local;
-        const int n = valid ? base + lane : base;            // idle lanes shadow the tile's first point (weight 0)
-        const double x = __ldcg(Xc + (long long)n * 3), y = __ldcg(Xc + (long long)n * 3 + 1), z = __ldcg(Xc + (long long)n * 3 + 2);
+        const bool valid = base + lane < n_local;            // idle lanes shadow the tile's first point (weight 0)
+        const double x = xn, y = yn, z = zn;
+        const double cx = sn.x, cy = sn.y, cz = sn.z, rho = sn.w;
+        {
+            const int nb = base + nw * 32;
+            if (nb < n_local) {
+                const int n = nb + lane < n_local ? nb + lane : nb;
+                xn = __ldcg(Xc + (long long)n * 3); yn = __ldcg(Xc + (long long)n * 3 + 1); zn = __ldcg(Xc + (long long)n * 3 + 2);
+                sn = ldcg4(sph + (nb >> 5));
+            }
+        }
 
-        // ---- nearest node: exact bounding-sphere pruning of the scan range (see estep_slice)
+        // ---- nearest node: exact bounding-sphere pruning of the scan range (see estep_slice); the sphere of the
+        // tile {centre c, radius rho} comes from the prune pass
         int ja, jb;
         {
-            const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
-            const double rho = sqrt(warp_max_pos_ub(dist2(x, y, z, cx, cy, cz) + 1e-300));
             double dc[NPASS];
             double dloc = 1e300;
 #pragma unroll
@@ -278,16 +316,23 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, in
             }
         }
         // whole column underflows to 0 in the reference -> maxCoeff returns index 0 (trackdlo.cpp:310)
-        if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
+        if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) {
+            a = 0;
+            const double4 q = nd[0];
+            best = dist2(q.x, q.y, q.z, x, y, z);
+        }
+        a = min(a, Nn - 1);                              // (only reachable with non-finite coordinates)
         int q1 = a - 1; if (q1 == -1) q1 = 2;
         int q2 = a + 1; if (q2 == Nn) q2 = Nn - 3;
-        double da, d1, d2n;
-        { const double4 q = nd[a];  da  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        { const double4 q = nd[q1]; d1  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        { const double4 q = nd[q2]; d2n = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        const bool pick1 = d1 < d2n;                     // trackdlo.cpp:324-329
+        double e1, e2;
+        { const double4 q = nd[q1]; e1 = dist2(q.x, q.y, q.z, x, y, z); }
+        { const double4 q = nd[q2]; e2 = dist2(q.x, q.y, q.z, x, y, z); }
+        // trackdlo.cpp:324-329 compares the two Euclidean distances; comparing their squares picks the same
+        // neighbour unless the two distances agree to the last bit
+        const bool pick1 = e1 < e2;
         const int b = pick1 ? q1 : q2;
-        const double db = pick1 ? d1 : d2n;
+        const double da = sqrt(best);
+        const double db = sqrt(pick1 ? e1 : e2);
         const int lo = a < b ? a : b, hi = a < b ? b : a;
         const double dlo = a < b ? da : db, dhi = a < b ? db : da;
         const double alo = nd[lo].w + dlo * rscale;      // t_j = alo - s'_j  for j <= lo
@@ -312,6 +357,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, in
             }
             jlo = min(jlo, lomin); jhi = max(jhi, himax);
         }
+        if (prof && lane == 0) { atomicAdd(prof + 11, 1ull); atomicAdd(prof + 12, (unsigned long long)(jhi - jlo + 1)); atomicAdd(prof + 13, (unsigned long long)((jhi - jlo) / TQ_ROWS + 1)); }
         const bool quirk = (hi - lo == 2);               // the row strictly between lo and hi keeps geodesic 0 -> P = 1 (x vw)
         const int jq = lo + 1;
 
@@ -741,7 +787,8 @@ __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
 // ------------------------------------------------------------------------------------------
 // m_step (trackdlo.cpp:392-438): run by the CTA that completed the frame's E-step wave.
 // ------------------------------------------------------------------------------------------
-__device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+__device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long& tprev) {
+    unsigned long long* prof = a.k.prof;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const int it = __ldcg(fr.ctl + FC_ITER);
@@ -757,7 +804,7 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     const bool ab_in_smem = (long long)Nn * ld <= (long long)a.L.ab_doubles;
     double* AB = ab_in_smem ? sm.ab : scr + sc.AB;
 
-    // ---- frame vectors -> shared; partial sums in chunk order
+    // ---- frame vectors -> shared; partial sums in chunk order (loads batched: the gather is latency bound)
     for (int i = tid; i < 3 * Nn; i += nt) {
         sm.y0[i] = __ldcg(scr + sc.Y0 + i);
         if (have_priors) sm.yext[i] = __ldcg(scr + sc.YEXT + i);
@@ -768,15 +815,28 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
         const double4 q = ldcg4(reinterpret_cast<const double4*>(scr + sc.NODE4) + i);
         sm.node4[i] = q;
     }
-    for (int i = tid; i < 4 * Nn; i += nt) {
+    const int np1 = 4 * Nn + 1;                                   // [Nn][4] sums + sum Pt1 |x|^2
+    for (int i = tid; i < np1; i += nt) {
+        const double* src = a.part + (long long)fr.gbase * a.part_stride + i;
         double v = 0.0;
-        for (int c = 0; c < n_chunks; c++) v += __ldcg(a.part + (long long)(fr.gbase + c) * a.part_stride + i);
-        const int m = i >> 2, kk = i & 3;
-        if (kk == 0) sm.p1[m] = v; else sm.px[3 * m + kk - 1] = v;
+        int c = 0;
+        for (; c + 8 <= n_chunks; c += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = __ldcg(src + (long long)(c + u) * a.part_stride);
+#pragma unroll
+            for (int u = 0; u < 8; u++) v += t[u];
+        }
+        for (; c < n_chunks; c++) v += __ldcg(src + (long long)c * a.part_stride);
+        if (i == 4 * Nn) sm.red[42] = v;
+        else { const int m = i >> 2, kk = i & 3; if (kk == 0) sm.p1[m] = v; else sm.px[3 * m + kk - 1] = v; }
     }
-    double sxx = 0.0;
-    for (int c = 0; c < n_chunks; c++) sxx += __ldcg(a.part + (long long)(fr.gbase + c) * a.part_stride + 4 * Nn);
+    // G -> shared (behind [A|B]) when it fits: used by the assembly and by T = Y0 + G W
+    const bool g_in_smem = ab_in_smem && (long long)Nn * ld + (long long)Nn * Nn <= (long long)a.L.ab_doubles;
+    double* sG = sm.ab + Nn * ld;
+    if (g_in_smem) for (int idx = tid; idx < Nn * Nn; idx += nt) sG[idx] = __ldcg(gG + idx);
     __syncthreads();
+    const double sxx = sm.red[42];
 
     // ---- assemble [A | B] (trackdlo.cpp:392-413); SPD form without LLE (see cpd_run)
     const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
@@ -788,7 +848,7 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     }
     for (int idx = tid; idx < Nn * Nn; idx += nt) {
         const int i = idx / Nn, j = idx - i * Nn;
-        const double g = __ldcg(gG + idx);
+        const double g = g_in_smem ? sG[idx] : __ldcg(gG + idx);
         double v;
         if (spd) v = sm.tnew[i] * g * sm.tnew[j] + (i == j ? ls : 0.0);
         else {
@@ -807,27 +867,42 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
         AB[(long long)i * ld + Nn + (idx - 3 * i)] = v;
     }
     __syncthreads();
+    TQ_TICK(6)
     int sing;
     if (small) {
         double sdreg[3];
         if (spd) for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sdreg[t] = sm.tnew[i / 3];
-        sing = gj_solve_small(sm.ab, Nn, ld, sm.gjbuf, sm.prow, sm.wsol, !spd, nullptr);
+        // register-resident elimination when the warps cover the columns, else the shared-memory one
+        if (nw * 8 >= ld) sing = spd ? gj_solve_regs<8, false>(sm.ab, Nn, ld, sm.gjbuf, sm.wsol) : gj_solve_regs<8, true>(sm.ab, Nn, ld, sm.gjbuf, sm.wsol);
+        else if (nw * 10 >= ld) sing = spd ? gj_solve_regs<10, false>(sm.ab, Nn, ld, sm.gjbuf, sm.wsol) : gj_solve_regs<10, true>(sm.ab, Nn, ld, sm.gjbuf, sm.wsol);
+        else sing = gj_solve_small(sm.ab, Nn, ld, sm.gjbuf, sm.prow, sm.wsol, !spd, nullptr);
         if (spd) {
             for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
             __syncthreads();
         }
-    } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
+    } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 43, sm.wsol);
     if (sing) status |= ST_SINGULAR;
+    TQ_TICK(7)
 
     // ---- T = Y0 + G W (trackdlo.cpp:417)
-    for (int i = warp; i < Nn; i += nw) {
-        double ax = 0.0, ay = 0.0, az = 0.0;
-        for (int kk = lane; kk < Nn; kk += 32) {
-            const double g = __ldcg(gG + (long long)i * Nn + kk);
-            ax = fma(g, sm.wsol[3 * kk], ax); ay = fma(g, sm.wsol[3 * kk + 1], ay); az = fma(g, sm.wsol[3 * kk + 2], az);
+    if (g_in_smem) {
+        for (int i = tid; i < 3 * Nn; i += nt) {
+            const int r = i / 3, d = i - 3 * r;
+            const double* __restrict__ grow = sG + r * Nn;
+            double acc = 0.0;
+            for (int kk = 0; kk < Nn; kk++) acc = fma(grow[kk], sm.wsol[3 * kk + d], acc);
+            sm.tnew[i] = sm.y0[i] + acc;
         }
-        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
+    } else {
+        for (int i = warp; i < Nn; i += nw) {
+            double ax = 0.0, ay = 0.0, az = 0.0;
+            for (int kk = lane; kk < Nn; kk += 32) {
+                const double g = __ldcg(gG + (long long)i * Nn + kk);
+                ax = fma(g, sm.wsol[3 * kk], ax); ay = fma(g, sm.wsol[3 * kk + 1], ay); az = fma(g, sm.wsol[3 * kk + 2], az);
+            }
+            ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+            if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
+        }
     }
     __syncthreads();
     // ---- sigma2 update and convergence test (trackdlo.cpp:418-431)
@@ -861,6 +936,7 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     __syncthreads();
     const int fin = sm.bcast[1];
     __syncthreads();
+    TQ_TICK(8)
     return fin ? A_FINISH_CALL : A_BEGIN_ITER;
 }
 
@@ -980,7 +1056,7 @@ __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int&
 // The persistent kernel
 // ------------------------------------------------------------------------------------------
 template <int NPASS, int MINB>
-__global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(const TqArgs a) {
+__global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(const TqArgs a) {   // <.,3>: 224 threads, 80 regs; <.,2>: 256 threads, 128 regs
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const TqSmemL& L = a.L;
@@ -1009,6 +1085,8 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
     __syncthreads();
 
     int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [2] frames done
+    unsigned long long* prof = a.k.prof;
+    long long tprev = prof ? clock64() : 0;
     int action = A_NONE, af = 0, astage = 0;
     if ((int)blockIdx.x < a.inflight && (int)blockIdx.x < a.k.n_frames) { action = A_START_CALL; af = blockIdx.x; astage = 0; }
 
@@ -1017,12 +1095,12 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
         while (action != A_NONE) {
             const TqFrame fr = tq_frame(a, af);
             switch (action) {
-                case A_START_CALL: action = tq_start_call(a, sm, fr, astage); break;
-                case A_AFTER_PRUNE: action = tq_after_prune(a, sm, fr); break;
-                case A_BEGIN_ITER: action = tq_begin_iter(a, sm, fr); break;
-                case A_AFTER_DMIN: action = tq_after_dmin(a, sm, fr); break;
-                case A_MSTEP: action = tq_mstep(a, sm, fr); break;
-                case A_FINISH_CALL: action = tq_finish_call(a, sm, fr, astage); break;
+                case A_START_CALL: action = tq_start_call(a, sm, fr, astage); TQ_TICK(4) break;
+                case A_AFTER_PRUNE: action = tq_after_prune(a, sm, fr); TQ_TICK(5) break;
+                case A_BEGIN_ITER: action = tq_begin_iter(a, sm, fr); TQ_TICK(5) break;
+                case A_AFTER_DMIN: action = tq_after_dmin(a, sm, fr); TQ_TICK(5) break;
+                case A_MSTEP: action = tq_mstep(a, sm, fr, tprev); break;
+                case A_FINISH_CALL: action = tq_finish_call(a, sm, fr, astage); TQ_TICK(9) break;
                 case A_FRAME_DONE: {
                     __threadfence();
                     __syncthreads();
@@ -1046,6 +1124,7 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
         }
         // ---- next task
         const unsigned long long wd = tq_pop(a, sm);
+        TQ_TICK(0)
         const int type = (int)((wd >> 37) & 7), f = (int)((wd >> 20) & 0x1ffff), c = (int)(wd & 0xfffff);
         if (type == TK_EXIT) break;
         const TqFrame fr = tq_frame(a, f);
@@ -1063,20 +1142,24 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
             const int kept = prune_sort_slice(os, fr.Xraw, r0, r1, fr.Xc, a.k.bkt + (fr.Xraw - a.k.X) / 3, Nn,
                                               tq_params(a, stage).prune_radius, &sum_local);
             if (tid == 0) { __stcg(a.nkept + g, kept); __stcg(a.gath + g, sum_local); }
+            __syncthreads();                                      // the sorted points of this chunk are in place
+            tq_tile_spheres(fr.Xc + r0 * 3, kept, a.tsph + (long long)g * (a.chunk >> 5));
         } else if (type == TK_DMIN) {
             tq_dmin_chunk<NPASS>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, a.dminp + (long long)g * a.k.scr_nodes);
         } else {
             const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
             const double sigma2 = __ldcg(fr.scal + FS_SIGMA2), c_norm = __ldcg(fr.scal + FS_CNORM), rscale = __ldcg(fr.scal + FS_RSCALE);
             double* part = a.part + (long long)g * a.part_stride;
+            if (prof && tid == 0) atomicAdd(prof + 10, 1ull);
             if (use_vis) {
                 for (int j = tid; j < Nn; j += nt) sm.vw[j] = __ldcg(fr.scr + fr.sc.VW + j);
                 __syncthreads();
-                tq_estep_chunk<NPASS, true>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part);
+                tq_estep_chunk<NPASS, true>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
             } else {
-                tq_estep_chunk<NPASS, false>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part);
+                tq_estep_chunk<NPASS, false>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
             }
         }
+        TQ_TICK(type)
         if (tq_arrive(sm, fr.ctl)) {
             af = f;
             action = type == TK_PRUNE ? A_AFTER_PRUNE : (type == TK_DMIN ? A_AFTER_DMIN : A_MSTEP);
