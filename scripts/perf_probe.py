@@ -66,6 +66,7 @@ for c in clusters:
         if v[11]:
             print(f"    estep tasks/run {v[10]/3:.0f}  tiles/run {v[11]/3:.0f}  avg window {v[12]/v[11]:.1f} nodes  blocks/tile {v[13]/v[11]:.2f}"
                   f"  cycles/estep-task {v[3]/max(v[10],1):.0f}  cycles/msolve {v[7]*1.0/max(iters*3,1):.0f} assemble {v[6]/max(iters*3,1):.0f} update {v[8]/max(iters*3,1):.0f}")
+            print(f"    per estep task: tile loop (avg over warps) {v[14]/max(v[10],1)/(info['threads']//32):.0f} cyc, end barrier+reduce (thread 0) {v[15]/max(v[10],1):.0f} cyc, whole task {v[3]/max(v[10],1):.0f} cyc")
         continue
     for k in ("rank0", "others"):
         tot = sum(ph[k].values()) or 1

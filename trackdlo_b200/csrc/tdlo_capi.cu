@@ -39,7 +39,7 @@ struct tdlo_ctx {
     // task-queue engine (tdlo_taskq.cuh)
     int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
     int tq_chunk = 1024;            // raw points per chunk task
-    int tq_threads = 224;           // threads per CTA
+    int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
     double* d_fscratch = nullptr; long long fstride = 0;
@@ -194,7 +194,6 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     CK(cudaSetDevice(ctx->device));
     const int nmax = a.nmax;
     const int threads = ctx->tq_threads;
-    const int nw = threads / 32;
     // ---- workspace (allocated on first use / when the chunk size changes)
     const int chunk = ctx->tq_chunk;
     if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {
@@ -220,18 +219,25 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
 #undef CKA
         ctx->tq_alloc_chunk = chunk;
     }
+    // kernel variants: <node passes, threads, resident CTAs>; the shared-memory layout is sized for 32*passes nodes
     tq_kern_t kern;
-    const TqSmemL L = tq_smem_layout(nmax, nw);
-    int minb;
-    if (nmax <= 64) { if (threads <= 224) { kern = tdlo_tq_kernel<2, 3>; minb = 3; } else { kern = tdlo_tq_kernel<2, 2>; minb = 2; } }
-    else if (nmax <= 128) { kern = tdlo_tq_kernel<4, 2>; minb = 2; }
-    else { kern = tdlo_tq_kernel<8, 2>; minb = 2; }
+    int npass;
+    if (nmax <= 64) {
+        npass = 2;
+        if (threads <= 224) kern = tdlo_tq_kernel<2, 224, 3>;
+        else if (threads <= 256) kern = tdlo_tq_kernel<2, 256, 2>;
+        else if (threads <= 288) kern = tdlo_tq_kernel<2, 288, 2>;
+        else kern = tdlo_tq_kernel<2, 320, 2>;
+    }
+    else if (nmax <= 128) { npass = 4; kern = tdlo_tq_kernel<4, 256, 2>; }
+    else { npass = 8; kern = tdlo_tq_kernel<8, 256, 2>; }
+    const int threads_eff = nmax <= 64 ? (threads <= 224 ? 224 : threads <= 256 ? 256 : threads <= 288 ? 288 : 320) : 256;
+    const TqSmemL L = tq_smem_layout(32 * npass, threads_eff / 32);
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, L.total));
-    if (occ < 1) return fail(ctx, TDLO_ERR_CUDA, "task-queue kernel does not fit (smem %d B, %d threads)", L.total, threads);
-    (void)minb;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads_eff, L.total));
+    if (occ < 1) return fail(ctx, TDLO_ERR_CUDA, "task-queue kernel does not fit (smem %d B, %d threads)", L.total, threads_eff);
     const int grid = ctx->sm_count * occ;
     TqArgs t;
     memset(&t, 0, sizeof(t));
@@ -248,9 +254,9 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.L = L;
     CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));
     CK(cudaMemcpyAsync(reinterpret_cast<int*>(ctx->d_q + 2), &t.inflight, sizeof(int), cudaMemcpyHostToDevice, stream));
-    kern<<<grid, threads, L.total, stream>>>(t);
+    kern<<<grid, threads_eff, L.total, stream>>>(t);
     CK(cudaGetLastError());
-    ctx->info[0] = 1; ctx->info[1] = grid; ctx->info[2] = threads; ctx->info[3] = L.total; ctx->info[4] = chunk;
+    ctx->info[0] = 1; ctx->info[1] = grid; ctx->info[2] = threads_eff; ctx->info[3] = L.total; ctx->info[4] = chunk;
     ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
     return TDLO_OK;
 }
@@ -525,7 +531,7 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             ctx->tq_inflight = (int)value; return TDLO_OK;
         case TDLO_OPT_THREADS: {
             const int t = (int)value;
-            if (t < 64 || t > 256 || (t % 32)) return fail(ctx, TDLO_ERR_INVALID, "threads must be a multiple of 32 in [64, 256]");
+            if (t != 224 && t != 256 && t != 288 && t != 320) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256/288/320 (2 CTAs/SM)");
             ctx->tq_threads = t; return TDLO_OK;
         }
         default: return fail(ctx, TDLO_ERR_INVALID, "unknown option %d", option);

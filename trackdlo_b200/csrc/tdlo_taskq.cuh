@@ -19,7 +19,7 @@
 
 namespace tdlo {
 
-constexpr int TQ_THREADS = 256;            // upper bound of threads per CTA (the host picks 224 or 256)
+constexpr int TQ_THREADS = 320;            // upper bound of threads per CTA (the host picks 224 or 256)
 constexpr int TQ_ROWS = 32, TQ_RS = 33;    // P tile of a warp: 32 node rows x 32 points (+1 pad)
 
 enum { TK_PRUNE = 1, TK_DMIN = 2, TK_ESTEP = 3, TK_EXIT = 7 };
@@ -62,13 +62,14 @@ __host__ __device__ inline TqScr tq_scr_layout(int N) {
 // ---- shared memory layout (bytes).  One fixed head (exp table, node data) + a region that is the E-step's
 // P tiles during chunk tasks and the M-step's [A|B] + vectors during continuations.
 struct TqSmemL {
-    int tab, node4, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, total;
+    int tab, node4, nsoa, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, total;
 };
-__host__ __device__ inline TqSmemL tq_smem_layout(int N, int nw) {
-    TqSmemL l;
+__host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
+    TqSmemL l{};
     int o = 0;
     l.tab = o; o += 64 * 8;
     l.node4 = o; o += N * 32;
+    l.nsoa = o; o += 4 * N * 8;          // node x[], y[], z[], s'[] (lane = node loads without bank conflicts)
     l.vw = o; o += N * 8;
     l.bcast = o; o += 64;
     l.red = o; o += 64 * 8;
@@ -114,7 +115,7 @@ struct TqArgs {
 };
 
 struct TqSm {
-    double* tab; double4* node4; double* vw; int* bcast; double* red;
+    double* tab; double4* node4; double* nsoa; double* vw; int* bcast; double* red;
     double4* wbuf; double* ptile;
     double *y0, *s, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *gjbuf; int *prow, *used; double* ab;
 };
@@ -226,6 +227,13 @@ __device__ void tq_tile_spheres(const double* __restrict__ Xc, int n_local, doub
     }
 }
 
+// Upper bound of sqrt(x), x > 0 (three instructions; only used for conservative search bounds).
+__device__ __forceinline__ double sqrt_ub(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return x * r * (1.0 + 1e-5);
+}
+
 // ------------------------------------------------------------------------------------------
 // E-step over one chunk (trackdlo.cpp:278-389); see estep_slice in tdlo_kernels.cuh for the maths.
 // Differences: (1) the P tile of a warp has a fixed 32 node rows -- the node WINDOW of the warp's 32 points
@@ -235,18 +243,24 @@ __device__ void tq_tile_spheres(const double* __restrict__ Xc, int n_local, doub
 // lanes; (3) window and search bounds use single-REDUX conservative bounds.
 // part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
 // ------------------------------------------------------------------------------------------
-template <int NPASS, bool VIS>
+template <int NPASS, bool VIS, int NW>
 __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, const double4* __restrict__ sph, int n_local, int Nn,
                                double sigma2, double c_norm, double rscale, double zcut, double* part_out,
                                unsigned long long* prof) {
     constexpr int RS = TQ_RS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = NW, nt = NW * 32;
     double* __restrict__ pt = sm.ptile + warp * (TQ_ROWS * RS);
-    double4* __restrict__ wb = sm.wbuf + warp * 32;
+    double2* __restrict__ wlo = reinterpret_cast<double2*>(sm.wbuf + warp * 32);     // (w, w x) per point
+    double2* __restrict__ whi = wlo + 32;                                               // (w y, w z) per point
     double* __restrict__ pcol = pt + lane;
     const double* __restrict__ tab = sm.tab;
     const double4* __restrict__ nd = sm.node4;
     const double* __restrict__ vw = sm.vw;
+    const double* __restrict__ nsx = sm.nsoa;
+    const double* __restrict__ nsy = sm.nsoa + Nn;
+    const double* __restrict__ nsz = sm.nsoa + 2 * Nn;
+    const double* __restrict__ nss = sm.nsoa + 3 * Nn;
     double acc[NPASS][4];
 #pragma unroll
     for (int ps = 0; ps < NPASS; ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
@@ -255,6 +269,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
     const double T = sqrt(zcut);
     const double s_last = nd[Nn - 1].w;
 
+    const long long t_loop0 = prof ? clock64() : 0;
     // software prefetch: the next tile's point and sphere are requested before the current tile is processed
     double xn = 0.0, yn = 0.0, zn = 0.0;
     double4 sn = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -287,10 +302,10 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
             for (int ps = 0; ps < NPASS; ps++) {
                 const int m = lane + 32 * ps;
                 dc[ps] = 1e300;
-                if (m < Nn) { const double4 q = nd[m]; dc[ps] = dist2(q.x, q.y, q.z, cx, cy, cz); }
+                if (m < Nn) dc[ps] = dist2(nsx[m], nsy[m], nsz[m], cx, cy, cz);
                 dloc = fmin(dloc, dc[ps]);
             }
-            double lim = (sqrt(warp_min_pos_ub(dloc + 1e-300)) + 2.0 * rho) * (1.0 + 1e-9);
+            double lim = (sqrt_ub(warp_min_pos_ub(dloc + 1e-300)) + 2.0 * rho) * (1.0 + 1e-9);
             lim = lim * lim;
             ja = Nn; jb = -1;
 #pragma unroll
@@ -349,7 +364,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
 #pragma unroll
             for (int ps = 0; ps < NPASS; ps++) {
                 const int j = lane + 32 * ps;
-                const double sj = j < Nn ? nd[j].w : 0.0;
+                const double sj = j < Nn ? nss[j] : 0.0;
                 const unsigned m1 = __ballot_sync(0xffffffffu, j < Nn && sj > thr_lo);
                 const unsigned m2 = __ballot_sync(0xffffffffu, j < Nn && sj < thr_hi);
                 if (m1 && jlo == Nn) jlo = 32 * ps + __ffs(m1) - 1;
@@ -379,7 +394,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                     const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
                     const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
                     const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
-                    double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
+                    double p0 = exp_neg16(t0 * t0, tab), p1 = exp_neg16(t1 * t1, tab), p2 = exp_neg16(t2 * t2, tab), p3 = exp_neg16(t3 * t3, tab);
                     if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
                     colsum += (p0 + p1) + (p2 + p3);
                     if (j + 3 <= j1) { pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3; }
@@ -393,7 +408,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                 for (; j <= jend; j++) {
                     const double sj = nd[j].w;
                     const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
-                    double p = exp_neg(t * t, tab);
+                    double p = exp_neg16(t * t, tab);
                     if (VIS) p *= vw[j];
                     colsum += p;
                     if (j <= j1) *pc = p;
@@ -404,7 +419,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                 const double pn = VIS ? vw[jq] : 1.0;
                 if (j0 == jlo) {
                     const double tq = ahi + nd[jq].w;    // what the loop computed for row jq (jq > lo)
-                    double pq = exp_neg(tq * tq, tab);
+                    double pq = exp_neg16(tq * tq, tab);
                     if (VIS) pq *= vw[jq];
                     colsum += pn - pq;
                 }
@@ -414,7 +429,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                 const double den = colsum + c_norm;      // trackdlo.cpp:379 / 382
                 w = valid ? 1.0 / den : 0.0;
                 sxx = fma(colsum * w, x * x + y * y + z * z, sxx);   // Pt1_n * |x_n|^2 (trackdlo.cpp:418)
-                wb[lane] = make_double4(w, w * x, w * y, w * z);
+                wlo[lane] = make_double2(w, w * x); whi[lane] = make_double2(w * y, w * z);
             }
             __syncwarp();
 
@@ -424,14 +439,17 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
             const int Wp = Wb <= 8 ? 8 : (Wb <= 16 ? 16 : 32);
             const int r = lane & (Wp - 1);
             const double* __restrict__ prow = pt + r * RS + (lane - r);       // points [g*Wp, (g+1)*Wp)
-            const double4* __restrict__ wg = wb + (lane - r);
+            const double2* __restrict__ wgl = wlo + (lane - r);
+            const double2* __restrict__ wgh = whi + (lane - r);
             double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
             if (r < Wb) {
-#pragma unroll 4
-                for (int i = 0; i < Wp; i++) {
-                    const double p = prow[i];
-                    const double4 w4 = wg[i];
-                    b0 = fma(p, w4.x, b0); b1 = fma(p, w4.y, b1); b2 = fma(p, w4.z, b2); b3 = fma(p, w4.w, b3);
+                for (int i0 = 0; i0 < Wp; i0 += 8) {                           // Wp is 8, 16 or 32
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const double p = prow[i0 + u];
+                        const double2 wa = wgl[i0 + u], wc = wgh[i0 + u];
+                        b0 = fma(p, wa.x, b0); b1 = fma(p, wa.y, b1); b2 = fma(p, wc.x, b2); b3 = fma(p, wc.y, b3);
+                    }
                 }
             }
             for (int off = Wp; off < 32; off <<= 1) {
@@ -452,6 +470,8 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
         }
     }
 
+    if (prof && lane == 0) atomicAdd(prof + 14, (unsigned long long)(clock64() - t_loop0));     // per-warp tile-loop cycles
+    const long long t_red0 = prof ? clock64() : 0;
     // ---- cross-warp reduction in a fixed order (deterministic)
     __syncthreads();
     double* __restrict__ racc = sm.ptile;                 // [nw][Nn][4]; the P tiles are dead now
@@ -472,6 +492,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
     const double sx = block_sum(sxx, sm.red);
     if (tid == 0) __stcg(part_out + 4 * Nn, sx);
     __syncthreads();
+    if (prof && tid == 0) atomicAdd(prof + 15, (unsigned long long)(clock64() - t_red0));         // barrier wait + reduction (thread 0)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1055,14 +1076,18 @@ __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int&
 // ------------------------------------------------------------------------------------------
 // The persistent kernel
 // ------------------------------------------------------------------------------------------
-template <int NPASS, int MINB>
-__global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(const TqArgs a) {   // <.,3>: 224 threads, 80 regs; <.,2>: 256 threads, 128 regs
+// THREADS x MINB: 224 x 3 (80 registers, 21 warps/SM) or 256 x 2 (128 registers, 16 warps/SM).  The shared-memory
+// layout is a compile-time constant (sized for 32*NPASS nodes) so that no address arithmetic survives in the loops.
+template <int NPASS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const TqSmemL& L = a.L;
+    const int tid = threadIdx.x;
+    constexpr int nt = THREADS;
+    constexpr TqSmemL L = tq_smem_layout(32 * NPASS, THREADS / 32);
     TqSm sm;
     sm.tab = reinterpret_cast<double*>(smem_raw + L.tab);
     sm.node4 = reinterpret_cast<double4*>(smem_raw + L.node4);
+    sm.nsoa = reinterpret_cast<double*>(smem_raw + L.nsoa);
     sm.vw = reinterpret_cast<double*>(smem_raw + L.vw);
     sm.bcast = reinterpret_cast<int*>(smem_raw + L.bcast);
     sm.red = reinterpret_cast<double*>(smem_raw + L.red);
@@ -1081,7 +1106,7 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
     sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
     sm.used = reinterpret_cast<int*>(smem_raw + L.used);
     sm.ab = reinterpret_cast<double*>(smem_raw + L.ab);
-    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];
+    for (int i = tid; i < 16; i += nt) sm.tab[i] = c_exp_tab[4 * i];      // 2^(i/16)
     __syncthreads();
 
     int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [2] frames done
@@ -1128,14 +1153,23 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
         const int type = (int)((wd >> 37) & 7), f = (int)((wd >> 20) & 0x1ffff), c = (int)(wd & 0xfffff);
         if (type == TK_EXIT) break;
         const TqFrame fr = tq_frame(a, f);
-        const int Nn = __ldcg(fr.ctl + FC_NN);
         const int g = fr.gbase + c;
         const long long r0 = (long long)c * a.chunk;
         const long long r1 = r0 + a.chunk < fr.m0 ? r0 + a.chunk : fr.m0;
-        for (int j = tid; j < Nn; j += nt) sm.node4[j] = ldcg4(reinterpret_cast<const double4*>(fr.scr + fr.sc.NODE4) + j);
+        // everything the task needs from L2 is requested in one go (the loads are independent: one round trip)
+        const int Nn = __ldcg(fr.ctl + FC_NN), stage = __ldcg(fr.ctl + FC_STAGE), use_vis = __ldcg(fr.ctl + FC_USEVIS);
+        const double sigma2 = __ldcg(fr.scal + FS_SIGMA2), c_norm = __ldcg(fr.scal + FS_CNORM), rscale = __ldcg(fr.scal + FS_RSCALE);
+        const int n_kept = type == TK_PRUNE ? 0 : __ldcg(a.nkept + g);
+        for (int j = tid; j < a.k.scr_nodes; j += nt) {            // rows beyond Nn are scratch: loaded, never used
+            const double4 q = ldcg4(reinterpret_cast<const double4*>(fr.scr + fr.sc.NODE4) + j);
+            const double v = __ldcg(fr.scr + fr.sc.VW + j);
+            if (j < Nn) {
+                sm.node4[j] = q; sm.vw[j] = v;
+                sm.nsoa[j] = q.x; sm.nsoa[Nn + j] = q.y; sm.nsoa[2 * Nn + j] = q.z; sm.nsoa[3 * Nn + j] = q.w;
+            }
+        }
         __syncthreads();
         if (type == TK_PRUNE) {
-            const int stage = __ldcg(fr.ctl + FC_STAGE);
             Smem os;                                              // view for prune_sort_slice (cluster engine helper)
             os.node4 = sm.node4; os.ptile = sm.ptile; os.red = sm.red;
             double sum_local;
@@ -1145,19 +1179,12 @@ __global__ void __launch_bounds__(MINB >= 3 ? 224 : 256, MINB) tdlo_tq_kernel(co
             __syncthreads();                                      // the sorted points of this chunk are in place
             tq_tile_spheres(fr.Xc + r0 * 3, kept, a.tsph + (long long)g * (a.chunk >> 5));
         } else if (type == TK_DMIN) {
-            tq_dmin_chunk<NPASS>(sm, fr.Xc + r0 * 3, __ldcg(a.nkept + g), Nn, a.dminp + (long long)g * a.k.scr_nodes);
+            tq_dmin_chunk<NPASS>(sm, fr.Xc + r0 * 3, n_kept, Nn, a.dminp + (long long)g * a.k.scr_nodes);
         } else {
-            const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
-            const double sigma2 = __ldcg(fr.scal + FS_SIGMA2), c_norm = __ldcg(fr.scal + FS_CNORM), rscale = __ldcg(fr.scal + FS_RSCALE);
             double* part = a.part + (long long)g * a.part_stride;
             if (prof && tid == 0) atomicAdd(prof + 10, 1ull);
-            if (use_vis) {
-                for (int j = tid; j < Nn; j += nt) sm.vw[j] = __ldcg(fr.scr + fr.sc.VW + j);
-                __syncthreads();
-                tq_estep_chunk<NPASS, true>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
-            } else {
-                tq_estep_chunk<NPASS, false>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), __ldcg(a.nkept + g), Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
-            }
+            if (use_vis) tq_estep_chunk<NPASS, true, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
+            else tq_estep_chunk<NPASS, false, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
         }
         TQ_TICK(type)
         if (tq_arrive(sm, fr.ctl)) {
