@@ -850,6 +850,174 @@ __device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, doubl
 }
 
 // ------------------------------------------------------------------------------------------
+// Blocked Cholesky solve for the SPD form of the M-step system at Nn > 64 (C5: Nn = 200), where [A|B] does not fit
+// in registers or shared memory: A (lower triangle, row-major, row stride ld, in L2-resident global scratch) is
+// factorised panel by panel (NB columns): the panel lives in shared memory, its diagonal block is factorised by
+// one warp, the rows below by one thread per row, and the trailing matrix is updated with FP64 tensor-core MMAs
+// (mma.sync.m8n8k4.f64: C[8x8] -= L21[8x4] L21^T[4x8], operands from the shared panel, C read-modify-written in L2).
+// Then L z = b and L^T x = z for the three right-hand sides, column-oriented so that no cross-thread reduction is
+// needed.  One CTA; rhs / solution in wsol[n][3] (shared).  Returns non-zero on a non-positive / non-finite pivot.
+// work: >= n * (NB + 4) + n + 64 doubles of shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NB>
+__device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double* wsol) {
+    constexpr int LDP = NB + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+    double* Lp = work;                       // [n][LDP] panel (rows k0.. of columns k0..k0+nb)
+    double* dinv = work + n * LDP;           // [n] reciprocal diagonal of L
+    int* flag = reinterpret_cast<int*>(dinv + n);
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0), R = n - k0;
+        // (1) panel -> shared
+        for (int idx = tid; idx < R * NB; idx += nt) {
+            const int r = idx / NB, c = idx - r * NB;
+            Lp[r * LDP + c] = (c < nb) ? A[(long long)(k0 + r) * ld + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        // (2) diagonal block: unblocked Cholesky by warp 0 (lane = row)
+        if (warp == 0) {
+            for (int c = 0; c < nb; c++) {
+                const double x = Lp[c * LDP + c];
+                double rs;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(x));
+                {   // two Newton steps: rs <- rs (1.5 - 0.5 x rs^2)
+                    const double hx = 0.5 * x;
+                    rs = rs * fma(-hx * rs, rs, 1.5);
+                    rs = rs * fma(-hx * rs, rs, 1.5);
+                }
+                if (!(x > 0.0) || !(fabs(rs) <= 1.79e308)) { if (lane == 0) *flag = 1; }
+                const double lrc = (lane > c && lane < nb) ? Lp[lane * LDP + c] * rs : 0.0;
+                if (lane == c) { Lp[c * LDP + c] = x * rs; dinv[k0 + c] = rs; }
+                if (lane > c && lane < nb) Lp[lane * LDP + c] = lrc;
+                __syncwarp();
+                // rank-1 update of the remaining lower triangle: row = lane, columns c+1..lane
+                if (lane > c && lane < nb) {
+                    for (int c2 = c + 1; c2 <= lane; c2++) Lp[lane * LDP + c2] = fma(-lrc, Lp[c2 * LDP + c], Lp[lane * LDP + c2]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // (3) rows below the diagonal block: L21 = A21 L11^-T, one thread per row
+        for (int r = nb + tid; r < R; r += nt) {
+            double* row = Lp + r * LDP;
+            for (int c = 0; c < nb; c++) {
+                double v = row[c];
+                for (int c2 = 0; c2 < c; c2++) v = fma(-row[c2], Lp[c * LDP + c2], v);
+                row[c] = v * dinv[k0 + c];
+            }
+        }
+        __syncthreads();
+        // (4) L panel back to global (needed by the substitutions)
+        for (int idx = tid; idx < R * NB; idx += nt) {
+            const int r = idx / NB, c = idx - r * NB;
+            if (c < nb && c <= r) A[(long long)(k0 + r) * ld + k0 + c] = Lp[r * LDP + c];
+        }
+        // (5) trailing update (lower triangle incl. diagonal tiles), 8x8 tiles, FP64 MMA, k = NB
+        const int t0 = k0 + nb;                                   // first trailing row / column
+        const int T = n - t0;
+        if (T > 0) {
+            const int T8 = (T + 7) >> 3;
+            const int ntile = T8 * (T8 + 1) / 2;
+            const int fr_ = lane >> 2, fk = lane & 3;             // fragment row / k index of this lane
+            for (int tile = warp; tile < ntile; tile += nw) {
+                // tile -> (ti, tj), tj <= ti
+                int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+                while (ti * (ti + 1) / 2 > tile) ti--;
+                const int tj = tile - ti * (ti + 1) / 2;
+                const int i0 = ti * 8, j0 = tj * 8;               // relative to t0
+                const int ri = nb + i0 + fr_, rj = nb + j0 + fr_; // panel rows of the A / B fragments
+                const bool iok = i0 + fr_ < T, jok = j0 + fr_ < T;
+                const int ci = t0 + i0 + fr_, cj = t0 + j0 + 2 * fk;   // this lane's C row, first C column
+                double c0 = 0.0, c1 = 0.0;
+                const bool ok0 = iok && (j0 + 2 * fk < T), ok1 = iok && (j0 + 2 * fk + 1 < T);
+                if (ok0) c0 = A[(long long)ci * ld + cj];
+                if (ok1) c1 = A[(long long)ci * ld + cj + 1];
+#pragma unroll
+                for (int kk = 0; kk < NB; kk += 4) {
+                    const double av = iok ? -Lp[ri * LDP + kk + fk] : 0.0;
+                    const double bv = jok ? Lp[rj * LDP + kk + fk] : 0.0;
+                    dmma_884(c0, c1, av, bv);
+                }
+                if (ok0) A[(long long)ci * ld + cj] = c0;
+                if (ok1) A[(long long)ci * ld + cj + 1] = c1;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- forward substitution L z = b (in place in wsol), panel by panel
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0), R = n - k0;
+        for (int idx = tid; idx < R * NB; idx += nt) {
+            const int r = idx / NB, c = idx - r * NB;
+            Lp[r * LDP + c] = (c < nb && c <= r) ? A[(long long)(k0 + r) * ld + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {                                          // diagonal block: lane = row, column oriented
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+            if (lane < nb) { b0 = wsol[(k0 + lane) * 3]; b1 = wsol[(k0 + lane) * 3 + 1]; b2 = wsol[(k0 + lane) * 3 + 2]; }
+            for (int c = 0; c < nb; c++) {
+                const double di = dinv[k0 + c];
+                const double z0 = __shfl_sync(0xffffffffu, b0, c) * di, z1 = __shfl_sync(0xffffffffu, b1, c) * di, z2 = __shfl_sync(0xffffffffu, b2, c) * di;
+                if (lane == c) { b0 = z0; b1 = z1; b2 = z2; }
+                else if (lane > c && lane < nb) { const double l = Lp[lane * LDP + c]; b0 = fma(-l, z0, b0); b1 = fma(-l, z1, b1); b2 = fma(-l, z2, b2); }
+            }
+            if (lane < nb) { wsol[(k0 + lane) * 3] = b0; wsol[(k0 + lane) * 3 + 1] = b1; wsol[(k0 + lane) * 3 + 2] = b2; }
+        }
+        __syncthreads();
+        for (int r = nb + tid; r < R; r += nt) {                  // rows below: b_r -= L21[r][:] z
+            double b0 = wsol[(k0 + r) * 3], b1 = wsol[(k0 + r) * 3 + 1], b2 = wsol[(k0 + r) * 3 + 2];
+            for (int c = 0; c < nb; c++) {
+                const double l = Lp[r * LDP + c];
+                b0 = fma(-l, wsol[(k0 + c) * 3], b0); b1 = fma(-l, wsol[(k0 + c) * 3 + 1], b1); b2 = fma(-l, wsol[(k0 + c) * 3 + 2], b2);
+            }
+            wsol[(k0 + r) * 3] = b0; wsol[(k0 + r) * 3 + 1] = b1; wsol[(k0 + r) * 3 + 2] = b2;
+        }
+        __syncthreads();
+    }
+    // ---- backward substitution L^T x = z, panels from the last to the first
+    const int last = ((n - 1) / NB) * NB;
+    for (int k0 = last; k0 >= 0; k0 -= NB) {
+        const int nb = min(NB, n - k0);
+        // diagonal block (rows/cols k0..k0+nb) -> shared
+        for (int idx = tid; idx < nb * NB; idx += nt) {
+            const int r = idx / NB, c = idx - r * NB;
+            Lp[r * LDP + c] = (c < nb && c <= r) ? A[(long long)(k0 + r) * ld + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {                                          // x_c for c = nb-1 .. 0; lane = row index i < c gets z_i -= L[c][i] x_c
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+            if (lane < nb) { b0 = wsol[(k0 + lane) * 3]; b1 = wsol[(k0 + lane) * 3 + 1]; b2 = wsol[(k0 + lane) * 3 + 2]; }
+            for (int c = nb - 1; c >= 0; c--) {
+                const double di = dinv[k0 + c];
+                const double x0 = __shfl_sync(0xffffffffu, b0, c) * di, x1 = __shfl_sync(0xffffffffu, b1, c) * di, x2 = __shfl_sync(0xffffffffu, b2, c) * di;
+                if (lane == c) { b0 = x0; b1 = x1; b2 = x2; }
+                else if (lane < c) { const double l = Lp[c * LDP + lane]; b0 = fma(-l, x0, b0); b1 = fma(-l, x1, b1); b2 = fma(-l, x2, b2); }
+            }
+            if (lane < nb) { wsol[(k0 + lane) * 3] = b0; wsol[(k0 + lane) * 3 + 1] = b1; wsol[(k0 + lane) * 3 + 2] = b2; }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += nt) {                      // rows above: z_i -= sum_{j in block} L[j][i] x_j
+            double b0 = wsol[i * 3], b1 = wsol[i * 3 + 1], b2 = wsol[i * 3 + 2];
+            for (int c = 0; c < nb; c++) {
+                const double l = A[(long long)(k0 + c) * ld + i];
+                b0 = fma(-l, wsol[(k0 + c) * 3], b0); b1 = fma(-l, wsol[(k0 + c) * 3 + 1], b1); b2 = fma(-l, wsol[(k0 + c) * 3 + 2], b2);
+            }
+            wsol[i * 3] = b0; wsol[i * 3 + 1] = b1; wsol[i * 3 + 2] = b2;
+        }
+        __syncthreads();
+    }
+    return *flag;
+}
+
+// ------------------------------------------------------------------------------------------
 // LLE weights, one node per thread (trackdlo.cpp:92-159).  Mirrors the operation order of
 // oracle/trackdlo_oracle.cpp::lle_weights_node with explicitly rounded mul/add/div so that both
 // produce identical bits (the 6x6 Gram matrices are rank 3; their inverse is rounding noise).

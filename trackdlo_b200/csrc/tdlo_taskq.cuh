@@ -825,44 +825,84 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
     const bool ab_in_smem = (long long)Nn * ld <= (long long)a.L.ab_doubles;
     double* AB = ab_in_smem ? sm.ab : scr + sc.AB;
 
-    // ---- frame vectors -> shared; partial sums in chunk order (loads batched: the gather is latency bound)
-    for (int i = tid; i < 3 * Nn; i += nt) {
-        sm.y0[i] = __ldcg(scr + sc.Y0 + i);
-        if (have_priors) sm.yext[i] = __ldcg(scr + sc.YEXT + i);
-        if (p.include_lle) sm.hy0[i] = __ldcg(scr + sc.HY0 + i);
-    }
-    for (int i = tid; i < Nn; i += nt) {
-        sm.jd[i] = have_priors ? __ldcg(scr + sc.JD + i) : 0.0;
-        const double4 q = ldcg4(reinterpret_cast<const double4*>(scr + sc.NODE4) + i);
-        sm.node4[i] = q;
-    }
-    const int np1 = 4 * Nn + 1;                                   // [Nn][4] sums + sum Pt1 |x|^2
-    for (int i = tid; i < np1; i += nt) {
-        const double* src = a.part + (long long)fr.gbase * a.part_stride + i;
-        double v = 0.0;
-        int c = 0;
-        for (; c + 8 <= n_chunks; c += 8) {
-            double t[8];
+    // ---- frame vectors -> shared; partial sums in chunk order.  The M-step is a latency chain on the frame's
+    // critical path: all loads of this block are requested before any is consumed (two L2 round trips in total).
+    {
+        constexpr int CB = 20;                                    // chunks gathered per batch
+        const int np1 = 4 * Nn + 1;                               // [Nn][4] sums + sum Pt1 |x|^2
+        const double* src = a.part + (long long)fr.gbase * a.part_stride + tid;
+        double t[CB];
+        const bool gth = tid < np1;
 #pragma unroll
-            for (int u = 0; u < 8; u++) t[u] = __ldcg(src + (long long)(c + u) * a.part_stride);
+        for (int u = 0; u < CB; u++) t[u] = (gth && u < n_chunks) ? __ldcg(src + (long long)u * a.part_stride) : 0.0;
+        double vy[3], ve[3], vh[3];                               // 3 Nn <= 3 nt for Nn <= nt (else looped below)
 #pragma unroll
-            for (int u = 0; u < 8; u++) v += t[u];
+        for (int u = 0; u < 3; u++) {
+            const int i = tid + u * nt;
+            const bool ok = i < 3 * Nn;
+            vy[u] = ok ? __ldcg(scr + sc.Y0 + i) : 0.0;
+            ve[u] = (ok && have_priors) ? __ldcg(scr + sc.YEXT + i) : 0.0;
+            vh[u] = (ok && p.include_lle) ? __ldcg(scr + sc.HY0 + i) : 0.0;
         }
-        for (; c < n_chunks; c++) v += __ldcg(src + (long long)c * a.part_stride);
-        if (i == 4 * Nn) sm.red[42] = v;
-        else { const int m = i >> 2, kk = i & 3; if (kk == 0) sm.p1[m] = v; else sm.px[3 * m + kk - 1] = v; }
+        const bool nd_ok = tid < Nn;
+        const double vj = (nd_ok && have_priors) ? __ldcg(scr + sc.JD + tid) : 0.0;
+        double4 q4 = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (nd_ok) q4 = ldcg4(reinterpret_cast<const double4*>(scr + sc.NODE4) + tid);
+        // consume
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int i = tid + u * nt;
+            if (i < 3 * Nn) { sm.y0[i] = vy[u]; sm.yext[i] = ve[u]; sm.hy0[i] = vh[u]; }
+        }
+        if (nd_ok) { sm.jd[tid] = vj; sm.node4[tid] = q4; }
+        for (int i = tid + 3 * nt; i < 3 * Nn; i += nt) {         // Nn > nt (not reachable with Nn <= 256, nt >= 224 ... kept for safety)
+            sm.y0[i] = __ldcg(scr + sc.Y0 + i);
+            sm.yext[i] = have_priors ? __ldcg(scr + sc.YEXT + i) : 0.0;
+            sm.hy0[i] = p.include_lle ? __ldcg(scr + sc.HY0 + i) : 0.0;
+        }
+        for (int i = tid + nt; i < Nn; i += nt) {
+            sm.jd[i] = have_priors ? __ldcg(scr + sc.JD + i) : 0.0;
+            sm.node4[i] = ldcg4(reinterpret_cast<const double4*>(scr + sc.NODE4) + i);
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < CB; u++) v += t[u];                   // chunk order (entries beyond n_chunks are +0.0)
+        for (int c0 = CB; c0 < n_chunks; c0 += CB) {
+#pragma unroll
+            for (int u = 0; u < CB; u++) t[u] = (gth && c0 + u < n_chunks) ? __ldcg(src + (long long)(c0 + u) * a.part_stride) : 0.0;
+#pragma unroll
+            for (int u = 0; u < CB; u++) v += t[u];
+        }
+        if (gth) {
+            if (tid == 4 * Nn) sm.red[42] = v;
+            else { const int m = tid >> 2, kk = tid & 3; if (kk == 0) sm.p1[m] = v; else sm.px[3 * m + kk - 1] = v; }
+        }
+        for (int i = tid + nt; i < np1; i += nt) {                // 4 Nn + 1 > nt (Nn > 55 with 224 threads)
+            const double* s2 = a.part + (long long)fr.gbase * a.part_stride + i;
+            double v2 = 0.0;
+            for (int c = 0; c < n_chunks; c++) v2 += __ldcg(s2 + (long long)c * a.part_stride);
+            if (i == 4 * Nn) sm.red[42] = v2;
+            else { const int m = i >> 2, kk = i & 3; if (kk == 0) sm.p1[m] = v2; else sm.px[3 * m + kk - 1] = v2; }
+        }
     }
     // G -> shared (behind [A|B]) when it fits: used by the assembly and by T = Y0 + G W
     const bool g_in_smem = ab_in_smem && (long long)Nn * ld + (long long)Nn * Nn <= (long long)a.L.ab_doubles;
     double* sG = sm.ab + Nn * ld;
-    if (g_in_smem) for (int idx = tid; idx < Nn * Nn; idx += nt) sG[idx] = __ldcg(gG + idx);
+    if (g_in_smem) {
+        double gv[20];                                            // Nn^2 <= 4096 <= 20 * 224
+#pragma unroll
+        for (int u = 0; u < 20; u++) { const int idx = tid + u * nt; gv[u] = idx < Nn * Nn ? __ldcg(gG + idx) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 20; u++) { const int idx = tid + u * nt; if (idx < Nn * Nn) sG[idx] = gv[u]; }
+    }
     __syncthreads();
     const double sxx = sm.red[42];
 
     // ---- assemble [A | B] (trackdlo.cpp:392-413); SPD form without LLE (see cpd_run)
     const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
     const bool small = ab_in_smem && Nn <= 64;
-    const bool spd = !p.include_lle && small;
+    const int chol_nb = (!small && !p.include_lle) ? ((long long)Nn * 20 + Nn + 64 <= (long long)a.L.ab_doubles ? 16 : ((long long)Nn * 12 + Nn + 64 <= (long long)a.L.ab_doubles ? 8 : 0)) : 0;
+    const bool spd = !p.include_lle && (small || chol_nb > 0);
     if (spd) {
         for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
         __syncthreads();
@@ -901,6 +941,14 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
             for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
             __syncthreads();
         }
+    } else if (chol_nb > 0) {
+        // Nn > 64, SPD form: blocked Cholesky with FP64 tensor-core trailing updates; rhs = B columns of [A|B]
+        double sdreg[3];
+        for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) { sdreg[t] = sm.tnew[i / 3]; sm.wsol[i] = AB[(long long)(i / 3) * ld + Nn + (i % 3)]; }
+        __syncthreads();
+        sing = chol_nb == 16 ? chol_solve_blocked<16>(AB, Nn, ld, sm.ab, sm.wsol) : chol_solve_blocked<8>(AB, Nn, ld, sm.ab, sm.wsol);
+        for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
+        __syncthreads();
     } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 43, sm.wsol);
     if (sing) status |= ST_SINGULAR;
     TQ_TICK(7)
