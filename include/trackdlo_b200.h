@@ -139,6 +139,31 @@ int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch* batch, con
 int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* batch,
                                       const tdlo_track_params* params, void* stream);
 
+/* Visibility front-end that feeds tracking_step (trackdlo/src/trackdlo_node.cpp:254-277, 346-360; the self-occlusion
+ * raster :280-343 is not included: every node counts as not self-occluded).  For every frame: shortest distance of
+ * each node of Y to the frame's points (100000 if there is none, as in the reference), visible_nodes = nodes with
+ * distance <= visibility_threshold (ascending), visible_nodes_extended = gaps filled where the rest arc length between
+ * consecutive visible nodes is <= d_vis.  The CSR outputs are exactly the visibility inputs of tdlo_track_batch. */
+typedef struct tdlo_vis_batch {
+    int32_t n_frames;
+    int32_t n_nodes;
+    const double* X;              /* [x_offsets[n_frames]][3]                                  */
+    const int64_t* x_offsets;     /* [n_frames+1]                                              */
+    const double* Y;              /* [n_frames][n_nodes][3] current node estimate (Y^{t-1})     */
+    const double* node_coord;     /* [n_frames][n_nodes] converted_node_coord (rest arc lengths) */
+    double visibility_threshold;  /* trackdlo_node.cpp:319                                      */
+    double d_vis;                 /* trackdlo_node.cpp:354                                      */
+    double* dmin;                 /* optional out [n_frames][n_nodes]                           */
+    int32_t* visible;             /* out, capacity n_frames*n_nodes                             */
+    int64_t* visible_offsets;     /* out [n_frames+1]                                           */
+    int32_t* visible_ext;         /* out, capacity n_frames*n_nodes                             */
+    int64_t* visible_ext_offsets; /* out [n_frames+1]                                           */
+} tdlo_vis_batch;
+/* Host pointers; synchronous. */
+int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);
+/* Device pointers; asynchronous on `stream` -- chain it in front of tdlo_tracking_step_batched_device. */
+int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* batch, void* stream);
+
 /* Launch geometry of the most recent call (for benchmarks / profiling):
  * info[0]=cluster size, [1]=CTAs launched, [2]=threads per CTA, [3]=dynamic smem bytes,
  * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */

@@ -138,6 +138,19 @@ def tracking_step(X, Y, sigma2, geodesic_coord, vis, vis_ext, tp: TrackParams, H
                 state=st.value, err=err)
 
 
+def visibility(X, Y, node_coord, visibility_threshold=0.008, d_vis=0.06):
+    """Oracle of the visibility front-end (trackdlo_node.cpp:254-277, 346-360, raster excluded).
+    Returns dict(dmin [Nn], vis, vis_ext)."""
+    L = lib()
+    X = _f64(X, (-1, 3)); Y = _f64(Y, (-1, 3)); Nn = Y.shape[0]
+    nc = _f64(node_coord)
+    dmin = np.zeros(Nn); vis = np.zeros(Nn, np.int32); ext = np.zeros(Nn, np.int32); ne = C.c_int32(0)
+    L.oracle_visibility.restype = C.c_int
+    nv = L.oracle_visibility(_p(X), C.c_int64(X.shape[0]), _p(Y), C.c_int32(Nn), _p(nc), C.c_double(visibility_threshold),
+                             C.c_double(d_vis), _p(dmin), _p(vis), _p(ext), C.byref(ne))
+    return dict(dmin=dmin, vis=vis[:nv].copy(), vis_ext=ext[:ne.value].copy())
+
+
 def traverse_euclidean(geodesic_coord, guide, vis, alignment, align_idx=-1):
     L = lib()
     geo = _f64(geodesic_coord); g = _f64(guide, (-1, 3)); v = np.ascontiguousarray(vis, dtype=np.int32)

@@ -768,4 +768,37 @@ int oracle_traverse_euclidean(const double* geodesic_coord, int32_t n_geo, const
     return err;
 }
 
+// Visibility front-end that feeds tracking_step: trackdlo/src/trackdlo_node.cpp:254-277 (shortest
+// node-to-point distances, initial value 100000 as in the reference) and :346-360 (visible_nodes sorted ascending,
+// visible_nodes_extended by the d_vis rule on converted_node_coord).  The self-occlusion raster (:280-343) is NOT
+// part of this restatement: every node counts as not self-occluded.  An empty visible list gives an empty extended
+// list (UB: the reference evaluates visible_nodes.size()-1 on an empty vector).
+// Returns the number of visible nodes; *n_ext_out the number of extended ones.
+int oracle_visibility(const double* X, int64_t Mp, const double* Y, int32_t Nn, const double* node_coord,
+                      double visibility_threshold, double d_vis, double* dmin_out, int32_t* vis_out, int32_t* ext_out,
+                      int32_t* n_ext_out) {
+    int nv = 0;
+    for (int m = 0; m < Nn; m++) {
+        double shortest = 100000;
+        for (int64_t n = 0; n < Mp; n++) {
+            const double dx = Y[3 * m] - X[3 * n], dy = Y[3 * m + 1] - X[3 * n + 1], dz = Y[3 * m + 2] - X[3 * n + 2];
+            const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+            if (dist < shortest) shortest = dist;
+        }
+        if (dmin_out) dmin_out[m] = shortest;
+        if (shortest <= visibility_threshold) vis_out[nv++] = m;      // ascending m == std::sort of the reference's list
+    }
+    int ne = 0;
+    if (nv > 0) {
+        for (int i = 0; i + 1 < nv; i++) {
+            ext_out[ne++] = vis_out[i];
+            if (std::fabs(node_coord[vis_out[i + 1]] - node_coord[vis_out[i]]) <= d_vis)
+                for (int j = 1; j < vis_out[i + 1] - vis_out[i]; j++) ext_out[ne++] = vis_out[i] + j;
+        }
+        ext_out[ne++] = vis_out[nv - 1];
+    }
+    *n_ext_out = ne;
+    return nv;
+}
+
 }  // extern "C"

@@ -252,6 +252,50 @@ def test_device_pointer_entry_matches_host_entry(ectx):
     assert np.array_equal(dit.cpu().numpy(), host["iters"])
 
 
+def test_visibility_front_end_matches_oracle_and_chains_into_tracking(ctx):
+    """node-point min distances + visible / extended lists (trackdlo_node.cpp:254-277, 346-360) on the
+    GPU equal the oracle's (integer lists exact); chained on the device in front of tracking_step it reproduces the
+    result obtained with host-built lists."""
+    import torch
+    specs = [(0.0, 5000), (0.3, 6000), (0.55, 3000), (0.0, 0)]                # last frame: empty cloud
+    frames = [synth.make_frame(40 + i, n_nodes=50, n_points=max(m, 1), occlusion=p) for i, (p, m) in enumerate(specs)]
+    frames[3]["X"] = frames[3]["X"][:0]
+    F, N = len(frames), 50
+    xo = np.zeros(F + 1, np.int64); xo[1:] = np.cumsum([f["X"].shape[0] for f in frames])
+    X = np.concatenate([f["X"] for f in frames]); Y = np.stack([f["Y"] for f in frames]); rest = np.stack([f["rest"] for f in frames])
+    r = ctx.visibility_batched(X, xo, Y, rest, 0.008, 0.06)
+    for i, f in enumerate(frames):
+        o = oracle.visibility(f["X"], f["Y"], f["rest"], 0.008, 0.06)
+        v = r["visible"][r["visible_offsets"][i]:r["visible_offsets"][i + 1]]
+        e = r["visible_ext"][r["visible_ext_offsets"][i]:r["visible_ext_offsets"][i + 1]]
+        assert np.array_equal(v, o["vis"]) and np.array_equal(e, o["vis_ext"]), i
+        assert np.array_equal(r["dmin"][i], o["dmin"]), i                       # same operation order, no FMA: bit-exact
+    assert len(r["visible"]) == r["visible_offsets"][-1] and r["visible_offsets"][-1] == r["visible_offsets"][-2]   # empty frame -> nothing visible
+    # device chain: visibility -> tracking_step without touching the host (first three frames)
+    F3 = 3
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dX, dxo, dY, drest = t(X[:xo[F3]]), t(xo[:F3 + 1]), t(Y[:F3].copy()), t(rest[:F3])
+    dvis = torch.zeros(F3 * N, dtype=torch.int32, device=dev); dext = torch.zeros(F3 * N, dtype=torch.int32, device=dev)
+    dvo = torch.zeros(F3 + 1, dtype=torch.int64, device=dev); deo = torch.zeros(F3 + 1, dtype=torch.int64, device=dev)
+    ds2 = torch.zeros(F3, dtype=torch.float64, device=dev)
+    dit = torch.zeros(F3, 2, dtype=torch.int32, device=dev); dst = torch.zeros(F3, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    vb = api.VisBatchC(F3, N, dX.data_ptr(), dxo.data_ptr(), dY.data_ptr(), drest.data_ptr(), 0.008, 0.06, None,
+                       dvis.data_ptr(), dvo.data_ptr(), dext.data_ptr(), deo.data_ptr())
+    ctx.visibility_batched_raw(vb, device=True, stream=stream.cuda_stream)
+    tb = api.TrackBatchC(F3, N, dX.data_ptr(), dxo.data_ptr(), dY.data_ptr(), ds2.data_ptr(), drest.data_ptr(), dvis.data_ptr(), dvo.data_ptr(),
+                         dext.data_ptr(), deo.data_ptr(), None, None, None, None, dit.data_ptr(), dst.data_ptr(), None)
+    tp = api.TrackParams(max_iter=15)
+    ctx.tracking_step_batched_raw(tb, tp.to_c(), device=True, stream=stream.cuda_stream)
+    stream.synchronize()
+    vis_h = np.concatenate([f["vis"] for f in frames[:F3]]); ext_h = np.concatenate([f["vis_ext"] for f in frames[:F3]])
+    vo_h = np.zeros(F3 + 1, np.int64); vo_h[1:] = np.cumsum([len(f["vis"]) for f in frames[:F3]])
+    eo_h = np.zeros(F3 + 1, np.int64); eo_h[1:] = np.cumsum([len(f["vis_ext"]) for f in frames[:F3]])
+    h = ctx.tracking_step_batched(X[:xo[F3]], xo[:F3 + 1], Y[:F3], np.zeros(F3), rest[:F3], vis_h, vo_h, ext_h, eo_h, tp)
+    assert np.array_equal(dY.cpu().numpy(), h["Y"]) and np.array_equal(dit.cpu().numpy(), h["iters"])
+
+
 def test_bad_arguments_are_rejected(ctx):
     f = synth.make_frame(0, n_nodes=30, n_points=100)
     with pytest.raises(api.TdloError):

@@ -175,3 +175,19 @@ def test_tracking_states():
         r = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], vis.astype(np.int32), vis.astype(np.int32), tp)
         assert r["state"] == state
         assert np.isfinite(r["Y"]).all()
+
+
+def test_visibility_front_end_oracle_matches_generator():
+    """oracle_visibility (trackdlo_node.cpp:254-277, 346-360 restated in C++) against the independent NumPy
+    statement in trackdlo_b200/synth.py, incl. occlusion gaps wider / narrower than d_vis and an empty cloud."""
+    import oracle
+    from trackdlo_b200 import synth
+    for occ in (0.0, 0.05, 0.3, 0.55):
+        f = synth.make_frame(7, n_nodes=50, n_points=4000, occlusion=occ)
+        r = oracle.visibility(f["X"], f["Y"], f["rest"], 0.008, 0.06)
+        assert np.array_equal(r["vis"], f["vis"]) and np.array_equal(r["vis_ext"], f["vis_ext"]), occ
+        d = np.linalg.norm(f["Y"][:, None, :] - f["X"][None, :, :], axis=2).min(axis=1)
+        assert np.allclose(r["dmin"], d, rtol=1e-14, atol=0)
+    f = synth.make_frame(7, n_nodes=20, n_points=100)
+    r = oracle.visibility(f["X"][:0], f["Y"], f["rest"])
+    assert len(r["vis"]) == 0 and len(r["vis_ext"]) == 0 and np.all(r["dmin"] == 100000.0)

@@ -21,6 +21,7 @@ ABI_SYMBOLS = [
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
     "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases", "tdlo_set_option",
+    "tdlo_visibility_batched", "tdlo_visibility_batched_device",
 ]
 
 
@@ -51,6 +52,13 @@ class TrackBatchC(C.Structure):
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "sigma2", "geodesic_coord", "visible",
                                            "visible_offsets", "visible_ext", "visible_ext_offsets", "H_pre",
                                            "guide_nodes", "priors", "n_priors", "iters", "status", "state")]
+
+
+class VisBatchC(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_nodes", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "node_coord")] + \
+               [("visibility_threshold", C.c_double), ("d_vis", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("dmin", "visible", "visible_offsets", "visible_ext", "visible_ext_offsets")]
 
 
 @dataclass
@@ -120,6 +128,8 @@ def load_library():
         lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
         lib.tdlo_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+        lib.tdlo_visibility_batched.argtypes = [C.c_void_p, C.POINTER(VisBatchC)]
+        lib.tdlo_visibility_batched_device.argtypes = [C.c_void_p, C.POINTER(VisBatchC), C.c_void_p]
         _lib = lib
     return _lib
 
@@ -230,6 +240,24 @@ class Context:
         pc = params.to_c()
         self._check(self.lib.tdlo_tracking_step_batched(self.h, C.byref(b), C.byref(pc)), "tdlo_tracking_step_batched")
         return dict(Y=Y, sigma2=s2, guide=guide, priors=pri, n_priors=npri, iters=iters, status=status, state=state)
+
+    # ------------------------------------------------------------------ visibility front-end (trackdlo_node.cpp:254-277, 346-360)
+    def visibility_batched(self, X, x_offsets, Y, node_coord, visibility_threshold=0.008, d_vis=0.06):
+        X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
+        Y = _np(Y, np.float64); F, N = Y.shape[0], Y.shape[1]
+        nc = _np(node_coord, np.float64, (F, N))
+        dmin = np.zeros((F, N)); vis = np.zeros(F * N, np.int32); ext = np.zeros(F * N, np.int32)
+        vo = np.zeros(F + 1, np.int64); eo = np.zeros(F + 1, np.int64)
+        b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo))
+        self._check(self.lib.tdlo_visibility_batched(self.h, C.byref(b)), "tdlo_visibility_batched")
+        return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo)
+
+    def visibility_batched_raw(self, batch: VisBatchC, device=True, stream=0):
+        if device:
+            rc = self.lib.tdlo_visibility_batched_device(self.h, C.byref(batch), C.c_void_p(stream))
+        else:
+            rc = self.lib.tdlo_visibility_batched(self.h, C.byref(batch))
+        self._check(rc, "tdlo_visibility_batched")
 
     def tracking_step_batched_raw(self, batch: TrackBatchC, params: TrackParamsC, device=False, stream=0):
         if device:

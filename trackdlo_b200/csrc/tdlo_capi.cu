@@ -4,6 +4,9 @@
 #include "../../include/trackdlo_b200.h"
 #include "tdlo_kernels.cuh"
 #include "tdlo_taskq.cuh"
+#include "tdlo_visibility.cuh"
+
+#include <vector>
 
 #include <cmath>
 #include <cstdarg>
@@ -36,6 +39,9 @@ struct tdlo_ctx {
     unsigned long long* d_prof = nullptr;   // phase cycle counters (enabled by tdlo_profile_phases)
     unsigned long long* d_prof_buf = nullptr;
     int cluster_override = 0;
+    // visibility front-end workspace
+    unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr, *d_vslice = nullptr; long long vslice_cap = 0;
+    double* d_vdmin = nullptr; int *d_vvis = nullptr, *d_vext = nullptr;
     // task-queue engine (tdlo_taskq.cuh)
     int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
     int tq_chunk = 1024;            // raw points per chunk task
@@ -81,7 +87,8 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
                     ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
                     ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf,
-                    ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph};
+                    ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph,
+                    ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -508,6 +515,112 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (b->iters) D2H(b->iters, ctx->d_iters, F * 2 * sizeof(int));
     if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
     if (b->state) D2H(b->state, ctx->d_state, F * sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// visibility front-end (tdlo_visibility.cuh)
+// ---------------------------------------------------------------------------------------------
+static int vis_workspace(tdlo_ctx* ctx) {
+    if (ctx->d_vbits) return TDLO_OK;
+    const size_t F = ctx->max_frames, N = ctx->max_nodes;
+    ctx->vslice_cap = ctx->max_points / VIS_SLICE + ctx->max_frames + 1;
+    CK(dalloc(&ctx->d_vbits, F * N));
+    CK(dalloc(&ctx->d_vtmp, 2 * F * N));
+    CK(dalloc(&ctx->d_vcnt, 2 * F));
+    CK(dalloc(&ctx->d_vslice, 2 * (size_t)ctx->vslice_cap));
+    return TDLO_OK;
+}
+
+// x_off_host: host copy of the offsets (the slice table is built on the host; the device entry point reads the
+// offsets back once -- they are a few KB)
+static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, const long long* x_off_host, cudaStream_t stream) {
+    int rc = vis_workspace(ctx);
+    if (rc) return rc;
+    const int F = b->n_frames, N = b->n_nodes;
+    std::vector<int> sl;
+    sl.reserve(2 * (size_t)ctx->vslice_cap);
+    std::vector<int> first;
+    for (int f = 0; f < F; f++) {
+        const long long m = x_off_host[f + 1] - x_off_host[f];
+        for (long long s = 0; s * VIS_SLICE < m; s++) { sl.push_back(f); first.push_back((int)s); }
+    }
+    const int ns = (int)first.size();
+    if (ns > ctx->vslice_cap) return fail(ctx, TDLO_ERR_INVALID, "visibility: %d slices exceed capacity %lld", ns, ctx->vslice_cap);
+    VisArgs a;
+    a.n_frames = F; a.n_nodes = N;
+    a.X = b->X; a.x_off = reinterpret_cast<const long long*>(b->x_offsets); a.Y = b->Y; a.node_coord = b->node_coord;
+    a.tau = b->visibility_threshold; a.d_vis = b->d_vis;
+    a.dmin2_bits = ctx->d_vbits; a.tmp_vis = ctx->d_vtmp; a.tmp_ext = ctx->d_vtmp + (size_t)ctx->max_frames * ctx->max_nodes;
+    a.counts = ctx->d_vcnt; a.dmin_out = b->dmin;
+    a.vis = b->visible; a.vis_off = reinterpret_cast<long long*>(b->visible_offsets);
+    a.ext = b->visible_ext; a.ext_off = reinterpret_cast<long long*>(b->visible_ext_offsets);
+    CK(cudaMemsetAsync(ctx->d_vbits, 0x7f, (size_t)F * N * sizeof(unsigned long long), stream));   // 0x7f7f... = 1.4e306
+    if (ns > 0) {
+        CK(cudaMemcpyAsync(ctx->d_vslice, sl.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(ctx->d_vslice + ctx->vslice_cap, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));                       // the host vectors go out of scope
+        tdlo_vis_dmin_kernel<<<ns, 256, 0, stream>>>(a, ctx->d_vslice, ctx->d_vslice + ctx->vslice_cap);
+    }
+    tdlo_vis_lists_kernel<<<(F + 63) / 64, 64, 0, stream>>>(a);
+    tdlo_vis_compact_kernel<<<1, 256, 0, stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->info[5] = ns > 0 ? 3 : 2;
+    return TDLO_OK;
+}
+
+static int vis_check(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
+    if (!b) return fail(ctx, TDLO_ERR_INVALID, "null batch");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->n_nodes < 1 || b->n_nodes > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "n_nodes %d outside [1,%d]", b->n_nodes, ctx->max_nodes);
+    if (!b->X || !b->x_offsets || !b->Y || !b->node_coord || !b->visible || !b->visible_offsets || !b->visible_ext || !b->visible_ext_offsets)
+        return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, node_coord and the four output arrays are required");
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* b, void* stream) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = vis_check(ctx, b);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (b->n_frames == 0) return TDLO_OK;
+    std::vector<long long> xo((size_t)b->n_frames + 1);
+    CK(cudaMemcpyAsync(xo.data(), b->x_offsets, xo.size() * sizeof(long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return vis_launch(ctx, b, xo.data(), (cudaStream_t)stream);
+}
+
+extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = vis_check(ctx, b);
+    if (rc) return rc;
+    if (b->n_frames == 0) return TDLO_OK;
+    const size_t F = b->n_frames, N = b->n_nodes;
+    const long long total = b->x_offsets[F];
+    if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
+    for (size_t f = 0; f < F; f++) if (b->x_offsets[f + 1] < b->x_offsets[f]) return fail(ctx, TDLO_ERR_INVALID, "x_offsets not monotone");
+    if (total > ctx->max_points) return fail(ctx, TDLO_ERR_INVALID, "%lld points exceed capacity %lld", total, ctx->max_points);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_vdmin) {
+        const size_t FM = ctx->max_frames, NM = ctx->max_nodes;
+        CK(dalloc(&ctx->d_vdmin, FM * NM)); CK(dalloc(&ctx->d_vvis, FM * NM)); CK(dalloc(&ctx->d_vext, FM * NM));
+    }
+    H2D(ctx->d_X, b->X, (size_t)total * 3 * sizeof(double));
+    H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
+    H2D(ctx->d_Y, b->Y, F * N * 3 * sizeof(double));
+    H2D(ctx->d_rest, b->node_coord, F * N * sizeof(double));
+    tdlo_vis_batch d = *b;
+    d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.node_coord = ctx->d_rest;
+    d.dmin = ctx->d_vdmin; d.visible = ctx->d_vvis; d.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
+    d.visible_ext = ctx->d_vext; d.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
+    rc = vis_launch(ctx, &d, reinterpret_cast<const long long*>(b->x_offsets), ctx->stream);
+    if (rc) return rc;
+    if (b->dmin) D2H(b->dmin, ctx->d_vdmin, F * N * sizeof(double));
+    D2H(b->visible_offsets, ctx->d_visoff, (F + 1) * sizeof(long long));
+    D2H(b->visible_ext_offsets, ctx->d_extoff, (F + 1) * sizeof(long long));
+    D2H(b->visible, ctx->d_vvis, F * N * sizeof(int));
+    D2H(b->visible_ext, ctx->d_vext, F * N * sizeof(int));
     CK(cudaStreamSynchronize(ctx->stream));
     return TDLO_OK;
 }

@@ -1,0 +1,113 @@
+// Visibility front-end feeding tracking_step, batched over independent frames:
+//   shortest node-to-point distances           trackdlo/src/trackdlo_node.cpp:254-277
+//   visible_nodes (sorted) / visible_nodes_extended (d_vis rule)   trackdlo_node.cpp:346-360
+// The self-occlusion raster (:280-343) is out of scope: every node counts as not self-occluded.
+// Three small kernels: (1) per-node min squared distance, point slices x frames, combined with atomicMin on the
+// bit pattern (non-negative doubles order like their bits); (2) per frame: sqrt, threshold, the two lists at a
+// fixed stride + their lengths; (3) one CTA: exclusive scan of the lengths -> CSR offsets, compaction.  The CSR
+// outputs are exactly the visibility inputs of tdlo_tracking_step_batched_device.
+#pragma once
+
+#include "tdlo_kernels.cuh"
+
+namespace tdlo {
+
+struct VisArgs {
+    int n_frames, n_nodes;
+    const double* X; const long long* x_off;
+    const double* Y; const double* node_coord;
+    double tau, d_vis;
+    unsigned long long* dmin2_bits;   // [F][N] workspace
+    int* tmp_vis; int* tmp_ext;       // [F][N] workspace
+    int* counts;                      // [F][2] workspace
+    double* dmin_out;                 // optional [F][N]
+    int* vis; long long* vis_off; int* ext; long long* ext_off;
+};
+
+constexpr int VIS_SLICE = 4096;       // points per CTA of kernel 1
+
+__global__ void __launch_bounds__(256) tdlo_vis_dmin_kernel(const VisArgs a, const int* slice_frame, const int* slice_first) {
+    __shared__ double4 nd[kMaxNodes];
+    const int f = slice_frame[blockIdx.x];
+    const long long x0 = a.x_off[f], m0 = a.x_off[f + 1] - x0;
+    const long long p0 = (long long)slice_first[blockIdx.x] * VIS_SLICE;
+    const long long p1 = p0 + VIS_SLICE < m0 ? p0 + VIS_SLICE : m0;
+    const int N = a.n_nodes, tid = threadIdx.x, lane = tid & 31;
+    for (int j = tid; j < N; j += blockDim.x) nd[j] = make_double4(a.Y[((long long)f * N + j) * 3], a.Y[((long long)f * N + j) * 3 + 1], a.Y[((long long)f * N + j) * 3 + 2], 0.0);
+    __syncthreads();
+    const double* X = a.X + x0 * 3;
+    for (long long base = p0 + (tid & ~31); base < p1; base += blockDim.x) {
+        const long long n = base + lane;
+        const bool valid = n < p1;
+        double x = 0, y = 0, z = 0;
+        if (valid) { x = __ldg(X + n * 3); y = __ldg(X + n * 3 + 1); z = __ldg(X + n * 3 + 2); }
+        for (int j = 0; j < N; j++) {
+            const double4 q = nd[j];
+            const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
+            // same operation order as the reference's (Y.row(m) - X.row(n)).norm(), no fused multiply-add
+            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (!valid) d2 = 1e300;
+            const unsigned hi = (unsigned)__double2hiint(d2);
+            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned lw = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
+            const unsigned ml = __reduce_min_sync(0xffffffffu, lw);
+            if (lane == 0) atomicMin(a.dmin2_bits + (long long)f * N + j, ((unsigned long long)mh << 32) | ml);
+        }
+    }
+}
+
+__global__ void tdlo_vis_lists_kernel(const VisArgs a) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n_frames) return;
+    const int N = a.n_nodes;
+    int* vis = a.tmp_vis + (long long)f * N;
+    int* ext = a.tmp_ext + (long long)f * N;
+    const double* nc = a.node_coord + (long long)f * N;
+    int nv = 0;
+    for (int m = 0; m < N; m++) {
+        const double d2 = __longlong_as_double((long long)a.dmin2_bits[(long long)f * N + m]);
+        double d = sqrt(d2);
+        if (!(d < 100000.0)) d = 100000.0;                        // the reference's initial shortest_dist
+        if (a.dmin_out) a.dmin_out[(long long)f * N + m] = d;
+        if (d <= a.tau) vis[nv++] = m;
+    }
+    int ne = 0;
+    if (nv > 0) {
+        for (int i = 0; i + 1 < nv; i++) {
+            ext[ne++] = vis[i];
+            if (fabs(nc[vis[i + 1]] - nc[vis[i]]) <= a.d_vis)
+                for (int j = 1; j < vis[i + 1] - vis[i]; j++) ext[ne++] = vis[i] + j;
+        }
+        ext[ne++] = vis[nv - 1];
+    }
+    a.counts[2 * f] = nv; a.counts[2 * f + 1] = ne;
+}
+
+__global__ void __launch_bounds__(256) tdlo_vis_compact_kernel(const VisArgs a) {
+    __shared__ long long run[2];
+    __shared__ long long part[256][2];
+    const int tid = threadIdx.x, F = a.n_frames, N = a.n_nodes;
+    if (tid == 0) { run[0] = run[1] = 0; a.vis_off[0] = 0; a.ext_off[0] = 0; }
+    __syncthreads();
+    for (int f0 = 0; f0 < F; f0 += 256) {
+        const int f = f0 + tid;
+        const long long cv = f < F ? a.counts[2 * f] : 0, ce = f < F ? a.counts[2 * f + 1] : 0;
+        part[tid][0] = cv; part[tid][1] = ce;
+        __syncthreads();
+        if (tid == 0) {                                           // sequential scan of <= 256 entries per round (F is small)
+            long long rv = run[0], re = run[1];
+            for (int i = 0; i < 256; i++) { const long long v = part[i][0], e = part[i][1]; part[i][0] = rv; part[i][1] = re; rv += v; re += e; }
+            run[0] = rv; run[1] = re;
+        }
+        __syncthreads();
+        if (f < F) {
+            const long long ov = part[tid][0], oe = part[tid][1];
+            a.vis_off[f + 1] = ov + cv; a.ext_off[f + 1] = oe + ce;
+            for (int i = 0; i < cv; i++) a.vis[ov + i] = a.tmp_vis[(long long)f * N + i];
+            for (int i = 0; i < ce; i++) a.ext[oe + i] = a.tmp_ext[(long long)f * N + i];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace tdlo
