@@ -394,7 +394,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                     const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
                     const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
                     const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
-                    double p0 = exp_neg16(t0 * t0, tab), p1 = exp_neg16(t1 * t1, tab), p2 = exp_neg16(t2 * t2, tab), p3 = exp_neg16(t3 * t3, tab);
+                    double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
                     if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
                     colsum += (p0 + p1) + (p2 + p3);
                     if (j + 3 <= j1) { pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3; }
@@ -408,7 +408,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                 for (; j <= jend; j++) {
                     const double sj = nd[j].w;
                     const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
-                    double p = exp_neg16(t * t, tab);
+                    double p = exp_neg(t * t, tab);
                     if (VIS) p *= vw[j];
                     colsum += p;
                     if (j <= j1) *pc = p;
@@ -419,7 +419,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
                 const double pn = VIS ? vw[jq] : 1.0;
                 if (j0 == jlo) {
                     const double tq = ahi + nd[jq].w;    // what the loop computed for row jq (jq > lo)
-                    double pq = exp_neg16(tq * tq, tab);
+                    double pq = exp_neg(tq * tq, tab);
                     if (VIS) pq *= vw[jq];
                     colsum += pn - pq;
                 }
@@ -1154,7 +1154,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
     sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
     sm.used = reinterpret_cast<int*>(smem_raw + L.used);
     sm.ab = reinterpret_cast<double*>(smem_raw + L.ab);
-    for (int i = tid; i < 16; i += nt) sm.tab[i] = c_exp_tab[4 * i];      // 2^(i/16)
+    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];          // 2^(i/64)
     __syncthreads();
 
     int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [2] frames done
