@@ -177,30 +177,6 @@ __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ t
     return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
 }
 
-// Same with a 16-entry table 2^(j/16) + degree-7 polynomial (two more FMAs).  Sixteen 8-byte entries sit in
-// sixteen distinct shared-memory banks, so a warp's 32 random look-ups never conflict (the 64-entry table
-// costs ~2.3x the wavefronts of a conflict-free load; the E-step is bound by the shared-memory pipe).
-__device__ __forceinline__ double exp_neg16(double z, const double* __restrict__ tab16) {
-    const double L = 23.083120654223414;          // 16 / ln 2
-    const double C_HI = 0.04332169878499658;      // ln 2 / 16
-    const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52
-    z = __hiloint2double(min(__double2hiint(z), 0x40861000), __double2loint(z));   // NaN also lands here
-    const double t = fma(z, -L, MAGIC);
-    const int n = __double2loint(t);
-    const double nf = t - MAGIC;
-    const double r = fma(nf, -C_HI, -z);           // |r| <= ln2/32
-    const double tj = tab16[n & 15];
-    const double r2 = r * r;
-    double q = fma(r, 1.9841269841269841e-4, 1.3888888888888889e-3);
-    q = fma(q, r, 8.3333333333333332e-3);
-    q = fma(q, r, 4.1666666666666664e-2);
-    q = fma(q, r, 1.6666666666666666e-1);
-    q = fma(q, r, 0.5);
-    const double p = fma(q, r2, r);
-    const double e = fma(tj, p, tj);
-    return __hiloint2double(__double2hiint(e) + ((n >> 4) << 20), __double2loint(e));
-}
-
 __device__ __forceinline__ double dist2(double ax, double ay, double az, double bx, double by, double bz) {
     const double dx = ax - bx, dy = ay - by, dz = az - bz;
     return dx * dx + dy * dy + dz * dz;
@@ -735,7 +711,7 @@ __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __
 // Implicit partial pivoting (PIVOT) or natural order (SPD systems).  Solution -> wsol[n][3].
 // buf (doubles): mcol[2][64] @0 | pvv[2] @128 | pivots[64] @130 | out[64][3] @194 | ints: pivi[2], prow[64], flag @386
 // ------------------------------------------------------------------------------------------
-constexpr int GJR_BUF_DOUBLES = 386 + 40;
+constexpr int GJR_BUF_DOUBLES = 386 + 40 + 16 * 12;     // + per-warp pivot-row buffers [<=16 warps][12]
 
 __device__ __forceinline__ double rcp_fast(double x) {          // ~1 ulp reciprocal, no slow path (callers flag non-finite results)
     double r;
@@ -756,6 +732,7 @@ __device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, doubl
     int* pivi = ibuf;                   // [2]
     int* prow = ibuf + 2;               // [64]
     int* flag = ibuf + 66;
+    double* rbuf = buf + 426 + w * 12;   // this warp's pivot-row buffer (16-byte aligned: buf is)
     const int r0 = lane, r1 = lane + 32;
     const int cbase = w * CW;
     double a0[CW], a1[CW];
@@ -790,41 +767,41 @@ __device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, doubl
             if (p == r1) { used1 = true; m1 = 0.0; }
             const double rd = -rcp_fast(pv);
             bad |= !(fabs(rd) <= 1.79e308);
+            m0 *= rd; m1 *= rd;                                   // a[i][j] += (m_i * -1/pivot) * r_j
             const int pl = p & 31;
             const bool ph = p >= 32;
-            // owner of column k+1: update it first and publish
-            constexpr bool same = true;
-            (void)same;
-            const int co = (kk + 1 < CW) ? kk + 1 : 0;            // static
-            const int wo = (kk + 1 < CW) ? kb : kb + 1;
-            if (w == wo && k + 1 < n) {
-                const double rj = __shfl_sync(0xffffffffu, ph ? a1[co] : a0[co], pl);
-                const double q = rj * rd;
-                a0[co] = fma(m0, q, a0[co]); a1[co] = fma(m1, q, a1[co]);
-                int pn; double pvn;
-                if (PIVOT) gj_pick(a0[co], a1[co], !used0, !used1, lane, pn, pvn);
-                else { pn = k + 1; pvn = __shfl_sync(0xffffffffu, pn < 32 ? a0[co] : a1[co], pn & 31); }
-                mcol[nxt * 64 + r0] = a0[co]; mcol[nxt * 64 + r1] = a1[co];
-                if (lane == 0) { pivi[nxt] = pn; pvv[nxt] = pvn; pivots[k + 1] = pvn; prow[k + 1] = pn; }
-            }
-            // the remaining columns > k of this warp
-            if (w > kb) {
+            const int co = (kk + 1 < CW) ? kk + 1 : 0;            // static: column k+1 inside its owner warp
+            const int wo = (kk + 1 < CW) ? kb : kb + 1;           // owner warp of column k+1
+            const bool active = (w > kb) || (w == kb && kk + 1 < CW) ;   // this warp still has columns > k
+            // pivot-row entries of this warp's columns: the lane that holds row p publishes them to the warp's
+            // shared buffer (4 predicated 16-byte stores), everybody reads them back with broadcast loads
+            if (active) {
+                if (lane == pl) {
+#pragma unroll
+                    for (int c = 0; c < CW; c += 2)
+                        *reinterpret_cast<double2*>(rbuf + c) = ph ? make_double2(a1[c], a1[c + 1]) : make_double2(a0[c], a0[c + 1]);
+                }
+                __syncwarp();
+                double rj[CW];
+#pragma unroll
+                for (int c = 0; c < CW; c += 2) { const double2 v = *reinterpret_cast<const double2*>(rbuf + c); rj[c] = v.x; rj[c + 1] = v.y; }
+                // owner of column k+1: update it first and publish
+                if (w == wo && k + 1 < n) {
+                    a0[co] = fma(m0, rj[co], a0[co]); a1[co] = fma(m1, rj[co], a1[co]);
+                    int pn; double pvn;
+                    if (PIVOT) gj_pick(a0[co], a1[co], !used0, !used1, lane, pn, pvn);
+                    else { pn = k + 1; pvn = __shfl_sync(0xffffffffu, pn < 32 ? a0[co] : a1[co], pn & 31); }
+                    mcol[nxt * 64 + r0] = a0[co]; mcol[nxt * 64 + r1] = a1[co];
+                    if (lane == 0) { pivi[nxt] = pn; pvv[nxt] = pvn; pivots[k + 1] = pvn; prow[k + 1] = pn; }
+                }
+                // the remaining columns > k of this warp
 #pragma unroll
                 for (int c = 0; c < CW; c++) {
-                    if (w == wo && c == co && k + 1 < n) continue;     // done above (only when kk == CW-1: co == 0)
-                    const double rj = __shfl_sync(0xffffffffu, ph ? a1[c] : a0[c], pl);
-                    const double q = rj * rd;
-                    a0[c] = fma(m0, q, a0[c]); a1[c] = fma(m1, q, a1[c]);
+                    if (c == co && k + 1 < n && w == wo) continue;         // done above
+                    if (w == kb && c <= kk) continue;                      // columns <= k are finished
+                    a0[c] = fma(m0, rj[c], a0[c]); a1[c] = fma(m1, rj[c], a1[c]);
                 }
-            } else if (w == kb) {
-#pragma unroll
-                for (int c = 0; c < CW; c++) {
-                    if (c <= kk) continue;                             // static: columns <= k are finished
-                    if (c == co && kk + 1 < CW && k + 1 < n) continue; // done above
-                    const double rj = __shfl_sync(0xffffffffu, ph ? a1[c] : a0[c], pl);
-                    const double q = rj * rd;
-                    a0[c] = fma(m0, q, a0[c]); a1[c] = fma(m1, q, a1[c]);
-                }
+                __syncwarp();                                             // rbuf is rewritten in the next step
             }
             __syncthreads();
         }
