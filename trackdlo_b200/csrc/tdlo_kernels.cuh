@@ -829,9 +829,9 @@ __device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, doubl
 // ------------------------------------------------------------------------------------------
 // Blocked Cholesky solve for the SPD form of the M-step system at Nn > 64 (C5: Nn = 200), where [A|B] does not fit
 // in registers or shared memory: A (lower triangle, row-major, row stride ld, in L2-resident global scratch) is
-// factorised panel by panel (NB columns): the panel lives in shared memory, its diagonal block is factorised by
-// one warp, the rows below by one thread per row, and the trailing matrix is updated with FP64 tensor-core MMAs
-// (mma.sync.m8n8k4.f64: C[8x8] -= L21[8x4] L21^T[4x8], operands from the shared panel, C read-modify-written in L2).
+// factorised panel by panel (NB columns), LEFT-looking: a panel is first brought up to date against all previous
+// panels with FP64 tensor-core MMAs (mma.sync.m8n8k4.f64: C[8x8] -= L[8x4] L^T[4x8], both operands streamed from L2,
+// C in registers), then its diagonal block is factorised by one warp and the rows below by one thread per row.
 // Then L z = b and L^T x = z for the three right-hand sides, column-oriented so that no cross-thread reduction is
 // needed.  One CTA; rhs / solution in wsol[n][3] (shared).  Returns non-zero on a non-positive / non-finite pivot.
 // work: >= n * (NB + 4) + n + 64 doubles of shared memory.
@@ -849,12 +849,50 @@ __device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double
     int* flag = reinterpret_cast<int*>(dinv + n);
     if (tid == 0) *flag = 0;
     __syncthreads();
+    const int fr_ = lane >> 2, fk = lane & 3;                     // MMA fragment row / k index of this lane
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = min(NB, n - k0), R = n - k0;
-        // (1) panel -> shared
-        for (int idx = tid; idx < R * NB; idx += nt) {
-            const int r = idx / NB, c = idx - r * NB;
-            Lp[r * LDP + c] = (c < nb) ? A[(long long)(k0 + r) * ld + k0 + c] : 0.0;
+        // (1) LEFT-LOOKING panel update with FP64 tensor-core MMAs:  panel = A[k0:, k0:k0+nb] - L[k0:, 0:k0] L[k0:k0+nb, 0:k0]^T.
+        // Every warp owns 8-row tiles of the panel; the K loop streams both operands from L2 (no read-modify-write of
+        // a trailing matrix: the loads of a tile are independent and stay in flight together).
+        {
+            constexpr int TR = 4;                                  // row tiles a warp advances together (they share the B fragment)
+            const int ntile = (R + 7) >> 3;
+            for (int g0 = warp * TR; g0 < ntile; g0 += nw * TR) {
+                for (int ct = 0; ct < NB / 8; ct++) {              // 8-column tiles of the panel
+                    const int bcol = ct * 8 + fr_;                 // panel column whose L row feeds the B fragment
+                    const bool bok = bcol < nb;
+                    const double* bro = A + (long long)(k0 + (bok ? bcol : 0)) * ld + fk;
+                    const int cc = ct * 8 + 2 * fk;                // this lane's first C column inside the panel
+                    double c0[TR], c1[TR];
+                    const double* arow[TR];
+                    bool rok[TR];
+#pragma unroll
+                    for (int t = 0; t < TR; t++) {
+                        const int row = k0 + (g0 + t) * 8 + fr_;
+                        rok[t] = (g0 + t < ntile) && row < n;
+                        arow[t] = A + (long long)(rok[t] ? row : k0) * ld + fk;
+                        c0[t] = (rok[t] && cc < nb) ? A[(long long)row * ld + k0 + cc] : 0.0;
+                        c1[t] = (rok[t] && cc + 1 < nb) ? A[(long long)row * ld + k0 + cc + 1] : 0.0;
+                    }
+#pragma unroll 4
+                    for (int kk = 0; kk < k0; kk += 4) {
+                        const double bv = bok ? bro[kk] : 0.0;
+#pragma unroll
+                        for (int t = 0; t < TR; t++) {
+                            const double av = rok[t] ? -arow[t][kk] : 0.0;
+                            dmma_884(c0[t], c1[t], av, bv);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < TR; t++) {
+                        if (rok[t]) {
+                            double* dst = Lp + ((g0 + t) * 8 + fr_) * LDP + cc;
+                            dst[0] = cc < nb ? c0[t] : 0.0; dst[1] = cc + 1 < nb ? c1[t] : 0.0;
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
         // (2) diagonal block: unblocked Cholesky by warp 0 (lane = row)
@@ -891,41 +929,10 @@ __device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double
             }
         }
         __syncthreads();
-        // (4) L panel back to global (needed by the substitutions)
+        // (4) L panel back to global (read by the later panels and by the substitutions)
         for (int idx = tid; idx < R * NB; idx += nt) {
             const int r = idx / NB, c = idx - r * NB;
             if (c < nb && c <= r) A[(long long)(k0 + r) * ld + k0 + c] = Lp[r * LDP + c];
-        }
-        // (5) trailing update (lower triangle incl. diagonal tiles), 8x8 tiles, FP64 MMA, k = NB
-        const int t0 = k0 + nb;                                   // first trailing row / column
-        const int T = n - t0;
-        if (T > 0) {
-            const int T8 = (T + 7) >> 3;
-            const int ntile = T8 * (T8 + 1) / 2;
-            const int fr_ = lane >> 2, fk = lane & 3;             // fragment row / k index of this lane
-            for (int tile = warp; tile < ntile; tile += nw) {
-                // tile -> (ti, tj), tj <= ti
-                int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
-                while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-                while (ti * (ti + 1) / 2 > tile) ti--;
-                const int tj = tile - ti * (ti + 1) / 2;
-                const int i0 = ti * 8, j0 = tj * 8;               // relative to t0
-                const int ri = nb + i0 + fr_, rj = nb + j0 + fr_; // panel rows of the A / B fragments
-                const bool iok = i0 + fr_ < T, jok = j0 + fr_ < T;
-                const int ci = t0 + i0 + fr_, cj = t0 + j0 + 2 * fk;   // this lane's C row, first C column
-                double c0 = 0.0, c1 = 0.0;
-                const bool ok0 = iok && (j0 + 2 * fk < T), ok1 = iok && (j0 + 2 * fk + 1 < T);
-                if (ok0) c0 = A[(long long)ci * ld + cj];
-                if (ok1) c1 = A[(long long)ci * ld + cj + 1];
-#pragma unroll
-                for (int kk = 0; kk < NB; kk += 4) {
-                    const double av = iok ? -Lp[ri * LDP + kk + fk] : 0.0;
-                    const double bv = jok ? Lp[rj * LDP + kk + fk] : 0.0;
-                    dmma_884(c0, c1, av, bv);
-                }
-                if (ok0) A[(long long)ci * ld + cj] = c0;
-                if (ok1) A[(long long)ci * ld + cj + 1] = c1;
-            }
         }
         __syncthreads();
     }
