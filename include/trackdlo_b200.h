@@ -164,6 +164,27 @@ int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);
 /* Device pointers; asynchronous on `stream` -- chain it in front of tdlo_tracking_step_batched_device. */
 int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* batch, void* stream);
 
+/* Sequence mode: S independent trackers advanced over T consecutive frames WITHOUT returning to the host
+ * between frames.  Per step t and sequence s, exactly what trackdlo_node.cpp does per callback: visibility lists from
+ * Y^{t-1} and the step's cloud (tdlo_visibility_batched semantics, visibility_threshold = params->visibility_threshold),
+ * then tracking_step, which leaves Y^{t} and sigma2 in place for step t+1 (trackdlo.cpp:998).  Host pointers; the clouds
+ * of step t+1 are uploaded while step t runs; one synchronisation at the end. */
+typedef struct tdlo_seq_batch {
+    int32_t n_sequences;
+    int32_t n_nodes;
+    int32_t n_steps;
+    const double* X;              /* clouds of all steps, step-major then sequence: [x_offsets[T*S]][3]            */
+    const int64_t* x_offsets;     /* [n_steps * n_sequences + 1]                                                   */
+    double* Y;                    /* [S][n_nodes][3] in: initial nodes (initialize_nodes), out: nodes after step T  */
+    double* sigma2;               /* [S] in/out                                                                    */
+    const double* geodesic_coord; /* [S][n_nodes] rest arc lengths (initialize_geodesic_coord / converted_node_coord) */
+    double d_vis;                 /* trackdlo_node.cpp:354                                                         */
+    double* Y_traj;               /* optional out [T][S][n_nodes][3] tracking result after every step              */
+    int32_t* iters_traj;          /* optional out [T][S][2]                                                        */
+    int32_t* status_traj;         /* optional out [T][S]                                                           */
+} tdlo_seq_batch;
+int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* batch, const tdlo_track_params* params);
+
 /* Launch geometry of the most recent call (for benchmarks / profiling):
  * info[0]=cluster size, [1]=CTAs launched, [2]=threads per CTA, [3]=dynamic smem bytes,
  * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */
@@ -183,7 +204,8 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         that are exactly 0 in the reference (double underflow); the default 100 skips entries
  *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
- *  TDLO_OPT_THREADS       threads per CTA of the task-queue engine (default 224). */
+ *  TDLO_OPT_THREADS       kernel variant of the task-queue engine for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
+ *                         224 (3 CTAs/SM, 80 registers), 288 or 320 (2 CTAs/SM, 96 registers).  Nn > 64 always uses 256. */
 #define TDLO_OPT_ENGINE 1
 #define TDLO_OPT_CHUNK_POINTS 2
 #define TDLO_OPT_TRUNCATION 3

@@ -296,6 +296,41 @@ def test_visibility_front_end_matches_oracle_and_chains_into_tracking(ctx):
     assert np.array_equal(dY.cpu().numpy(), h["Y"]) and np.array_equal(dit.cpu().numpy(), h["iters"])
 
 
+def test_sequence_mode_matches_frame_by_frame_oracle(ctx):
+    """S trackers advanced over T frames on the device (visibility from Y^{t-1}, tracking_step, state
+    carried over) reproduce the oracle run frame by frame the way trackdlo_node.cpp drives the class."""
+    S, T, N = 3, 4, 30
+    rng_frames = [[synth.make_frame(100 * s + t, n_nodes=N, n_points=1500 + 200 * s, occlusion=0.25 if (s == 1 and t >= 2) else 0.0)
+                   for s in range(S)] for t in range(T)]
+    Y0 = np.stack([rng_frames[0][s]["Y"] for s in range(S)]); rest = np.stack([rng_frames[0][s]["rest"] for s in range(S)])
+    clouds = [rng_frames[t][s]["X"] for t in range(T) for s in range(S)]
+    xo = np.zeros(T * S + 1, np.int64); xo[1:] = np.cumsum([len(c) for c in clouds])
+    tp = api.TrackParams(max_iter=20)
+    r = ctx.track_sequences(np.concatenate(clouds), xo, Y0, np.zeros(S), rest, tp, T, d_vis=0.06)
+    otp = oracle.TrackParams(max_iter=20)
+    for s in range(S):
+        Y, s2 = Y0[s].copy(), 0.0
+        for t in range(T):
+            X = rng_frames[t][s]["X"]
+            v = oracle.visibility(X, Y, rest[s], tp.visibility_threshold, 0.06)
+            o = oracle.tracking_step(X, Y, s2, rest[s], v["vis"], v["vis_ext"], otp)
+            Y, s2 = o["Y"], o["sigma2"]
+            assert list(r["iters"][t, s]) == list(o["iters"]), (s, t)
+            assert rel(r["Y_traj"][t, s], Y) < 1e-6, (s, t)
+        assert rel(r["Y"][s], Y) < 1e-6 and abs(r["sigma2"][s] - s2) / s2 < 1e-5
+
+
+def test_engine_options_are_validated(ctx):
+    for name, bad in (("engine", 2), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
+                      ("threads", 128), ("inflight", -1)):
+        with pytest.raises(api.TdloError):
+            ctx.set_option(name, bad)
+    _configure(ctx, "tq")                                  # valid values are accepted and leave the context usable
+    f = synth.make_frame(3, n_nodes=30, n_points=800)
+    r = ctx.cpd_lle_batched(f["X"], np.array([0, 800], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=5, tol=0.0))
+    assert r["iters"][0] == 5
+
+
 def test_bad_arguments_are_rejected(ctx):
     f = synth.make_frame(0, n_nodes=30, n_points=100)
     with pytest.raises(api.TdloError):

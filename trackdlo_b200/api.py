@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
     "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases", "tdlo_set_option",
-    "tdlo_visibility_batched", "tdlo_visibility_batched_device",
+    "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences",
 ]
 
 
@@ -59,6 +59,12 @@ class VisBatchC(C.Structure):
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "node_coord")] + \
                [("visibility_threshold", C.c_double), ("d_vis", C.c_double)] + \
                [(n, C.c_void_p) for n in ("dmin", "visible", "visible_offsets", "visible_ext", "visible_ext_offsets")]
+
+
+class SeqBatchC(C.Structure):
+    _fields_ = [("n_sequences", C.c_int32), ("n_nodes", C.c_int32), ("n_steps", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "sigma2", "geodesic_coord")] + [("d_vis", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("Y_traj", "iters_traj", "status_traj")]
 
 
 @dataclass
@@ -128,6 +134,7 @@ def load_library():
         lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
         lib.tdlo_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+        lib.tdlo_track_sequences.argtypes = [C.c_void_p, C.POINTER(SeqBatchC), C.POINTER(TrackParamsC)]
         lib.tdlo_visibility_batched.argtypes = [C.c_void_p, C.POINTER(VisBatchC)]
         lib.tdlo_visibility_batched_device.argtypes = [C.c_void_p, C.POINTER(VisBatchC), C.c_void_p]
         _lib = lib
@@ -251,6 +258,18 @@ class Context:
         b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo))
         self._check(self.lib.tdlo_visibility_batched(self.h, C.byref(b)), "tdlo_visibility_batched")
         return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo)
+
+    # ------------------------------------------------------------------ sequence mode (visibility + tracking_step per frame on the device)
+    def track_sequences(self, X, x_offsets, Y, sigma2, geodesic_coord, params: TrackParams, n_steps, d_vis=0.06):
+        X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
+        Y = _np(Y, np.float64).copy(); S, N = Y.shape[0], Y.shape[1]
+        s2 = _np(sigma2, np.float64).copy().reshape(S)
+        geo = _np(geodesic_coord, np.float64, (S, N))
+        traj = np.zeros((n_steps, S, N, 3)); its = np.zeros((n_steps, S, 2), np.int32); st = np.zeros((n_steps, S), np.int32)
+        b = SeqBatchC(S, N, n_steps, _ptr(X), _ptr(xo), _ptr(Y), _ptr(s2), _ptr(geo), d_vis, _ptr(traj), _ptr(its), _ptr(st))
+        pc = params.to_c()
+        self._check(self.lib.tdlo_track_sequences(self.h, C.byref(b), C.byref(pc)), "tdlo_track_sequences")
+        return dict(Y=Y, sigma2=s2, Y_traj=traj, iters=its, status=st)
 
     def visibility_batched_raw(self, batch: VisBatchC, device=True, stream=0):
         if device:

@@ -42,6 +42,7 @@ struct tdlo_ctx {
     // visibility front-end workspace
     unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr, *d_vslice = nullptr; long long vslice_cap = 0;
     double* d_vdmin = nullptr; int *d_vvis = nullptr, *d_vext = nullptr;
+    std::vector<int> h_vslice, h_vfirst;
     // task-queue engine (tdlo_taskq.cuh)
     int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
     int tq_chunk = 1024;            // raw points per chunk task
@@ -199,6 +200,7 @@ typedef void (*tq_kern_t)(const TqArgs);
 // Task-queue engine: one persistent launch, grid = SMs x resident CTAs, no clusters.
 static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     CK(cudaSetDevice(ctx->device));
+    if (a.n_frames > 0x1ffff) return fail(ctx, TDLO_ERR_INVALID, "task-queue engine: at most 131071 frames per call (got %d)", a.n_frames);
     const int nmax = a.nmax;
     const int threads = ctx->tq_threads;
     // ---- workspace (allocated on first use / when the chunk size changes)
@@ -539,9 +541,9 @@ static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, const long long* x
     int rc = vis_workspace(ctx);
     if (rc) return rc;
     const int F = b->n_frames, N = b->n_nodes;
-    std::vector<int> sl;
-    sl.reserve(2 * (size_t)ctx->vslice_cap);
-    std::vector<int> first;
+    std::vector<int>& sl = ctx->h_vslice;          // kept alive in the context: the uploads below are asynchronous
+    std::vector<int>& first = ctx->h_vfirst;
+    sl.clear(); first.clear();
     for (int f = 0; f < F; f++) {
         const long long m = x_off_host[f + 1] - x_off_host[f];
         for (long long s = 0; s * VIS_SLICE < m; s++) { sl.push_back(f); first.push_back((int)s); }
@@ -560,7 +562,6 @@ static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, const long long* x
     if (ns > 0) {
         CK(cudaMemcpyAsync(ctx->d_vslice, sl.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(ctx->d_vslice + ctx->vslice_cap, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaStreamSynchronize(stream));                       // the host vectors go out of scope
         tdlo_vis_dmin_kernel<<<ns, 256, 0, stream>>>(a, ctx->d_vslice, ctx->d_vslice + ctx->vslice_cap);
     }
     tdlo_vis_lists_kernel<<<(F + 63) / 64, 64, 0, stream>>>(a);
@@ -621,6 +622,74 @@ extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
     D2H(b->visible_ext_offsets, ctx->d_extoff, (F + 1) * sizeof(long long));
     D2H(b->visible, ctx->d_vvis, F * N * sizeof(int));
     D2H(b->visible_ext, ctx->d_vext, F * N * sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sequence mode: visibility + tracking_step per frame, state carried on the device
+// ---------------------------------------------------------------------------------------------
+extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, const tdlo_track_params* p) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
+    const int S = b->n_sequences, N = b->n_nodes, T = b->n_steps;
+    if (S < 0 || S > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_sequences %d exceeds capacity %d", S, ctx->max_frames);
+    if (N < 4 || N > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "n_nodes %d outside [4,%d]", N, ctx->max_nodes);
+    if (T < 0) return fail(ctx, TDLO_ERR_INVALID, "n_steps must be >= 0");
+    if (!b->X || !b->x_offsets || !b->Y || !b->sigma2 || !b->geodesic_coord) return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2, geodesic_coord are required");
+    int rc = check_params(ctx, p->mu, p->beta, p->max_iter, p->prune_radius);
+    if (rc) return rc;
+    if (S == 0 || T == 0) return TDLO_OK;
+    if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
+    for (long long i = 0; i < (long long)T * S; i++) if (b->x_offsets[i + 1] < b->x_offsets[i]) return fail(ctx, TDLO_ERR_INVALID, "x_offsets not monotone");
+    for (int t = 0; t < T; t++)
+        if (b->x_offsets[(long long)(t + 1) * S] - b->x_offsets[(long long)t * S] > ctx->max_points)
+            return fail(ctx, TDLO_ERR_INVALID, "step %d: %lld points exceed capacity %lld", t, (long long)(b->x_offsets[(long long)(t + 1) * S] - b->x_offsets[(long long)t * S]), ctx->max_points);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_vdmin) {
+        const size_t FM = ctx->max_frames, NM = ctx->max_nodes;
+        CK(dalloc(&ctx->d_vdmin, FM * NM)); CK(dalloc(&ctx->d_vvis, FM * NM)); CK(dalloc(&ctx->d_vext, FM * NM));
+    }
+    const size_t SN = (size_t)S * N;
+    H2D(ctx->d_Y, b->Y, SN * 3 * sizeof(double));
+    H2D(ctx->d_sigma2, b->sigma2, (size_t)S * sizeof(double));
+    H2D(ctx->d_rest, b->geodesic_coord, SN * sizeof(double));
+    std::vector<long long> xo((size_t)S + 1);
+    for (int t = 0; t < T; t++) {
+        const long long base = b->x_offsets[(long long)t * S];
+        for (int s = 0; s <= S; s++) xo[s] = b->x_offsets[(long long)t * S + s] - base;
+        // the offsets are consumed by kernels of THIS step only after the previous step's kernels (stream order); the
+        // pageable-memory copy is staged before cudaMemcpyAsync returns, so `xo` can be reused in the next round
+        H2D(ctx->d_xoff, xo.data(), ((size_t)S + 1) * sizeof(long long));
+        if (xo[S] > 0) H2D(ctx->d_X, b->X + base * 3, (size_t)xo[S] * 3 * sizeof(double));
+        tdlo_vis_batch v;
+        memset(&v, 0, sizeof(v));
+        v.n_frames = S; v.n_nodes = N;
+        v.X = ctx->d_X; v.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); v.Y = ctx->d_Y; v.node_coord = ctx->d_rest;
+        v.visibility_threshold = p->visibility_threshold; v.d_vis = b->d_vis;
+        v.visible = ctx->d_vvis; v.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
+        v.visible_ext = ctx->d_vext; v.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
+        rc = vis_launch(ctx, &v, xo.data(), ctx->stream);
+        if (rc) return rc;
+        tdlo_track_batch d;
+        memset(&d, 0, sizeof(d));
+        d.n_frames = S; d.n_nodes = N;
+        d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.sigma2 = ctx->d_sigma2;
+        d.geodesic_coord = ctx->d_rest;
+        d.visible = ctx->d_vvis; d.visible_offsets = reinterpret_cast<const int64_t*>(ctx->d_visoff);
+        d.visible_ext = ctx->d_vext; d.visible_ext_offsets = reinterpret_cast<const int64_t*>(ctx->d_extoff);
+        d.guide_nodes = ctx->d_guide; d.priors = ctx->d_priors_out; d.n_priors = ctx->d_npri_out;
+        d.iters = ctx->d_iters; d.status = ctx->d_status; d.state = ctx->d_state;
+        ctx->points_hint = xo[S] / S;
+        rc = tdlo_tracking_step_batched_device(ctx, &d, p, ctx->stream);
+        ctx->points_hint = 0;
+        if (rc) return rc;
+        if (b->Y_traj) D2H(b->Y_traj + (size_t)t * SN * 3, ctx->d_Y, SN * 3 * sizeof(double));
+        if (b->iters_traj) D2H(b->iters_traj + (size_t)t * S * 2, ctx->d_iters, (size_t)S * 2 * sizeof(int));
+        if (b->status_traj) D2H(b->status_traj + (size_t)t * S, ctx->d_status, (size_t)S * sizeof(int));
+    }
+    D2H(b->Y, ctx->d_Y, SN * 3 * sizeof(double));
+    D2H(b->sigma2, ctx->d_sigma2, (size_t)S * sizeof(double));
     CK(cudaStreamSynchronize(ctx->stream));
     return TDLO_OK;
 }
