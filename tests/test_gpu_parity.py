@@ -320,6 +320,31 @@ def test_sequence_mode_matches_frame_by_frame_oracle(ctx):
         assert rel(r["Y"][s], Y) < 1e-6 and abs(r["sigma2"][s] - s2) / s2 < 1e-5
 
 
+def test_pipelined_upload_matches_device_entry(ctx):
+    """Host-buffer entry with >= 16 frames / >= 200k points: the clouds are uploaded in groups on a copy stream while the
+    persistent kernel already registers the first frames (a frame's first task waits for its group's flag).  Results
+    must be bit-identical to the device-pointer entry on resident inputs."""
+    import torch
+    F, N, M = 18, 30, 12000
+    wl = synth.make_batch(F, first_frame=300, n_nodes=N, n_points=M)
+    tp = api.TrackParams(max_iter=6, tol=0.0)
+    h = ctx.tracking_step_batched(wl["X"], wl["x_offsets"], wl["Y"], np.zeros(F), wl["rest"], wl["vis"], wl["vis_offsets"],
+                                  wl["vis_ext"], wl["vis_ext_offsets"], tp)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).to(dev) for k in ("X", "x_offsets", "Y", "rest", "vis", "vis_offsets", "vis_ext", "vis_ext_offsets")}
+    s2 = torch.zeros(F, dtype=torch.float64, device=dev); it = torch.zeros(F, 2, dtype=torch.int32, device=dev); st = torch.zeros(F, dtype=torch.int32, device=dev)
+    tb = api.TrackBatchC(F, N, d["X"].data_ptr(), d["x_offsets"].data_ptr(), d["Y"].data_ptr(), s2.data_ptr(), d["rest"].data_ptr(), d["vis"].data_ptr(),
+                         d["vis_offsets"].data_ptr(), d["vis_ext"].data_ptr(), d["vis_ext_offsets"].data_ptr(), None, None, None, None, it.data_ptr(), st.data_ptr(), None)
+    stream = torch.cuda.current_stream()
+    ctx.tracking_step_batched_raw(tb, tp.to_c(), device=True, stream=stream.cuda_stream)
+    stream.synchronize()
+    assert np.array_equal(d["Y"].cpu().numpy(), h["Y"]) and np.array_equal(s2.cpu().numpy(), h["sigma2"]) and np.array_equal(it.cpu().numpy(), h["iters"])
+    # twice in a row on the same context (flag reset, stream ordering)
+    h2 = ctx.tracking_step_batched(wl["X"], wl["x_offsets"], wl["Y"], np.zeros(F), wl["rest"], wl["vis"], wl["vis_offsets"],
+                                   wl["vis_ext"], wl["vis_ext_offsets"], tp)
+    assert np.array_equal(h2["Y"], h["Y"])
+
+
 def test_engine_options_are_validated(ctx):
     for name, bad in (("engine", 2), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
                       ("threads", 128), ("inflight", -1)):

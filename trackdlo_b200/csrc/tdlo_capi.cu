@@ -23,6 +23,9 @@ struct tdlo_ctx {
     int max_frames = 0, max_nodes = 0;
     long long max_points = 0;
     cudaStream_t stream = nullptr;
+    // pipelined upload of the point clouds (host-buffer entry points, task-queue engine): copy stream + progress flag
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_small = nullptr, ev_copy = nullptr; int* d_ready = nullptr; int* h_ready_vals = nullptr;
+    const int* cur_ready = nullptr; int cur_ready_frames = 0;
     // device staging for the host-pointer entry points
     double *d_X = nullptr, *d_Y = nullptr, *d_sigma2 = nullptr, *d_priors = nullptr, *d_H = nullptr, *d_W = nullptr;
     double *d_rest = nullptr, *d_guide = nullptr, *d_priors_out = nullptr;
@@ -92,6 +95,11 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
                     ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->d_ready) cudaFree(ctx->d_ready);
+    if (ctx->h_ready_vals) cudaFreeHost(ctx->h_ready_vals);
     delete ctx;
 }
 
@@ -136,6 +144,12 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
         }                                                                                           \
     } while (0)
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    CKC(dalloc(&ctx->d_ready, 1));
+    CKC(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ready_vals), 16 * sizeof(int)));
+    for (int i = 0; i < 16; i++) ctx->h_ready_vals[i] = i;
     CKC(dalloc(&ctx->d_X, P * 3));
     CKC(dalloc(&ctx->d_Xc, P * 3));
     CKC(dalloc(&ctx->d_bkt, P));
@@ -260,6 +274,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.fscratch = ctx->d_fscratch; t.fstride = ctx->fstride;
     t.part = ctx->d_part; t.dminp = ctx->d_dminp; t.gath = ctx->d_gath; t.nkept = ctx->d_nkept; t.tsph = ctx->d_tsph;
     t.part_stride = 4 * ctx->max_nodes + 4;
+    t.ready = ctx->cur_ready; t.ready_frames = ctx->cur_ready_frames;
     t.L = L;
     CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));
     CK(cudaMemcpyAsync(reinterpret_cast<int*>(ctx->d_q + 2), &t.inflight, sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -416,6 +431,39 @@ extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track
 #define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
 #define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream))
 
+// Uploads the concatenated point clouds.  With the task-queue engine and a batch worth splitting, the upload runs in
+// (up to) 8 groups of frames on the copy stream, each followed by a progress flag; the persistent kernel starts right
+// away on the main stream and a frame's first task waits for its group's flag, so that the transfer of the later
+// frames overlaps the registration of the earlier ones.  Call after the small arrays are queued on ctx->stream.
+static int upload_points(tdlo_ctx* ctx, const double* X, const int64_t* x_offsets, int F) {
+    const long long total = x_offsets[F];
+    ctx->cur_ready = nullptr; ctx->cur_ready_frames = 0;
+    const int G = (ctx->engine == 1 && F >= 16 && total >= 200000) ? 8 : 1;
+    if (G == 1) {
+        if (total > 0) H2D(ctx->d_X, X, (size_t)total * 3 * sizeof(double));
+        return TDLO_OK;
+    }
+    const int per = (F + G - 1) / G;
+    CK(cudaMemsetAsync(ctx->d_ready, 0, sizeof(int), ctx->stream));
+    CK(cudaEventRecord(ctx->ev_small, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_small, 0));
+    for (int g = 0; g * per < F; g++) {
+        const int f0 = g * per, f1 = std::min(F, f0 + per);
+        const long long p0 = x_offsets[f0], p1 = x_offsets[f1];
+        if (p1 > p0) CK(cudaMemcpyAsync(ctx->d_X + p0 * 3, X + p0 * 3, (size_t)(p1 - p0) * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(ctx->d_ready, ctx->h_ready_vals + g + 1, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    ctx->cur_ready = ctx->d_ready; ctx->cur_ready_frames = per;
+    return TDLO_OK;
+}
+// after the kernel has been queued: later work on the main stream must not overtake the copy stream
+static int upload_points_join(tdlo_ctx* ctx) {
+    if (ctx->cur_ready) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    ctx->cur_ready = nullptr; ctx->cur_ready_frames = 0;
+    return TDLO_OK;
+}
+
 extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, const tdlo_cpd_params* p) {
     if (!ctx) return TDLO_ERR_INVALID;
     if (!b || !p) return fail(ctx, TDLO_ERR_INVALID, "null batch/params");
@@ -431,7 +479,6 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     if (b->n_nodes) for (size_t f = 0; f < F; f++) if (b->n_nodes[f] > (int)S || b->n_nodes[f] < 0) return fail(ctx, TDLO_ERR_INVALID, "n_nodes[%zu] outside [0,node_stride]", f);
     CK(cudaSetDevice(ctx->device));
     if (b->H && !ctx->d_H) CK(dalloc(&ctx->d_H, (size_t)ctx->max_frames * ctx->max_nodes * ctx->max_nodes));
-    H2D(ctx->d_X, b->X, (size_t)total * 3 * sizeof(double));
     H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
     H2D(ctx->d_Y, b->Y, F * S * 3 * sizeof(double));
     H2D(ctx->d_sigma2, b->sigma2, F * sizeof(double));
@@ -440,6 +487,7 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     if (b->n_priors) H2D(ctx->d_npriors, b->n_priors, F * sizeof(int));
     if (b->n_visible) H2D(ctx->d_nvis, b->n_visible, F * sizeof(int));
     if (b->H) H2D(ctx->d_H, b->H, F * S * S * sizeof(double));
+    { int rcu = upload_points(ctx, b->X, b->x_offsets, (int)F); if (rcu) return rcu; }
     tdlo_cpd_batch d = *b;
     d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.sigma2 = ctx->d_sigma2;
     d.n_nodes = b->n_nodes ? ctx->d_nnodes : nullptr;
@@ -451,6 +499,7 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     ctx->points_hint = total / (long long)F;
     int rc = tdlo_cpd_lle_batched_device(ctx, &d, p, ctx->stream);
     ctx->points_hint = 0;
+    { int rcj = upload_points_join(ctx); if (!rc) rc = rcj; }
     if (rc) return rc;
     D2H(b->Y, ctx->d_Y, F * S * 3 * sizeof(double));
     D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));
@@ -487,7 +536,6 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     }
     CK(cudaSetDevice(ctx->device));
     if (b->H_pre && !ctx->d_H) CK(dalloc(&ctx->d_H, (size_t)ctx->max_frames * ctx->max_nodes * ctx->max_nodes));
-    H2D(ctx->d_X, b->X, (size_t)total * 3 * sizeof(double));
     H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
     H2D(ctx->d_Y, b->Y, F * N * 3 * sizeof(double));
     H2D(ctx->d_sigma2, b->sigma2, F * sizeof(double));
@@ -497,6 +545,7 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (b->visible_offsets[F] > 0) H2D(ctx->d_vis, b->visible, (size_t)b->visible_offsets[F] * sizeof(int));
     if (b->visible_ext_offsets[F] > 0) H2D(ctx->d_ext, b->visible_ext, (size_t)b->visible_ext_offsets[F] * sizeof(int));
     if (b->H_pre) H2D(ctx->d_H, b->H_pre, F * N * N * sizeof(double));
+    { int rcu = upload_points(ctx, b->X, b->x_offsets, (int)F); if (rcu) return rcu; }
     tdlo_track_batch d = *b;
     d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.sigma2 = ctx->d_sigma2;
     d.geodesic_coord = ctx->d_rest;
@@ -508,6 +557,7 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     ctx->points_hint = total / (long long)F;
     int rc = tdlo_tracking_step_batched_device(ctx, &d, p, ctx->stream);
     ctx->points_hint = 0;
+    { int rcj = upload_points_join(ctx); if (!rc) rc = rcj; }
     if (rc) return rc;
     D2H(b->Y, ctx->d_Y, F * N * 3 * sizeof(double));
     D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));

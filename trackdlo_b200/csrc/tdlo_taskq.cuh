@@ -111,6 +111,7 @@ struct TqArgs {
     double* part; double* dminp; double* gath; int* nkept;   // per global chunk
     double4* tsph;                   // per tile of 32 sorted points: bounding sphere {centre = first point, radius}; [chunk id][chunk/32]
     int part_stride;                 // doubles per chunk in `part`
+    const int* ready; int ready_frames;   // optional: frames [0, *ready * ready_frames) have their points uploaded (pipelined H2D)
     TqSmemL L;
 };
 
@@ -138,6 +139,11 @@ __device__ __forceinline__ double4 ldcg4(const double4* p) {
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
@@ -605,6 +611,13 @@ __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int s
     const int f = fr.f;
     double* scr = fr.scr;
     const TqScr& sc = fr.sc;
+    if (a.ready && stage == 0) {           // points of this frame still in flight on the copy stream? (host-buffer entry points)
+        if (tid == 0) {
+            unsigned ns = 256;
+            while ((long long)ld_acquire_s32(a.ready) * a.ready_frames <= f) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+        }
+        __syncthreads();
+    }
     int Nn, n_priors = 0, n_visible = 0;
     const double* priors = nullptr;
     const double* Hext = nullptr;
