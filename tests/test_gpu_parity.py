@@ -39,7 +39,8 @@ def ctx():
 # Gaussian truncation (z_cut = 100) and with exact-zero skipping only (z_cut = 745.2), small chunks (many
 # partial sums per frame) and the 256-thread kernel variant; "cluster" = the cluster-per-frame engine.
 ENGINE_CFGS = {
-    "tq": dict(engine=1, chunk_points=1024, truncation=100.0, threads=224),
+    "tq": dict(engine=1, chunk_points=0, truncation=100.0, threads=256),
+    "tq_224thr": dict(engine=1, chunk_points=1024, truncation=100.0, threads=224),
     "tq_exact_small_chunks": dict(engine=1, chunk_points=256, truncation=745.2, threads=224),
     "tq_256thr": dict(engine=1, chunk_points=2048, truncation=100.0, threads=256),
     "cluster": dict(engine=0),

@@ -48,7 +48,7 @@ struct tdlo_ctx {
     std::vector<int> h_vslice, h_vfirst;
     // task-queue engine (tdlo_taskq.cuh)
     int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
-    int tq_chunk = 1024;            // raw points per chunk task
+    int tq_chunk = 0;               // raw points per chunk task (0 = automatic: 1024, or 2048 / 4096 for large batches)
     int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
@@ -217,8 +217,19 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     if (a.n_frames > 0x1ffff) return fail(ctx, TDLO_ERR_INVALID, "task-queue engine: at most 131071 frames per call (got %d)", a.n_frames);
     const int nmax = a.nmax;
     const int threads = ctx->tq_threads;
+    // ---- chunk size: small chunks shorten a frame's E-wave (few frames: latency bound), large chunks amortise the
+    // per-task overhead (many frames: throughput bound).  Measured on C2 / C4 shapes: scripts/c4_probe.py.
+    int chunk = ctx->tq_chunk;
+    if (chunk == 0) {
+        // chosen from the context CAPACITY (not the batch), so that host- and device-pointer entry points split the
+        // points identically and stay bit-identical to each other
+        const long long est = ctx->max_points;
+        const long long slots = 2LL * ctx->sm_count;
+        chunk = 1024;                                  // the largest chunk that still gives every CTA slot >= 2 tasks per wave
+        if (est / 2048 >= 2 * slots) chunk = 2048;
+        if (est / 4096 >= 2 * slots) chunk = 4096;
+    }
     // ---- workspace (allocated on first use / when the chunk size changes)
-    const int chunk = ctx->tq_chunk;
     if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {
         void* old[] = {ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph};
         CK(cudaDeviceSynchronize());
@@ -752,7 +763,7 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             ctx->engine = (int)value; return TDLO_OK;
         case TDLO_OPT_CHUNK_POINTS: {
             const int c = (int)value;
-            if (c < 256 || c > (1 << 20) || (c % 32)) return fail(ctx, TDLO_ERR_INVALID, "chunk must be a multiple of 32 in [256, 2^20]");
+            if (c != 0 && (c < 256 || c > (1 << 20) || (c % 32))) return fail(ctx, TDLO_ERR_INVALID, "chunk must be 0 (automatic) or a multiple of 32 in [256, 2^20]");
             ctx->tq_chunk = c; return TDLO_OK;
         }
         case TDLO_OPT_TRUNCATION:
