@@ -200,7 +200,8 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         cut into chunk tasks that any SM may run, the CTA finishing a frame's last chunk runs
  *                         its M-step; 0 = cluster-per-frame engine.
  *  TDLO_OPT_CHUNK_POINTS  raw points per chunk task; 0 (default) = automatic from the context's point
- *                         capacity: 1024, or 2048 / 4096 for large batches (results are bit-deterministic for a given chunk size).
+ *                         capacity: 256 / 512 for small contexts (one live sequence), 1024, or 2048 / 4096 for large batches (results are
+ *                         bit-deterministic for a given chunk size).
  *  TDLO_OPT_TRUNCATION    z_cut: affinity entries exp(-z) with z > z_cut are skipped.  745.2 skips only entries
  *                         that are exactly 0 in the reference (double underflow); the default 100 skips entries
  *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.

@@ -225,9 +225,11 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
         // points identically and stay bit-identical to each other
         const long long est = ctx->max_points;
         const long long slots = 2LL * ctx->sm_count;
-        chunk = 1024;                                  // the largest chunk that still gives every CTA slot >= 2 tasks per wave
-        if (est / 2048 >= 2 * slots) chunk = 2048;
-        if (est / 4096 >= 2 * slots) chunk = 4096;
+        chunk = 1024;                                  // the largest chunk that still gives every CTA slot >= 2 tasks per wave;
+        if (est / 2048 >= 2 * slots) chunk = 2048;     // small contexts (a single live sequence): short tasks, the E-wave
+        if (est / 4096 >= 2 * slots) chunk = 4096;     // latency is on the frame's critical path
+        if (est < 512 * slots) chunk = 512;
+        if (est < 256 * slots) chunk = 256;
     }
     // ---- workspace (allocated on first use / when the chunk size changes)
     if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {
