@@ -48,8 +48,10 @@ def test_struct_layout_matches_header():
 #include "trackdlo_b200.h"
 int main(void){
   printf("%zu %zu %zu %zu ", sizeof(tdlo_cpd_params), sizeof(tdlo_track_params), sizeof(tdlo_cpd_batch), sizeof(tdlo_track_batch));
-  printf("%zu %zu %zu %zu\n", offsetof(tdlo_cpd_params, max_iter), offsetof(tdlo_track_params, max_iter),
+  printf("%zu %zu %zu %zu ", offsetof(tdlo_cpd_params, max_iter), offsetof(tdlo_track_params, max_iter),
          offsetof(tdlo_cpd_batch, status), offsetof(tdlo_track_batch, state));
+  printf("%zu %zu %zu %zu\n", sizeof(tdlo_vis_batch), offsetof(tdlo_vis_batch, visible_ext_offsets),
+         sizeof(tdlo_seq_batch), offsetof(tdlo_seq_batch, status_traj));
   return 0; }
 '''
     import tempfile
@@ -62,6 +64,8 @@ int main(void){
     assert vals[2] == C.sizeof(api.CpdBatchC) and vals[3] == C.sizeof(api.TrackBatchC)
     assert vals[4] == api.CpdParamsC.max_iter.offset and vals[5] == api.TrackParamsC.max_iter.offset
     assert vals[6] == api.CpdBatchC.status.offset and vals[7] == api.TrackBatchC.state.offset
+    assert vals[8] == C.sizeof(api.VisBatchC) and vals[9] == api.VisBatchC.visible_ext_offsets.offset
+    assert vals[10] == C.sizeof(api.SeqBatchC) and vals[11] == api.SeqBatchC.status_traj.offset
 
 
 def test_create_fails_loudly_without_gpu():

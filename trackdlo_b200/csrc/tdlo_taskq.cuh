@@ -62,7 +62,7 @@ __host__ __device__ inline TqScr tq_scr_layout(int N) {
 // ---- shared memory layout (bytes).  One fixed head (exp table, node data) + a region that is the E-step's
 // P tiles during chunk tasks and the M-step's [A|B] + vectors during continuations.
 struct TqSmemL {
-    int tab, node4, nsoa, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, total;
+    int tab, node4, nsoa, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, chol_doubles, total;
 };
 __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     TqSmemL l{};
@@ -83,9 +83,6 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     o = u;
     l.y0 = o; o += 3 * N * 8;
     l.s = o; o += N * 8;
-    l.yext = o; o += 3 * N * 8;
-    l.jd = o; o += N * 8;
-    l.hy0 = o; o += 3 * N * 8;
     l.p1 = o; o += N * 8;
     l.px = o; o += 3 * N * 8;
     l.wsol = o; o += 3 * N * 8;
@@ -94,8 +91,15 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     l.prow = o; o += N * 4;
     l.used = o; o += N * 4;
     o = (o + 31) & ~31;
+    // yext / jd / hy0 are only read while [A|B] is assembled: the blocked Cholesky (Nn > 64) takes its workspace from
+    // here to the end of the region
+    l.yext = o; o += 3 * N * 8;
+    l.jd = o; o += N * 8;
+    l.hy0 = o; o += 3 * N * 8;
+    o = (o + 31) & ~31;
     l.ab = o;
     l.ab_doubles = (e_end - o) / 8;
+    l.chol_doubles = (e_end - l.yext) / 8;
     l.total = e_end;
     return l;
 }
@@ -914,7 +918,7 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
     // ---- assemble [A | B] (trackdlo.cpp:392-413); SPD form without LLE (see cpd_run)
     const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
     const bool small = ab_in_smem && Nn <= 64;
-    const int chol_nb = (!small && !p.include_lle) ? ((long long)Nn * 20 + Nn + 64 <= (long long)a.L.ab_doubles ? 16 : ((long long)Nn * 12 + Nn + 64 <= (long long)a.L.ab_doubles ? 8 : 0)) : 0;
+    const int chol_nb = (!small && !p.include_lle) ? ((long long)Nn * 20 + Nn + 64 <= (long long)a.L.chol_doubles ? 16 : ((long long)Nn * 12 + Nn + 64 <= (long long)a.L.chol_doubles ? 8 : 0)) : 0;
     const bool spd = !p.include_lle && (small || chol_nb > 0);
     if (spd) {
         for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
@@ -959,7 +963,7 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
         double sdreg[3];
         for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) { sdreg[t] = sm.tnew[i / 3]; sm.wsol[i] = AB[(long long)(i / 3) * ld + Nn + (i % 3)]; }
         __syncthreads();
-        sing = chol_nb == 16 ? chol_solve_blocked<16>(AB, Nn, ld, sm.ab, sm.wsol) : chol_solve_blocked<8>(AB, Nn, ld, sm.ab, sm.wsol);
+        sing = chol_nb == 16 ? chol_solve_blocked<16>(AB, Nn, ld, sm.yext, sm.wsol) : chol_solve_blocked<8>(AB, Nn, ld, sm.yext, sm.wsol);   // workspace: yext .. end of the region
         for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
         __syncthreads();
     } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 43, sm.wsol);
