@@ -310,9 +310,10 @@ def run_ours(args):
             ach = alg_b / kern_s / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic_bytes(),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_b,
-                    "kernel": "tdlo_tq_kernel<2,3> (one persistent task-queue launch per step: prune, E-step chunks, M-steps, traversal)",
+                    "kernel": "tdlo_tq_kernel<2,256,2> (one persistent task-queue launch per step: prune, E-step chunks, M-steps, traversal)",
                     "note": "the path is 52 flop/B at Nn=50 (SURVEY.md §8d): compute-side bound, HBM fraction is tiny by construction; "
-                            "see `fp64` for the FP64-pipe fraction and profiles/ for the shared-memory (MIO) pipe that limits the E-step"}
+                            "see `fp64` for the FP64 fraction; the E-step is bound by the SMSP issue port (an FP64 instruction holds it ~2.3 cycles, "
+                            "profiles/r1_ilp_microbench.txt, DESIGN.md §7)"}
             tf = alg_f / kern_s / 1e12
             fp64 = {"achieved": tf, "peak": FP64_PEAK_MEASURED_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_MEASURED_TFLOPS,
                     "peak_source": "measured DFMA loop (scripts/micro/fp64pipe.cu -> profiles/r1_fp64pipe_microbench.txt)",

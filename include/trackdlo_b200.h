@@ -190,9 +190,11 @@ int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* batch, const tdlo_
  * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */
 int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]);
 
-/* Development aid: enables/disables the kernel's per-phase cycle counters and returns + resets the
- * totals accumulated since the previous call.  cycles[0..5] (cluster rank 0) = {set-up, visibility
- * pre-pass, E-step, wait, M-step, wait}; cycles[8..13] = the same for the other ranks.  Synchronises. */
+/* Development aid: enables/disables the kernel's per-phase cycle counters and returns + resets the totals accumulated
+ * since the previous call.  Task-queue engine: cycles[0..9] = {queue wait, prune, visibility pre-pass, E-step, start_call,
+ * wave glue, M-step gather+assemble, solve, update, finish_call}, [10..15] = {E-step tasks, tiles, sum of window widths,
+ * row blocks, per-warp tile-loop cycles, end-of-task reduction cycles}.  Cluster engine: cycles[0..7] (rank 0) = {set-up,
+ * visibility pre-pass, E-step, wait, assemble, wait, solve, update}, [8..15] the other ranks.  Synchronises. */
 int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 
 /* Engine options.
