@@ -321,6 +321,45 @@ def test_sequence_mode_matches_frame_by_frame_oracle(ctx):
         assert rel(r["Y"][s], Y) < 1e-6 and abs(r["sigma2"][s] - s2) / s2 < 1e-5
 
 
+def test_c3_full_size_occlusion_visibility_branch(ctx):
+    """BASELINE configs[2]: Nn=50, Mp0=50000 with 40 % of the DLO occluded (~30000 points remain, ~31 of 50 nodes visible):
+    the k_vis branch (trackdlo.cpp:358-379) and the traversal priors are active in the main registration.  Full
+    tracking_step against the oracle at the default tolerance (converges) -- iteration counts must match exactly."""
+    f = synth.make_frame(0, n_nodes=50, n_points=50000, occlusion=0.4)
+    assert 0 < len(f["vis"]) < 50
+    one = lambda n: np.array([0, n], np.int64)
+    tp = api.TrackParams()
+    r = ctx.tracking_step_batched(f["X"], one(len(f["X"])), f["Y"][None], np.zeros(1), f["rest"][None], f["vis"], one(len(f["vis"])),
+                                  f["vis_ext"], one(len(f["vis_ext"])), tp)
+    o = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], oracle.TrackParams())
+    assert list(r["iters"][0]) == list(o["iters"]) and r["state"][0] == o["state"] and r["status"][0] == 0
+    assert rel(r["Y"][0], o["Y"]) < 1e-6 < GATE
+    assert abs(r["sigma2"][0] - o["sigma2"]) / o["sigma2"] < 1e-5
+
+
+def test_c5_size_dense_solve_properties():
+    """BASELINE configs[4] shape (Nn=200, Mp=100000): blocked-Cholesky solve path.  Size-independent properties at full
+    size: rigid-translation equivariance of Y, invariance of W, and bit-exact repeatability; plus the oracle on a
+    2-iteration run."""
+    Nn, Mp = 200, 100000
+    f = synth.make_frame(2, n_nodes=Nn, n_points=Mp)
+    c = api.Context(max_frames=1, max_nodes=Nn, max_points_total=Mp)
+    try:
+        one = np.array([0, Mp], np.int64)
+        pg = api.CpdParams(max_iter=6, tol=0.0)
+        r = c.cpd_lle_batched(f["X"], one, f["Y"][None], np.zeros(1), pg)
+        r2 = c.cpd_lle_batched(f["X"], one, f["Y"][None], np.zeros(1), pg)
+        assert r["iters"][0] == 6 and np.array_equal(r["Y"], r2["Y"]) and np.array_equal(r["W"], r2["W"])
+        t = np.array([0.125, -0.25, 0.0625])
+        rt = c.cpd_lle_batched(f["X"] + t, one, (f["Y"] + t)[None], np.zeros(1), pg)
+        assert rel(rt["Y"][0] - t, r["Y"][0]) < 1e-8 and rel(rt["W"][0], r["W"][0]) < 1e-5
+        o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(max_iter=2, tol=0.0))
+        g = c.cpd_lle_batched(f["X"], one, f["Y"][None], np.zeros(1), api.CpdParams(max_iter=2, tol=0.0))
+        assert rel(g["Y"][0], o["Y"]) < 1e-7 and rel(g["W"][0], o["W"]) < 1e-6
+    finally:
+        c.close()
+
+
 def test_pipelined_upload_matches_device_entry(ctx):
     """Host-buffer entry with >= 16 frames / >= 200k points: the clouds are uploaded in groups on a copy stream while the
     persistent kernel already registers the first frames (a frame's first task waits for its group's flag).  Results
