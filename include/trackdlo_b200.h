@@ -209,7 +209,8 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
  *  TDLO_OPT_THREADS       kernel variant of the task-queue engine for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
- *                         224 (3 CTAs/SM, 80 registers), 288 or 320 (2 CTAs/SM, 96 registers).  Nn > 64 always uses 256. */
+ *                         224 (3 CTAs/SM, 80 registers; measured equal or slower, as were 288/320-thread variants).
+ *                         Nn > 64 always uses 256. */
 #define TDLO_OPT_ENGINE 1
 #define TDLO_OPT_CHUNK_POINTS 2
 #define TDLO_OPT_TRUNCATION 3

@@ -261,13 +261,11 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     if (nmax <= 64) {
         npass = 2;
         if (threads <= 224) kern = tdlo_tq_kernel<2, 224, 3>;
-        else if (threads <= 256) kern = tdlo_tq_kernel<2, 256, 2>;
-        else if (threads <= 288) kern = tdlo_tq_kernel<2, 288, 2>;
-        else kern = tdlo_tq_kernel<2, 320, 2>;
+        else kern = tdlo_tq_kernel<2, 256, 2>;
     }
     else if (nmax <= 128) { npass = 4; kern = tdlo_tq_kernel<4, 256, 2>; }
     else { npass = 8; kern = tdlo_tq_kernel<8, 256, 2>; }
-    const int threads_eff = nmax <= 64 ? (threads <= 224 ? 224 : threads <= 256 ? 256 : threads <= 288 ? 288 : 320) : 256;
+    const int threads_eff = (nmax <= 64 && threads <= 224) ? 224 : 256;
     const TqSmemL L = tq_smem_layout(32 * npass, threads_eff / 32);
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -776,7 +774,7 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             ctx->tq_inflight = (int)value; return TDLO_OK;
         case TDLO_OPT_THREADS: {
             const int t = (int)value;
-            if (t != 224 && t != 256 && t != 288 && t != 320) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256/288/320 (2 CTAs/SM)");
+            if (t != 224 && t != 256) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256 (2 CTAs/SM)");
             ctx->tq_threads = t; return TDLO_OK;
         }
         default: return fail(ctx, TDLO_ERR_INVALID, "unknown option %d", option);

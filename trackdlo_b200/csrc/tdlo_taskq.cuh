@@ -19,7 +19,7 @@
 
 namespace tdlo {
 
-constexpr int TQ_THREADS = 320;            // upper bound of threads per CTA (the host picks 224 or 256)
+constexpr int TQ_THREADS = 256;            // upper bound of threads per CTA (the host picks 224 or 256)
 constexpr int TQ_ROWS = 32, TQ_RS = 33;    // P tile of a warp: 32 node rows x 32 points (+1 pad)
 
 enum { TK_PRUNE = 1, TK_DMIN = 2, TK_ESTEP = 3, TK_EXIT = 7 };
