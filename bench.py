@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -259,12 +259,12 @@ def run_ours(args):
         return time.perf_counter() - t0
 
     # ---------------- device-resident timing (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                    # nvidia-smi needs ~0.1 s to emit its first sample: start it before the warm-up
     for _ in range(max(args.warmup, 3)):
         device_step(False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     evs = [device_step(True) for _ in range(args.steps)]
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
