@@ -1,0 +1,29 @@
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck): gpurun -- compute-sanitizer --tool racecheck python scripts/sanitizer_case.py"""
+import sys, os
+sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
+import numpy as np
+from trackdlo_b200 import api, synth
+f = synth.make_frame(0, n_nodes=30, n_points=700, occlusion=0.3)
+ctx = api.Context(max_frames=2, max_nodes=30, max_points_total=1400)
+one = lambda n: np.array([0, n, 2 * n], np.int64)
+X = np.concatenate([f["X"], f["X"]]); n = len(f["X"])
+Y = np.stack([f["Y"], f["Y"]]); rest = np.stack([f["rest"], f["rest"]])
+vis = np.concatenate([f["vis"], f["vis"]]); ext = np.concatenate([f["vis_ext"], f["vis_ext"]])
+vo = np.array([0, len(f["vis"]), 2 * len(f["vis"])], np.int64); eo = np.array([0, len(f["vis_ext"]), 2 * len(f["vis_ext"])], np.int64)
+r = ctx.tracking_step_batched(X, one(n), Y, np.zeros(2), rest, vis, vo, ext, eo, api.TrackParams(max_iter=4))
+print("iters", r["iters"].tolist(), "status", r["status"].tolist())
+v = ctx.visibility_batched(X, one(n), Y, rest)
+print("vis ok", len(v["visible"]))
+ctx.close()
+# Nn = 100: blocked Cholesky (16-column panels, FP64 MMA); Nn = 200: 8/16-column panels; cluster engine on the small case
+for Nn, Mp in ((100, 1500), (200, 2500)):
+    g = synth.make_frame(1, n_nodes=Nn, n_points=Mp)
+    c2 = api.Context(max_frames=1, max_nodes=Nn, max_points_total=Mp)
+    r2 = c2.cpd_lle_batched(g["X"], np.array([0, Mp], np.int64), g["Y"][None], np.zeros(1), api.CpdParams(max_iter=2, tol=0.0))
+    print("Nn", Nn, "iters", r2["iters"].tolist(), "status", r2["status"].tolist())
+    c2.close()
+c3 = api.Context(max_frames=1, max_nodes=30, max_points_total=700)
+c3.set_option("engine", 0)
+r3 = c3.cpd_lle_batched(f["X"], np.array([0, n], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=3, tol=0.0, include_lle=True, beta=3.0, lambda_=1.0))
+print("cluster engine iters", r3["iters"].tolist())
+c3.close()

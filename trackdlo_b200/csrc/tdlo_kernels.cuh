@@ -908,6 +908,7 @@ __device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double
                 }
                 if (!(x > 0.0) || !(fabs(rs) <= 1.79e308)) { if (lane == 0) *flag = 1; }
                 const double lrc = (lane > c && lane < nb) ? Lp[lane * LDP + c] * rs : 0.0;
+                __syncwarp();                                     // every lane has read Lp[c][c] before lane c overwrites it
                 if (lane == c) { Lp[c * LDP + c] = x * rs; dinv[k0 + c] = rs; }
                 if (lane > c && lane < nb) Lp[lane * LDP + c] = lrc;
                 __syncwarp();
