@@ -164,6 +164,20 @@ int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);
 /* Device pointers; asynchronous on `stream` -- chain it in front of tdlo_tracking_step_batched_device. */
 int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* batch, void* stream);
 
+/* Evaluator frame error (trackdlo/src/evaluator.cpp:233-283, 333-341): for every frame the mean distance of
+ * the nodes of Y_track to the nearest segment of the polyline Y_true, symmetrised ((E1 + E2) / 2). */
+typedef struct tdlo_err_batch {
+    int32_t n_frames;
+    int32_t n_track;          /* nodes of every tracked polyline (<= TDLO_MAX_NODES, >= 2) */
+    int32_t n_true;           /* nodes of every ground-truth polyline (<= TDLO_MAX_NODES, >= 2) */
+    int32_t reserved;
+    const double* Y_track;    /* [n_frames][n_track][3] */
+    const double* Y_true;     /* [n_frames][n_true][3]  */
+    double* error;            /* out [n_frames]         */
+} tdlo_err_batch;
+int tdlo_tracking_error_batched(tdlo_ctx* ctx, const tdlo_err_batch* batch);                      /* host pointers, synchronous */
+int tdlo_tracking_error_batched_device(tdlo_ctx* ctx, const tdlo_err_batch* batch, void* stream);  /* device pointers */
+
 /* Sequence mode: S independent trackers advanced over T consecutive frames WITHOUT returning to the host
  * between frames.  Per step t and sequence s, exactly what trackdlo_node.cpp does per callback: visibility lists from
  * Y^{t-1} and the step's cloud (tdlo_visibility_batched semantics, visibility_threshold = params->visibility_threshold),

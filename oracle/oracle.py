@@ -151,6 +151,14 @@ def visibility(X, Y, node_coord, visibility_threshold=0.008, d_vis=0.06):
     return dict(dmin=dmin, vis=vis[:nv].copy(), vis_ext=ext[:ne.value].copy())
 
 
+def tracking_error(Y_track, Y_true):
+    """Oracle of the evaluator's frame error (evaluator.cpp:233-283, 333-341)."""
+    L = lib()
+    a = _f64(Y_track, (-1, 3)); b = _f64(Y_true, (-1, 3))
+    L.oracle_tracking_error.restype = C.c_double
+    return float(L.oracle_tracking_error(_p(a), C.c_int32(a.shape[0]), _p(b), C.c_int32(b.shape[0])))
+
+
 def traverse_euclidean(geodesic_coord, guide, vis, alignment, align_idx=-1):
     L = lib()
     geo = _f64(geodesic_coord); g = _f64(guide, (-1, 3)); v = np.ascontiguousarray(vis, dtype=np.int32)

@@ -801,4 +801,40 @@ int oracle_visibility(const double* X, int64_t Mp, const double* Y, int32_t Nn, 
     return nv;
 }
 
+// Evaluator error metric: trackdlo/src/evaluator.cpp:233-283 (calc_min_distance, get_piecewise_error)
+// and :333-341 (compute_error), helpers utils.cpp:477-489.  Mean over the nodes of one polyline of the distance to the
+// nearest segment of the other, symmetrised.
+static double seg_point_distance(const double* A, const double* B, const double* E) {
+    const double AB[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, AE[3] = {E[0] - A[0], E[1] - A[1], E[2] - A[2]};
+    const double cx = AE[1] * AB[2] - AE[2] * AB[1], cy = -(AE[0] * AB[2] - AE[2] * AB[0]), cz = AE[0] * AB[1] - AE[1] * AB[0];
+    const double abab = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    const double aeab = AE[0] * AB[0] + AE[1] * AB[1] + AE[2] * AB[2];
+    double distance = std::sqrt(cx * cx + cy * cy + cz * cz) / std::sqrt(abab);
+    const double P[3] = {A[0] + AB[0] * aeab / abab, A[1] + AB[1] * aeab / abab, A[2] + AB[2] * aeab / abab};
+    const double AP[3] = {P[0] - A[0], P[1] - A[1], P[2] - A[2]};
+    const double apab = AP[0] * AB[0] + AP[1] * AB[1] + AP[2] * AB[2];
+    if (apab < 0 || apab > abab) {
+        const double BE[3] = {E[0] - B[0], E[1] - B[1], E[2] - B[2]};
+        const double dAE = std::sqrt(AE[0] * AE[0] + AE[1] * AE[1] + AE[2] * AE[2]);
+        const double dBE = std::sqrt(BE[0] * BE[0] + BE[1] * BE[1] + BE[2] * BE[2]);
+        distance = dAE > dBE ? dBE : dAE;
+    }
+    return distance;
+}
+static double piecewise_error(const double* Yt, int nt, const double* Yr, int nr) {
+    double total = 0.0;
+    for (int idx = 0; idx < nt; idx++) {
+        double dist = -1;
+        for (int i = 0; i < nr - 1; i++) {
+            const double di = seg_point_distance(Yr + 3 * i, Yr + 3 * (i + 1), Yt + 3 * idx);
+            if (dist == -1 || di < dist) dist = di;
+        }
+        total += dist;
+    }
+    return total / nt;
+}
+double oracle_tracking_error(const double* Y_track, int32_t n_track, const double* Y_true, int32_t n_true) {
+    return (piecewise_error(Y_track, n_track, Y_true, n_true) + piecewise_error(Y_true, n_true, Y_track, n_track)) / 2;
+}
+
 }  // extern "C"

@@ -50,8 +50,9 @@ int main(void){
   printf("%zu %zu %zu %zu ", sizeof(tdlo_cpd_params), sizeof(tdlo_track_params), sizeof(tdlo_cpd_batch), sizeof(tdlo_track_batch));
   printf("%zu %zu %zu %zu ", offsetof(tdlo_cpd_params, max_iter), offsetof(tdlo_track_params, max_iter),
          offsetof(tdlo_cpd_batch, status), offsetof(tdlo_track_batch, state));
-  printf("%zu %zu %zu %zu\n", sizeof(tdlo_vis_batch), offsetof(tdlo_vis_batch, visible_ext_offsets),
+  printf("%zu %zu %zu %zu ", sizeof(tdlo_vis_batch), offsetof(tdlo_vis_batch, visible_ext_offsets),
          sizeof(tdlo_seq_batch), offsetof(tdlo_seq_batch, status_traj));
+  printf("%zu %zu\n", sizeof(tdlo_err_batch), offsetof(tdlo_err_batch, error));
   return 0; }
 '''
     import tempfile
@@ -66,6 +67,7 @@ int main(void){
     assert vals[6] == api.CpdBatchC.status.offset and vals[7] == api.TrackBatchC.state.offset
     assert vals[8] == C.sizeof(api.VisBatchC) and vals[9] == api.VisBatchC.visible_ext_offsets.offset
     assert vals[10] == C.sizeof(api.SeqBatchC) and vals[11] == api.SeqBatchC.status_traj.offset
+    assert vals[12] == C.sizeof(api.ErrBatchC) and vals[13] == api.ErrBatchC.error.offset
 
 
 def test_create_fails_loudly_without_gpu():

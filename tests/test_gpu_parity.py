@@ -385,6 +385,20 @@ def test_pipelined_upload_matches_device_entry(ctx):
     assert np.array_equal(h2["Y"], h["Y"])
 
 
+def test_evaluator_error_metric_matches_oracle(ctx):
+    """the evaluator's symmetric node-to-polyline frame error (evaluator.cpp:233-283, 333-341)."""
+    rng = np.random.default_rng(11)
+    F, N1, N2 = 5, 50, 37
+    Yt = np.stack([synth.curve(np.linspace(0, 1, N1)) + rng.normal(0, 0.004, (N1, 3)) for _ in range(F)])
+    Yr = np.stack([synth.observed_curve(np.linspace(0, 1, N2), i) for i in range(F)])
+    Yt[0, 0] = Yr[0, 0] - 0.05 * (Yr[0, 1] - Yr[0, 0])          # a node beyond the end of the polyline: end-point branch
+    e = ctx.tracking_error_batched(Yt, Yr)
+    for i in range(F):
+        o = oracle.tracking_error(Yt[i], Yr[i])
+        assert abs(e[i] - o) <= 1e-15 * max(1.0, abs(o)) + 1e-18, (i, e[i], o)
+    assert np.all(e > 0)
+
+
 def test_engine_options_are_validated(ctx):
     for name, bad in (("engine", 2), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
                       ("threads", 128), ("inflight", -1)):

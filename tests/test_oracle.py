@@ -191,3 +191,17 @@ def test_visibility_front_end_oracle_matches_generator():
     f = synth.make_frame(7, n_nodes=20, n_points=100)
     r = oracle.visibility(f["X"][:0], f["Y"], f["rest"])
     assert len(r["vis"]) == 0 and len(r["vis_ext"]) == 0 and np.all(r["dmin"] == 100000.0)
+
+
+def test_evaluator_error_metric_oracle_known_answers():
+    """oracle_tracking_error (evaluator.cpp:233-283, 333-341) on hand-computable cases."""
+    import oracle
+    line = np.array([[0.0, 0, 0], [1.0, 0, 0], [2.0, 0, 0]])
+    assert oracle.tracking_error(line, line) == 0.0
+    up = line + np.array([0.0, 0.5, 0.0])
+    assert abs(oracle.tracking_error(up, line) - 0.5) < 1e-15            # parallel polylines 0.5 apart
+    # nodes beyond the ends: distances to the end points, not to the infinite lines
+    p = np.array([[3.0, 4.0, 0.0], [4.0, 4.0, 0.0]])
+    e1 = (np.hypot(1.0, 4.0) + np.hypot(2.0, 4.0)) / 2                     # nodes of p -> end point (2,0,0)
+    e2 = (5.0 + np.hypot(2.0, 4.0) + np.hypot(1.0, 4.0)) / 3               # nodes of line -> end point (3,4,0)
+    assert abs(oracle.tracking_error(p, line) - (e1 + e2) / 2) < 1e-14

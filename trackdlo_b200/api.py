@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
     "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases", "tdlo_set_option",
-    "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences",
+    "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences", "tdlo_tracking_error_batched", "tdlo_tracking_error_batched_device",
 ]
 
 
@@ -59,6 +59,11 @@ class VisBatchC(C.Structure):
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "node_coord")] + \
                [("visibility_threshold", C.c_double), ("d_vis", C.c_double)] + \
                [(n, C.c_void_p) for n in ("dmin", "visible", "visible_offsets", "visible_ext", "visible_ext_offsets")]
+
+
+class ErrBatchC(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_track", C.c_int32), ("n_true", C.c_int32), ("reserved", C.c_int32),
+                ("Y_track", C.c_void_p), ("Y_true", C.c_void_p), ("error", C.c_void_p)]
 
 
 class SeqBatchC(C.Structure):
@@ -134,6 +139,8 @@ def load_library():
         lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
         lib.tdlo_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+        lib.tdlo_tracking_error_batched.argtypes = [C.c_void_p, C.POINTER(ErrBatchC)]
+        lib.tdlo_tracking_error_batched_device.argtypes = [C.c_void_p, C.POINTER(ErrBatchC), C.c_void_p]
         lib.tdlo_track_sequences.argtypes = [C.c_void_p, C.POINTER(SeqBatchC), C.POINTER(TrackParamsC)]
         lib.tdlo_visibility_batched.argtypes = [C.c_void_p, C.POINTER(VisBatchC)]
         lib.tdlo_visibility_batched_device.argtypes = [C.c_void_p, C.POINTER(VisBatchC), C.c_void_p]
@@ -258,6 +265,15 @@ class Context:
         b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo))
         self._check(self.lib.tdlo_visibility_batched(self.h, C.byref(b)), "tdlo_visibility_batched")
         return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo)
+
+    # ------------------------------------------------------------------ evaluator frame error (evaluator.cpp:233-283, 333-341)
+    def tracking_error_batched(self, Y_track, Y_true):
+        a = _np(Y_track, np.float64); b = _np(Y_true, np.float64)
+        F = a.shape[0]
+        err = np.zeros(F)
+        eb = ErrBatchC(F, a.shape[1], b.shape[1], 0, _ptr(a), _ptr(b), _ptr(err))
+        self._check(self.lib.tdlo_tracking_error_batched(self.h, C.byref(eb)), "tdlo_tracking_error_batched")
+        return err
 
     # ------------------------------------------------------------------ sequence mode (visibility + tracking_step per frame on the device)
     def track_sequences(self, X, x_offsets, Y, sigma2, geodesic_coord, params: TrackParams, n_steps, d_vis=0.06):

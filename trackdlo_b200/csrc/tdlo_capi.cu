@@ -688,6 +688,53 @@ extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// evaluator frame error
+// ---------------------------------------------------------------------------------------------
+static int err_check(tdlo_ctx* ctx, const tdlo_err_batch* b) {
+    if (!b) return fail(ctx, TDLO_ERR_INVALID, "null batch");
+    if (b->n_frames < 0) return fail(ctx, TDLO_ERR_INVALID, "n_frames must be >= 0");
+    if (b->n_track < 2 || b->n_track > TDLO_MAX_NODES || b->n_true < 2 || b->n_true > TDLO_MAX_NODES)
+        return fail(ctx, TDLO_ERR_INVALID, "n_track / n_true must be in [2, %d]", TDLO_MAX_NODES);
+    if (!b->Y_track || !b->Y_true || !b->error) return fail(ctx, TDLO_ERR_INVALID, "Y_track, Y_true, error are required");
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_tracking_error_batched_device(tdlo_ctx* ctx, const tdlo_err_batch* b, void* stream) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = err_check(ctx, b);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (b->n_frames == 0) return TDLO_OK;
+    tdlo_tracking_error_kernel<<<b->n_frames, 256, 0, (cudaStream_t)stream>>>(b->n_track, b->n_true, b->Y_track, b->Y_true, b->error);
+    CK(cudaGetLastError());
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_tracking_error_batched(tdlo_ctx* ctx, const tdlo_err_batch* b) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = err_check(ctx, b);
+    if (rc) return rc;
+    if (b->n_frames == 0) return TDLO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t F = b->n_frames;
+    double *dt = nullptr, *dr = nullptr, *de = nullptr;
+    CK(dalloc(&dt, F * b->n_track * 3));
+    cudaError_t e1 = dalloc(&dr, F * b->n_true * 3), e2 = dalloc(&de, F);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(dt); cudaFree(dr); cudaFree(de); return fail(ctx, TDLO_ERR_NOMEM, "tracking error: out of device memory"); }
+    cudaMemcpyAsync(dt, b->Y_track, F * b->n_track * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dr, b->Y_true, F * b->n_true * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    tdlo_err_batch d = *b;
+    d.Y_track = dt; d.Y_true = dr; d.error = de;
+    rc = tdlo_tracking_error_batched_device(ctx, &d, ctx->stream);
+    cudaMemcpyAsync(b->error, de, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dt); cudaFree(dr); cudaFree(de);
+    if (rc) return rc;
+    if (es != cudaSuccess) return fail(ctx, TDLO_ERR_CUDA, "tracking error: %s", cudaGetErrorString(es));
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // sequence mode: visibility + tracking_step per frame, state carried on the device
 // ---------------------------------------------------------------------------------------------
 extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, const tdlo_track_params* p) {

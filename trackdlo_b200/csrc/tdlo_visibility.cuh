@@ -110,4 +110,58 @@ __global__ void __launch_bounds__(256) tdlo_vis_compact_kernel(const VisArgs a) 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Evaluator frame error (trackdlo/src/evaluator.cpp:233-283 calc_min_distance / get_piecewise_error,
+// :333-341 compute_error): mean distance of the nodes of one polyline to the nearest segment of the other, symmetrised.
+// One CTA per frame; node distances in parallel, summed in node order by one thread (same order as the reference).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double seg_point_distance(const double* A, const double* B, const double* E) {
+    const double ABx = B[0] - A[0], ABy = B[1] - A[1], ABz = B[2] - A[2];
+    const double AEx = E[0] - A[0], AEy = E[1] - A[1], AEz = E[2] - A[2];
+    const double cx = __dsub_rn(__dmul_rn(AEy, ABz), __dmul_rn(AEz, ABy));
+    const double cy = -__dsub_rn(__dmul_rn(AEx, ABz), __dmul_rn(AEz, ABx));
+    const double cz = __dsub_rn(__dmul_rn(AEx, ABy), __dmul_rn(AEy, ABx));
+    const double abab = __dadd_rn(__dadd_rn(__dmul_rn(ABx, ABx), __dmul_rn(ABy, ABy)), __dmul_rn(ABz, ABz));
+    const double aeab = __dadd_rn(__dadd_rn(__dmul_rn(AEx, ABx), __dmul_rn(AEy, ABy)), __dmul_rn(AEz, ABz));
+    double distance = __ddiv_rn(sqrt(__dadd_rn(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)), __dmul_rn(cz, cz))), sqrt(abab));
+    const double Px = __dadd_rn(A[0], __ddiv_rn(__dmul_rn(ABx, aeab), abab)), Py = __dadd_rn(A[1], __ddiv_rn(__dmul_rn(ABy, aeab), abab)),
+                 Pz = __dadd_rn(A[2], __ddiv_rn(__dmul_rn(ABz, aeab), abab));
+    const double APx = Px - A[0], APy = Py - A[1], APz = Pz - A[2];
+    const double apab = __dadd_rn(__dadd_rn(__dmul_rn(APx, ABx), __dmul_rn(APy, ABy)), __dmul_rn(APz, ABz));
+    if (apab < 0 || apab > abab) {
+        const double BEx = E[0] - B[0], BEy = E[1] - B[1], BEz = E[2] - B[2];
+        const double dAE = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(AEx, AEx), __dmul_rn(AEy, AEy)), __dmul_rn(AEz, AEz)));
+        const double dBE = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(BEx, BEx), __dmul_rn(BEy, BEy)), __dmul_rn(BEz, BEz)));
+        distance = dAE > dBE ? dBE : dAE;
+    }
+    return distance;
+}
+
+__global__ void __launch_bounds__(256) tdlo_tracking_error_kernel(int n_track, int n_true, const double* Yt_all, const double* Yr_all, double* err) {
+    __shared__ double yt[kMaxNodes * 3], yr[kMaxNodes * 3], d1[kMaxNodes], d2[kMaxNodes];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const double* Yt = Yt_all + (long long)f * n_track * 3;
+    const double* Yr = Yr_all + (long long)f * n_true * 3;
+    for (int i = tid; i < 3 * n_track; i += blockDim.x) yt[i] = Yt[i];
+    for (int i = tid; i < 3 * n_true; i += blockDim.x) yr[i] = Yr[i];
+    __syncthreads();
+    for (int idx = tid; idx < n_track; idx += blockDim.x) {
+        double dist = -1;
+        for (int i = 0; i < n_true - 1; i++) { const double di = seg_point_distance(yr + 3 * i, yr + 3 * (i + 1), yt + 3 * idx); if (dist == -1 || di < dist) dist = di; }
+        d1[idx] = dist;
+    }
+    for (int idx = tid; idx < n_true; idx += blockDim.x) {
+        double dist = -1;
+        for (int i = 0; i < n_track - 1; i++) { const double di = seg_point_distance(yt + 3 * i, yt + 3 * (i + 1), yr + 3 * idx); if (dist == -1 || di < dist) dist = di; }
+        d2[idx] = dist;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < n_track; i++) t1 += d1[i];
+        for (int i = 0; i < n_true; i++) t2 += d2[i];
+        err[f] = (t1 / n_track + t2 / n_true) / 2;
+    }
+}
+
 }  // namespace tdlo
