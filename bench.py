@@ -125,7 +125,7 @@ def run_reference(args):
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     cores = os.cpu_count() or 1
-    per_step = max(1, min(cores, 16))
+    per_step = max(1, min(cores, FRAMES_PER_GPU))          # one frame per host thread, up to the C2 batch of 64
     frames = make_workload(0, per_step)["frames"]
     tp = oracle.TrackParams(max_iter=MAX_ITER, tol=0.0)
     oracle.lib()
