@@ -1,0 +1,53 @@
+"""Randomised differential run: CUDA path (C ABI) vs the CPU oracle on random shapes (development aid).
+Usage: python scripts/fuzz_parity.py [n_cases] [seed]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import oracle
+from trackdlo_b200 import api, synth
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+worst = 0.0
+ctx = api.Context(max_frames=4, max_nodes=64, max_points_total=4 * 9000)
+for case in range(n_cases):
+    Nn = int(rng.integers(4, 65)); Mp = int(rng.integers(50, 9000)); occ = float(rng.choice([0.0, 0.0, 0.2, 0.45]))
+    f = synth.make_frame(int(rng.integers(0, 10000)), n_nodes=Nn, n_points=Mp, occlusion=occ)
+    ctx.set_option("chunk_points", int(rng.choice([0, 256, 512, 1024, 4096])))
+    ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
+    ctx.set_option("threads", int(rng.choice([224, 256])))
+    one = lambda n: np.array([0, n], np.int64)
+    if len(f["vis"]) == 0:
+        continue
+    mi = int(rng.integers(1, 25)); tol = float(rng.choice([0.0, 2e-4]))
+    if rng.random() < 0.5:
+        kw = dict(max_iter=mi, tol=tol, include_lle=bool(rng.random() < 0.3))
+        if kw["include_lle"]:
+            kw.update(beta=3.0, lambda_=1.0)
+        o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(**kw))
+        r = ctx.cpd_lle_batched(f["X"], one(len(f["X"])), f["Y"][None], np.zeros(1), api.CpdParams(**kw))
+        ok = r["iters"][0] == o["iters"]
+        e = rel(r["Y"][0], o["Y"])
+        tag = f"cpd lle={kw['include_lle']}"
+    else:
+        tp = dict(max_iter=mi, tol=tol)
+        o = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], oracle.TrackParams(**tp))
+        r = ctx.tracking_step_batched(f["X"], one(len(f["X"])), f["Y"][None], np.zeros(1), f["rest"][None], f["vis"], one(len(f["vis"])),
+                                      f["vis_ext"], one(len(f["vis_ext"])), api.TrackParams(**tp))
+        ok = list(r["iters"][0]) == list(o["iters"]) and r["state"][0] == o["state"]
+        e = rel(r["Y"][0], o["Y"])
+        tag = f"track state={o['state']}"
+    worst = max(worst, e)
+    flag = "" if (ok and e < 1e-6) else "   <-- CHECK"
+    print(f"case {case:3d} Nn={Nn:2d} Mp={Mp:5d} occ={occ:.2f} it={mi:2d} tol={tol:g} {tag:22s} rel err Y {e:.2e} iters match {ok}{flag}", flush=True)
+print("worst rel err", worst)
+ctx.close()
