@@ -26,8 +26,9 @@ for case in range(n_cases):
     ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
     ctx.set_option("threads", int(rng.choice([224, 256])))
     one = lambda n: np.array([0, n], np.int64)
-    if len(f["vis"]) == 0:
-        continue
+    if len(f["vis_ext"]) < 4:
+        continue          # fewer than 4 guide nodes: undefined behaviour in the reference (trackdlo.cpp:92-117, 313-321); the
+                          # CUDA path reports TDLO_ST_TOO_FEW_NODES, the oracle clips -- not comparable
     mi = int(rng.integers(1, 25)); tol = float(rng.choice([0.0, 2e-4]))
     if rng.random() < 0.5:
         kw = dict(max_iter=mi, tol=tol, include_lle=bool(rng.random() < 0.3))
@@ -46,6 +47,9 @@ for case in range(n_cases):
         ok = list(r["iters"][0]) == list(o["iters"]) and r["state"][0] == o["state"]
         e = rel(r["Y"][0], o["Y"])
         tag = f"track state={o['state']}"
+        if not ok:
+            print("   gpu iters", list(r["iters"][0]), "state", r["state"][0], "status", r["status"][0], "| oracle iters", list(o["iters"]), "state", o["state"],
+                  "err", o["err"], "| vis", len(f["vis"]), "ext", len(f["vis_ext"]))
     worst = max(worst, e)
     flag = "" if (ok and e < 1e-6) else "   <-- CHECK"
     print(f"case {case:3d} Nn={Nn:2d} Mp={Mp:5d} occ={occ:.2f} it={mi:2d} tol={tol:g} {tag:22s} rel err Y {e:.2e} iters match {ok}{flag}", flush=True)
