@@ -427,7 +427,7 @@ def test_larger_node_counts(engine):
     c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)
     c.set_option("engine", engine)
     try:
-        for Nn, Mp in ((100, 6000), (200, 8000)):
+        for Nn, Mp in ((65, 3000), (100, 6000), (200, 8000)):      # 65: [A|B] would still fit shared memory, Cholesky path
             f = synth.make_frame(1, n_nodes=Nn, n_points=Mp)
             o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(max_iter=8, tol=0.0))
             r = c.cpd_lle_batched(f["X"], np.array([0, Mp], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=8, tol=0.0))

@@ -839,7 +839,9 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
     const double* gG = scr + sc.G;
     const double* gHG = scr + sc.HG;
     const int ld = Nn + 3;
-    const bool ab_in_smem = (long long)Nn * ld <= (long long)a.L.ab_doubles;
+    // [A|B] in shared memory only for the register-resident solvers (Nn <= 64); the blocked Cholesky keeps it in global
+    // scratch (its shared workspace reuses the whole tail of the region)
+    const bool ab_in_smem = Nn <= 64 && (long long)Nn * ld <= (long long)a.L.ab_doubles;
     double* AB = ab_in_smem ? sm.ab : scr + sc.AB;
 
     // ---- frame vectors -> shared; partial sums in chunk order.  The M-step is a latency chain on the frame's
