@@ -180,8 +180,8 @@ __device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
         const unsigned long long lap = (t / ((unsigned long long)a.qmask + 1ull) + 1ull) & 0xffffffull;
         const unsigned long long* slot = a.qslots + (t & a.qmask);
         unsigned long long v = ld_acquire_u64(slot);
-        unsigned ns = 128;
-        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 2048) ns <<= 1; v = ld_acquire_u64(slot); }
+        unsigned ns = 64;
+        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 512) ns <<= 1; v = ld_acquire_u64(slot); }
         *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = v;
     }
     __syncthreads();
