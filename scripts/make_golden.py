@@ -1,14 +1,16 @@
-"""Mints tests/golden/*.npz from the CPU oracle (oracle/trackdlo_oracle.cpp).
+"""Mints tests/golden/*.npz: seeded inputs, the CPU oracle's outputs (oracle/trackdlo_oracle.cpp) and -- fields
+`ref_*` -- the outputs of the REFERENCE ITSELF run here: oracle/_ref/libtrackdlo_ref.so is the unmodified
+/root/reference/trackdlo/src/trackdlo.cpp + utils.cpp compiled by `make -C oracle _ref` (Eigen calls served by
+oracle/ref_shim/eigen, or by the real Eigen with EIGEN_INCLUDE=...; the field `ref_eigen_shim` records which).
 
-The reference (RMDLO/trackdlo) ships no golden vectors and cannot be built or imported in this
-environment (Eigen/ROS/PCL/OpenCV absent), so these goldens pin the ORACLE, not the reference:
-they catch regressions of the restatement and give the GPU box (where /root/reference does not
-exist) fixed inputs/outputs.  Regenerate with `python scripts/make_golden.py`.
+The reference ships no golden vectors of its own.  /root/reference does not exist on the GPU box, so these files are
+how the reference's results travel there.  Regenerate with `make -C oracle all _ref && python scripts/make_golden.py`.
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import oracle
+from oracle import ref
 from trackdlo_b200 import synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -29,6 +31,12 @@ TRACK_CASES = {
     "track_occl_head": (dict(n_nodes=50, n_points=6000, occlusion=0.4), 0),
     "track_occl_mid": (dict(n_nodes=50, n_points=6000, occlusion=0.4), 1),
     "track_all_visible": (dict(n_nodes=40, n_points=8000, tau_vis=0.02), 2),
+    # trackdlo.cpp:968-973 "Tail occluded" (state 2) and :980-995 "Both ends occluded" (state 4 -> traverse_euclidean
+    # alignment 2, :749-895); _b: two visible runs; _lists: visible_nodes != visible_nodes_extended (:986-990)
+    "track_occl_tail": (dict(n_nodes=50, n_points=6000, occl_windows=[(0.7, 1.0)]), 1),
+    "track_occl_both": (dict(n_nodes=50, n_points=6000, occl_windows=[(0.0, 0.2), (0.8, 1.0)]), 0),
+    "track_occl_both_b": (dict(n_nodes=50, n_points=6000, occl_windows=[(0.0, 0.15), (0.45, 0.6), (0.85, 1.0)]), 2),
+    "track_occl_both_lists": (dict(n_nodes=50, n_points=5000, occl_windows=[(0.0, 0.2), (0.47, 0.53), (0.8, 1.0)]), 7),
 }
 
 
@@ -45,6 +53,7 @@ def main():
         vis = f["vis_ext"] if use_vis else None
         s2_in = 0.0 if name != "n64_sigma_given" else 1e-4
         r = oracle.cpd_lle(f["X"], f["Y"], s2_in, prm, priors=priors, vis=vis, trace=True)
+        rr = ref.cpd_lle(f["X"].astype(np.float32).astype(np.float64), f["Y"], s2_in, prm, priors=priors, vis=vis)
         np.savez_compressed(
             os.path.join(OUT, f"cpd_{name}.npz"),
             X=f["X"].astype(np.float32), Y_in=f["Y"], sigma2_in=s2_in,
@@ -54,17 +63,24 @@ def main():
             n_visible=-1 if vis is None else len(vis),
             Y=r["Y"], W=r["W"], sigma2=r["sigma2"], iters=r["iters"], converged=int(r["converged"]), kept=r["kept"],
             tr_sigma2=r["trace"]["sigma2"], tr_Np=r["trace"]["Np"], tr_P1=r["trace"]["P1"], tr_PX=r["trace"]["PX"],
-            A0=r["trace"]["A"], B0=r["trace"]["B"])
+            A0=r["trace"]["A"], B0=r["trace"]["B"],
+            ref_Y=rr["Y"], ref_sigma2=rr["sigma2"], ref_iters=rr["iters"], ref_converged=int(rr["converged"]),
+            ref_eigen_shim=int(ref.uses_eigen_shim()))
         print(name, "iters", r["iters"], "converged", r["converged"], "sigma2", r["sigma2"], "kept", r["kept"])
     tp = oracle.TrackParams()
     for name, (fkw, idx) in TRACK_CASES.items():
         f = synth.make_frame(idx, **fkw)
         r = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tp)
+        assert r["err"] == 0, name         # no input here may drive the reference into its out-of-range reads
+        rr = ref.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tp)
+        assert rr["state"] == r["state"] and list(rr["iters"]) == list(r["iters"]), name
         np.savez_compressed(
             os.path.join(OUT, f"{name}.npz"),
             X=f["X"].astype(np.float32), Y_in=f["Y"], rest=f["rest"], vis=f["vis"], vis_ext=f["vis_ext"],
             Y=r["Y"], sigma2=r["sigma2"], guide=r["guide"], priors=r["priors"], iters=r["iters"],
-            converged=r["converged"], state=r["state"], err=r["err"])
+            converged=r["converged"], state=r["state"], err=r["err"],
+            ref_Y=rr["Y"], ref_sigma2=rr["sigma2"], ref_guide=rr["guide"], ref_priors=rr["priors"], ref_iters=rr["iters"],
+            ref_state=rr["state"], ref_eigen_shim=int(ref.uses_eigen_shim()))
         print(name, "state", r["state"], "iters", r["iters"], "err", r["err"], "npriors", len(r["priors"]))
 
 

@@ -46,8 +46,12 @@ def visibility(Y, X, rest, tau_vis=0.008, d_vis=0.06):
 
 
 def make_frame(frame_idx, n_nodes=50, n_points=20000, occlusion=0.0, tau_vis=0.008, d_vis=0.06,
-               outlier_frac=0.01, noise=0.002):
-    """One independent frame: dict(X [Mp,3] f64, Y [Nn,3], rest [Nn], vis, vis_ext)."""
+               outlier_frac=0.01, noise=0.002, occl_start=0.3, occl_windows=None):
+    """One independent frame: dict(X [Mp,3] f64, Y [Nn,3], rest [Nn], vis, vis_ext).
+
+    Occlusion deletes the points whose curve parameter lies in [occl_start, occl_start + occlusion] (SURVEY §8d:
+    occl_start = 0.3 -> mid-section / head states of trackdlo.cpp:929-995); `occl_windows` = [(t0, t1), ...] deletes
+    several windows instead, e.g. [(0.75, 1.0)] -> "Tail occluded", [(0, 0.2), (0.8, 1)] -> "Both ends occluded"."""
     rng = np.random.default_rng(SEED0 + frame_idx)
     Y = curve(np.linspace(0.0, 1.0, n_nodes))
     t = rng.random(n_points)
@@ -56,8 +60,12 @@ def make_frame(frame_idx, n_nodes=50, n_points=20000, occlusion=0.0, tau_vis=0.0
     if n_out:
         idx = rng.choice(n_points, size=n_out, replace=False)
         X[idx] = np.array([0.0, 0.0, 0.65]) + rng.uniform(-0.3, 0.3, size=(n_out, 3))
-    if occlusion > 0:
-        keep = ~((t >= 0.3) & (t <= 0.3 + occlusion))
+    if occl_windows is None and occlusion > 0:
+        occl_windows = [(occl_start, occl_start + occlusion)]
+    if occl_windows:
+        keep = np.ones(n_points, bool)
+        for (t0, t1) in occl_windows:
+            keep &= ~((t >= t0) & (t <= t1))
         X = X[keep]
     X = X.astype(np.float32).astype(np.float64)      # trackdlo_node.cpp:242
     rest = rest_arclengths(Y)
