@@ -118,8 +118,10 @@ def test_tracking_step_states_against_live_reference(ctx, state):
             if state == 0:
                 kw["tau_vis"] = 0.02
             f = synth.make_frame(60 + 10 * li + idx, **kw)
-            if state == 2 and f["vis_ext"][0] != 0:
+            if state in (1, 2) and f["vis_ext"][0] != 0:            # the end node itself may sit just outside tau_vis
                 f["vis"] = np.concatenate([[0], f["vis"]]).astype(np.int32); f["vis_ext"] = np.concatenate([[0], f["vis_ext"]]).astype(np.int32)
+            if state in (1, 3) and f["vis_ext"][-1] != 39:
+                f["vis"] = np.concatenate([f["vis"], [39]]).astype(np.int32); f["vis_ext"] = np.concatenate([f["vis_ext"], [39]]).astype(np.int32)
             o = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], oracle.TrackParams())
             if o["err"] != 0:
                 continue                        # the reference itself reads out of range on this input
