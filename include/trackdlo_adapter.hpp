@@ -10,7 +10,12 @@
 // Build: compile the node with -I<repo>/include and link -ltrackdlo_b200 instead of compiling
 // trackdlo/src/trackdlo.cpp.  Eigen is the only dependency of this header; a build without Eigen
 // (this repo's CI) defines TRACKDLO_ADAPTER_MATRIX_HEADER to a minimal column-major MatrixXd.
-#pragma once
+//
+// Where it goes: in trackdlo/include/trackdlo.h the class declaration (:53-130) is replaced by
+// `#include <trackdlo_adapter.hpp>`, i.e. this header is included INSIDE the reference's `#ifndef TRACKDLO_H` guard
+// (trackdlo.h:47-48, :131) -- it therefore carries a guard of its own and never tests TRACKDLO_H.
+#ifndef TRACKDLO_B200_ADAPTER_HPP
+#define TRACKDLO_B200_ADAPTER_HPP
 
 #ifdef TRACKDLO_ADAPTER_MATRIX_HEADER
 #include TRACKDLO_ADAPTER_MATRIX_HEADER
@@ -31,9 +36,6 @@
 #ifndef TRACKDLO_ADAPTER_LOG_ERROR
 #define TRACKDLO_ADAPTER_LOG_ERROR(msg) std::fprintf(stderr, "[trackdlo_b200] %s\n", msg)
 #endif
-
-#ifndef TRACKDLO_H
-#define TRACKDLO_H
 
 using Eigen::MatrixXd;
 
@@ -71,21 +73,25 @@ public:
         const int64_t Mp = (int64_t)X_orig.rows();
         if (!ensure_ctx(Nn, Mp)) return false;
         std::vector<double> X = to_rows(X_orig), Yr = to_rows(Y), W((size_t)Nn * 3);
-        std::vector<double> pri((size_t)Nn * 4, 0.0);
-        int32_t n_pri = 0;
-        for (size_t i = 0; i < correspondence_priors.size() && n_pri < Nn; i++, n_pri++)
-            for (int t = 0; t < 4; t++) pri[(size_t)n_pri * 4 + t] = correspondence_priors[i](0, t);
+        // the reference takes a prior list of ANY length (trackdlo.cpp:244-254): the whole list is passed on
+        const int32_t n_pri = (int32_t)correspondence_priors.size();
+        const int32_t pri_stride = n_pri > Nn ? n_pri : Nn;
+        if (pri_stride > 4 * TDLO_MAX_NODES) { TRACKDLO_ADAPTER_LOG_ERROR("cpd_lle: correspondence prior list too long for the GPU path"); return false; }
+        std::vector<double> pri((size_t)pri_stride * 4, 0.0);
+        for (int32_t i = 0; i < n_pri; i++)
+            for (int t = 0; t < 4; t++) pri[(size_t)i * 4 + t] = correspondence_priors[(size_t)i](0, t);
         const int64_t xoff[2] = {0, Mp};
         int32_t n_vis = (int32_t)visible_nodes.size(), iters = 0, status = 0;
         tdlo_cpd_batch b{};
         b.n_frames = 1; b.node_stride = Nn; b.X = X.data(); b.x_offsets = xoff; b.Y = Yr.data(); b.sigma2 = &sigma2;
-        b.priors = pri.data(); b.n_priors = &n_pri; b.n_visible = &n_vis; b.W = W.data(); b.iters = &iters; b.status = &status;
+        b.priors = pri.data(); b.n_priors = &n_pri; b.priors_stride = pri_stride; b.n_visible = &n_vis; b.W = W.data(); b.iters = &iters; b.status = &status;
         tdlo_cpd_params p{};
         p.beta = beta; p.lambda = lambda; p.lle_weight = lle_weight; p.mu = mu; p.tol = tol; p.alpha = alpha; p.k_vis = k_vis;
         p.visibility_threshold = visibility_threshold; p.prune_radius = 0.1; p.max_iter = max_iter; p.include_lle = include_lle ? 1 : 0;
         if (tdlo_cpd_lle_batched(ctx_->h, &b, &p) != TDLO_OK) { TRACKDLO_ADAPTER_LOG_ERROR(tdlo_last_error(ctx_->h)); return false; }
         last_status_ = status;
         from_rows(Yr, Y);
+        report_status(status);
         if (status & TDLO_ST_NOT_CONVERGED) { TRACKDLO_ADAPTER_LOG_ERROR("optimization did not converge!"); return false; }  // trackdlo.cpp:434
         return true;
     }
@@ -116,6 +122,7 @@ public:
         p.lle_weight = lle_weight_; p.prune_radius = 0.1; p.max_iter = max_iter_;
         if (tdlo_tracking_step_batched(ctx_->h, &b, &p) != TDLO_OK) { TRACKDLO_ADAPTER_LOG_ERROR(tdlo_last_error(ctx_->h)); return; }
         last_status_ = status;
+        report_status(status);
         static const char* kState[] = {"All nodes visible / minor occlusion", "Mid-section occluded", "Tail occluded",
                                        "Head occluded", "Both ends occluded"};
         if (state >= 0 && state <= 4) { TRACKDLO_ADAPTER_LOG_INFO(kState[state]); }
@@ -141,6 +148,14 @@ private:
     };
     // copies of a tracker share one GPU context (the node copy-assigns the tracker once, trackdlo_node.cpp:131)
     std::shared_ptr<Ctx> ctx_;
+
+    // inputs for which the reference itself has no defined result (it reads out of range / divides by zero): say so
+    static void report_status(int status) {
+        if (status & TDLO_ST_TOO_FEW_NODES) TRACKDLO_ADAPTER_LOG_ERROR("fewer than 4 (guide) nodes: registration skipped, nodes left unchanged");
+        if (status & TDLO_ST_EMPTY_CLOUD) TRACKDLO_ADAPTER_LOG_ERROR("no point within 0.1 m of any node: registration skipped, nodes left unchanged");
+        if (status & TDLO_ST_SINGULAR) TRACKDLO_ADAPTER_LOG_ERROR("singular / non-finite pivot in the M-step solve");
+        if (status & TDLO_ST_TRAVERSE_UB) TRACKDLO_ADAPTER_LOG_ERROR("traverse_euclidean took a path on which the reference reads out of range; priors are defined but have no reference counterpart");
+    }
 
     bool ensure_ctx(int nodes, int64_t points) {
         if (ctx_ && ctx_->h && ctx_->nodes >= nodes && ctx_->points >= points) return true;
@@ -183,4 +198,4 @@ private:
     int last_status_ = 0;
 };
 
-#endif  // TRACKDLO_H
+#endif  // TRACKDLO_B200_ADAPTER_HPP

@@ -44,6 +44,9 @@ extern "C" {
                                     behaviour in the reference; result is defined
                                     but has no reference counterpart                              */
 #define TDLO_ST_PRE_NOT_CONVERGED 32 /* tracking_step: the pre-processing registration hit max_iter */
+#define TDLO_ST_INVALID_INPUT 64 /* device-pointer entry points: the frame's offsets / node count / visibility lists would
+                                    overrun the context's capacity or index outside [0, n_nodes): frame not run, outputs
+                                    untouched (the host-pointer entry points reject such a batch with TDLO_ERR_INVALID) */
 
 #define TDLO_MAX_NODES 256
 
@@ -83,8 +86,8 @@ typedef struct tdlo_cpd_batch {
     const int32_t* n_nodes;     /* [n_frames] or NULL (= node_stride for all frames)                */
     double* Y;                  /* [n_frames][node_stride][3]  in: Y, out: registered Y             */
     double* sigma2;             /* [n_frames] in/out; 0 selects the data-driven init (:271-273)     */
-    const double* priors;       /* [n_frames][node_stride][4] or NULL                               */
-    const int32_t* n_priors;    /* [n_frames] or NULL                                               */
+    const double* priors;       /* [n_frames][priors_stride][4] or NULL                             */
+    const int32_t* n_priors;    /* [n_frames] or NULL; 0 <= n_priors[f] <= priors_stride            */
     const int32_t* n_visible;   /* [n_frames] or NULL: visible_nodes.size() (cpd_lle only uses the
                                    size of that vector, trackdlo.cpp:358)                           */
     const double* H;            /* optional [n_frames][node_stride][node_stride] LLE matrix
@@ -92,6 +95,10 @@ typedef struct tdlo_cpd_batch {
     double* W;                  /* optional out [n_frames][node_stride][3] last W (:415)           */
     int32_t* iters;             /* optional out [n_frames] EM iterations executed                   */
     int32_t* status;            /* optional out [n_frames] TDLO_ST_* mask                           */
+    int32_t priors_stride;      /* rows per frame in `priors`; 0 = node_stride.  The reference accepts a prior list of
+                                   any length (later rows overwrite earlier ones with the same node index,
+                                   trackdlo.cpp:244-254): pass a larger stride for lists longer than the node count  */
+    int32_t reserved;
 } tdlo_cpd_batch;
 
 /* A batch of independent tracking_step problems (one tracker object each). */
@@ -117,6 +124,9 @@ typedef struct tdlo_track_batch {
     int32_t* status;             /* optional out [n_frames]                                          */
     int32_t* state;              /* optional out [n_frames] 0 all visible,1 mid occluded,2 tail occluded,
                                     3 head occluded,4 both ends occluded (trackdlo.cpp:929-995)      */
+    double* packed_results;      /* optional out [n_frames][3*n_nodes + 4]: per frame one contiguous record
+                                    {Y[n_nodes][3], sigma2, iters_pre, iters_main, status} written by the kernel's
+                                    epilogue -- the payload a multi-GPU caller all-gathers in ONE collective     */
 } tdlo_track_batch;
 
 /* Creates a context on CUDA device `device`.  Capacities bound later batches:
@@ -129,13 +139,17 @@ const char* tdlo_version(void);
 
 /* trackdlo::cpd_lle over a batch.  Host pointers; synchronous. */
 int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* batch, const tdlo_cpd_params* params);
-/* Same with device pointers; asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+/* Same with device pointers; asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ * PRECONDITIONS the host cannot check on device memory: x_offsets ascending from >= 0 with x_offsets[n_frames] <=
+ * max_points_total of the context, n_nodes[f] <= node_stride, n_priors[f] <= priors_stride.  The kernel re-checks them
+ * per frame: a violating frame is not run and gets TDLO_ST_INVALID_INPUT (n_priors is clamped). */
 int tdlo_cpd_lle_batched_device(tdlo_ctx* ctx, const tdlo_cpd_batch* batch, const tdlo_cpd_params* params,
                                 void* stream);
 
 /* trackdlo::tracking_step over a batch.  Host pointers; synchronous. */
 int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch* batch, const tdlo_track_params* params);
-/* Same with device pointers; asynchronous on `stream`. */
+/* Same with device pointers; asynchronous on `stream`.  Same per-frame re-check as above, plus: both visibility
+ * lists at most n_nodes long, entries in [0, n_nodes), visible_ext strictly ascending. */
 int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* batch,
                                       const tdlo_track_params* params, void* stream);
 
@@ -161,7 +175,8 @@ typedef struct tdlo_vis_batch {
 } tdlo_vis_batch;
 /* Host pointers; synchronous. */
 int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);
-/* Device pointers; asynchronous on `stream` -- chain it in front of tdlo_tracking_step_batched_device. */
+/* Device pointers; asynchronous on `stream` (no host read-back: the slice table is built on the device) -- chain it in
+ * front of tdlo_tracking_step_batched_device. */
 int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* batch, void* stream);
 
 /* Evaluator frame error (trackdlo/src/evaluator.cpp:233-283, 333-341): for every frame the mean distance of
@@ -181,8 +196,9 @@ int tdlo_tracking_error_batched_device(tdlo_ctx* ctx, const tdlo_err_batch* batc
 /* Sequence mode: S independent trackers advanced over T consecutive frames WITHOUT returning to the host
  * between frames.  Per step t and sequence s, exactly what trackdlo_node.cpp does per callback: visibility lists from
  * Y^{t-1} and the step's cloud (tdlo_visibility_batched semantics, visibility_threshold = params->visibility_threshold),
- * then tracking_step, which leaves Y^{t} and sigma2 in place for step t+1 (trackdlo.cpp:998).  Host pointers; the clouds
- * of step t+1 are uploaded while step t runs; one synchronisation at the end. */
+ * then tracking_step, which leaves Y^{t} and sigma2 in place for step t+1 (trackdlo.cpp:998).  Host pointers; every copy
+ * and kernel of all T steps is queued on one stream without a host synchronisation in between (the host runs ahead of the
+ * device), one synchronisation at the end. */
 typedef struct tdlo_seq_batch {
     int32_t n_sequences;
     int32_t n_nodes;
@@ -199,6 +215,11 @@ typedef struct tdlo_seq_batch {
 } tdlo_seq_batch;
 int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* batch, const tdlo_track_params* params);
 
+/* Waits for the most recent *_device call of this context and reports what only the device knows: TDLO_ERR_CUDA if the
+ * persistent kernel's watchdog gave up (a CTA waited longer than TDLO_OPT_WATCHDOG_MS for a task; results invalid),
+ * TDLO_OK otherwise.  The host-pointer entry points do this themselves. */
+int tdlo_synchronize(tdlo_ctx* ctx);
+
 /* Launch geometry of the most recent call (for benchmarks / profiling):
  * info[0]=cluster size, [1]=CTAs launched, [2]=threads per CTA, [3]=dynamic smem bytes,
  * [4]=points per tile, [5]=kernels launched by that call, [6]=resident CTAs per SM, [7]=SM count. */
@@ -207,14 +228,11 @@ int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]);
 /* Development aid: enables/disables the kernel's per-phase cycle counters and returns + resets the totals accumulated
  * since the previous call.  Task-queue engine: cycles[0..9] = {queue wait, prune, visibility pre-pass, E-step, start_call,
  * wave glue, M-step gather+assemble, solve, update, finish_call}, [10..15] = {E-step tasks, tiles, sum of window widths,
- * row blocks, per-warp tile-loop cycles, end-of-task reduction cycles}.  Cluster engine: cycles[0..7] (rank 0) = {set-up,
- * visibility pre-pass, E-step, wait, assemble, wait, solve, update}, [8..15] the other ranks.  Synchronises. */
+ * row blocks, per-warp tile-loop cycles, end-of-task reduction cycles}.  Synchronises. */
 int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 
-/* Engine options.
- *  TDLO_OPT_ENGINE        1 (default) = task-queue engine: one persistent launch, the E-step of every frame is
- *                         cut into chunk tasks that any SM may run, the CTA finishing a frame's last chunk runs
- *                         its M-step; 0 = cluster-per-frame engine.
+/* Engine options (the engine: ONE persistent launch per call; the E-step of every frame is cut into chunk tasks on a
+ * global ticket queue that any SM may run; the CTA finishing a frame's last chunk runs its M-step).
  *  TDLO_OPT_CHUNK_POINTS  raw points per chunk task; 0 (default) = automatic from the context's point
  *                         capacity: 256 / 512 for small contexts (one live sequence), 1024, or 2048 / 4096 for large batches (results are
  *                         bit-deterministic for a given chunk size).
@@ -222,18 +240,17 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         that are exactly 0 in the reference (double underflow); the default 100 skips entries
  *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
- *  TDLO_OPT_THREADS       kernel variant of the task-queue engine for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
- *                         224 (3 CTAs/SM, 80 registers; measured equal or slower, as were 288/320-thread variants).
- *                         Nn > 64 always uses 256. */
-#define TDLO_OPT_ENGINE 1
+ *  TDLO_OPT_THREADS       kernel variant for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
+ *                         224 (3 CTAs/SM, 80 registers; measured equal or slower).  Nn > 64 always uses 256.
+ *  TDLO_OPT_WATCHDOG_MS   a CTA of the persistent kernel that waits longer than this for its next task (or for a frame's
+ *                         upload) abandons the launch and the call returns TDLO_ERR_CUDA instead of hanging the caller
+ *                         (default 20000; 0 = never). */
 #define TDLO_OPT_CHUNK_POINTS 2
 #define TDLO_OPT_TRUNCATION 3
 #define TDLO_OPT_INFLIGHT 4
 #define TDLO_OPT_THREADS 5
+#define TDLO_OPT_WATCHDOG_MS 6
 int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value);
-
-/* Overrides the automatic cluster-size choice of the cluster engine (0 = automatic; 1,2,4,8,16). */
-int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t cluster_size);
 
 #ifdef __cplusplus
 }

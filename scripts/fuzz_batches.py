@@ -1,4 +1,4 @@
-"""Randomised differential run on BATCHES: several ragged frames per call (tracking_step), both engines, random
+"""Randomised differential run on BATCHES: several ragged frames per call (tracking_step), random engine options, random
 sigma2_in, against the per-frame oracle (development aid).  Usage: python scripts/fuzz_batches.py [n_cases] [seed]"""
 import os
 import sys
@@ -26,10 +26,9 @@ for case in range(n_cases):
         f = synth.make_frame(int(rng.integers(0, 100000)), n_nodes=Nn, n_points=int(rng.integers(100, 7000)), occlusion=float(rng.choice([0.0, 0.15, 0.4])))
         if len(f["vis_ext"]) >= 4:
             frames.append(f)
-    engine = int(rng.random() < 0.8)
-    ctx.set_option("engine", engine)
+    engine = "tq"
     ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048])))
-    ctx.set_cluster_size(int(rng.choice([0, 1, 2, 4])))
+    ctx.set_option("threads", int(rng.choice([224, 256])))
     s2 = np.where(rng.random(F) < 0.3, 10.0 ** rng.uniform(-6, -3, F), 0.0)
     mi = int(rng.integers(1, 20)); tol = float(rng.choice([0.0, 2e-4]))
     xo = np.zeros(F + 1, np.int64); xo[1:] = np.cumsum([len(f["X"]) for f in frames])

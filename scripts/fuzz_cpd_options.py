@@ -22,7 +22,7 @@ ctx = api.Context(max_frames=4, max_nodes=S, max_points_total=4 * 6000)
 bad = 0; worst = 0.0
 for case in range(n_cases):
     F = int(rng.integers(1, 5))
-    ctx.set_option("engine", int(rng.random() < 0.8)); ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024])))
+    ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024])))
     lle = bool(rng.random() < 0.3)
     kw = dict(max_iter=int(rng.integers(1, 16)), tol=float(rng.choice([0.0, 2e-4])), include_lle=lle, alpha=3.0, k_vis=float(rng.choice([0.0, 50.0])),
               visibility_threshold=0.008)

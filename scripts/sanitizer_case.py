@@ -15,15 +15,18 @@ print("iters", r["iters"].tolist(), "status", r["status"].tolist())
 v = ctx.visibility_batched(X, one(n), Y, rest)
 print("vis ok", len(v["visible"]))
 ctx.close()
-# Nn = 100: blocked Cholesky (16-column panels, FP64 MMA); Nn = 200: 8/16-column panels; cluster engine on the small case
+# Nn = 100: blocked Cholesky (16-column panels, FP64 MMA); Nn = 200: 8/16-column panels
 for Nn, Mp in ((100, 1500), (200, 2500)):
     g = synth.make_frame(1, n_nodes=Nn, n_points=Mp)
     c2 = api.Context(max_frames=1, max_nodes=Nn, max_points_total=Mp)
     r2 = c2.cpd_lle_batched(g["X"], np.array([0, Mp], np.int64), g["Y"][None], np.zeros(1), api.CpdParams(max_iter=2, tol=0.0))
     print("Nn", Nn, "iters", r2["iters"].tolist(), "status", r2["status"].tolist())
     c2.close()
-c3 = api.Context(max_frames=1, max_nodes=30, max_points_total=700)
-c3.set_option("engine", 0)
-r3 = c3.cpd_lle_batched(f["X"], np.array([0, n], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=3, tol=0.0, include_lle=True, beta=3.0, lambda_=1.0))
-print("cluster engine iters", r3["iters"].tolist())
-c3.close()
+# tracking states 2 (tail occluded) and 4 (both ends occluded -> traverse_euclidean alignment 2)
+for win in ([(0.7, 1.0)], [(0.0, 0.2), (0.8, 1.0)]):
+    g = synth.make_frame(1, n_nodes=40, n_points=1500, occl_windows=win)
+    c3 = api.Context(max_frames=1, max_nodes=40, max_points_total=len(g["X"]))
+    o1 = lambda m: np.array([0, m], np.int64)
+    r3 = c3.tracking_step_batched(g["X"], o1(len(g["X"])), g["Y"][None], np.zeros(1), g["rest"][None], g["vis"], o1(len(g["vis"])), g["vis_ext"], o1(len(g["vis_ext"])), api.TrackParams(max_iter=4))
+    print("state", r3["state"].tolist(), "iters", r3["iters"].tolist(), "status", r3["status"].tolist())
+    c3.close()

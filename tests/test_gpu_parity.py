@@ -35,22 +35,18 @@ def ctx():
     c.close()
 
 
-# Engine configurations every golden is run under.  "tq" = task-queue engine (the default), with its default
-# Gaussian truncation (z_cut = 100) and with exact-zero skipping only (z_cut = 745.2), small chunks (many
-# partial sums per frame) and the 256-thread kernel variant; "cluster" = the cluster-per-frame engine.
+# Engine configurations every golden is run under: the default Gaussian truncation (z_cut = 100) and exact-zero
+# skipping only (z_cut = 745.2), small chunks (many partial sums per frame), both kernel variants (224 / 256 threads).
 ENGINE_CFGS = {
-    "tq": dict(engine=1, chunk_points=0, truncation=100.0, threads=256),
-    "tq_224thr": dict(engine=1, chunk_points=1024, truncation=100.0, threads=224),
-    "tq_exact_small_chunks": dict(engine=1, chunk_points=256, truncation=745.2, threads=224),
-    "tq_256thr": dict(engine=1, chunk_points=2048, truncation=100.0, threads=256),
-    "cluster": dict(engine=0),
-    "cluster4": dict(engine=0, cluster=4),
+    "tq": dict(chunk_points=0, truncation=100.0, threads=256),
+    "tq_224thr": dict(chunk_points=1024, truncation=100.0, threads=224),
+    "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, threads=224),
+    "tq_256thr": dict(chunk_points=2048, truncation=100.0, threads=256),
 }
 
 
 def _configure(c, cfg):
     d = dict(ENGINE_CFGS["tq"]); d.update(ENGINE_CFGS[cfg])
-    c.set_cluster_size(d.pop("cluster", 0))
     for k, v in d.items():
         c.set_option(k, v)
 
@@ -94,7 +90,7 @@ def test_cpd_against_golden(ctx, golden_dir, name, cfg):
 
 
 @pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
-@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "cluster"])
+@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr"])
 def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
@@ -118,7 +114,7 @@ def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
 
 
-@pytest.fixture(params=["tq", "cluster"])
+@pytest.fixture(params=["tq", "tq_exact_small_chunks"])
 def ectx(ctx, request):
     _configure(ctx, request.param)
     ctx.engine_name = request.param
@@ -237,8 +233,6 @@ def test_device_pointer_entry_matches_host_entry(ectx):
     frames = [synth.make_frame(20 + i, n_nodes=50, n_points=3000) for i in range(3)]
     X, xo, Y = _batch(frames)
     pg = api.CpdParams(max_iter=12, tol=0.0)
-    if ectx.engine_name == "cluster":
-        ctx.set_cluster_size(4)      # same split of the points on both entries => bit-identical sums
     host = ctx.cpd_lle_batched(X, xo, Y, np.zeros(3), pg)
     dev = torch.device("cuda:0")
     dX = torch.from_numpy(X).to(dev); dxo = torch.from_numpy(xo).to(dev); dY = torch.from_numpy(Y.copy()).to(dev)
@@ -400,7 +394,7 @@ def test_evaluator_error_metric_matches_oracle(ctx):
 
 
 def test_engine_options_are_validated(ctx):
-    for name, bad in (("engine", 2), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
+    for name, bad in (("watchdog_ms", -1.0), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
                       ("threads", 128), ("inflight", -1)):
         with pytest.raises(api.TdloError):
             ctx.set_option(name, bad)
@@ -421,11 +415,9 @@ def test_bad_arguments_are_rejected(ctx):
         ctx.cpd_lle_batched(f["X"], np.zeros(201, np.int64), big, np.zeros(200), api.CpdParams())
 
 
-@pytest.mark.parametrize("engine", [1, 0])
-def test_larger_node_counts(engine):
+def test_larger_node_counts():
     """Nn = 100 and 200 take the other kernel variants (more node passes per lane, global-memory solve workspace)."""
     c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)
-    c.set_option("engine", engine)
     try:
         for Nn, Mp in ((65, 3000), (100, 6000), (200, 8000)):      # 65: [A|B] would still fit shared memory, Cholesky path
             f = synth.make_frame(1, n_nodes=Nn, n_points=Mp)

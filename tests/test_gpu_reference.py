@@ -57,15 +57,15 @@ def test_goldens_cover_every_tracking_state(golden_dir):
 
 
 @pytest.mark.parametrize("name", TRACK_GOLDENS)
-@pytest.mark.parametrize("engine", [1, 0])
-def test_tracking_step_against_reference_outputs(ctx, golden_dir, name, engine):
+@pytest.mark.parametrize("chunk", [0, 256])
+def test_tracking_step_against_reference_outputs(ctx, golden_dir, name, chunk):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     f = dict(X=g["X"].astype(np.float64), Y=g["Y_in"], rest=g["rest"], vis=g["vis"].astype(np.int32), vis_ext=g["vis_ext"].astype(np.int32))
-    ctx.set_option("engine", engine)
+    ctx.set_option("chunk_points", chunk)
     try:
         r = _track(ctx, f, api.TrackParams())
     finally:
-        ctx.set_option("engine", 1)
+        ctx.set_option("chunk_points", 0)
     npri = len(g["ref_priors"])
     assert r["status"][0] == 0
     assert r["state"][0] == int(g["ref_state"]) == int(g["state"])
@@ -272,9 +272,7 @@ def test_fuzz_slice_ragged_batches(ctx):
                                  occlusion=float(rng.choice([0.0, 0.15, 0.4])), occl_start=float(rng.choice([0.3, 0.0, 0.7])))
             if len(f["vis_ext"]) >= 4:
                 frames.append(f)
-        engine = int(rng.random() < 0.8)
-        ctx.set_option("engine", engine); ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048])))
-        ctx.set_cluster_size(int(rng.choice([0, 1, 2, 4])))
+        ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048]))); ctx.set_option("threads", int(rng.choice([224, 256])))
         try:
             s2 = np.where(rng.random(F) < 0.3, 10.0 ** rng.uniform(-6, -3, F), 0.0)
             mi = int(rng.integers(1, 20)); tol = float(rng.choice([0.0, 2e-4]))
@@ -292,5 +290,5 @@ def test_fuzz_slice_ragged_batches(ctx):
                 assert rel(r["Y"][i], o["Y"]) < 1e-6 and abs(r["sigma2"][i] - o["sigma2"]) / o["sigma2"] < 1e-5, (case, i)
                 checked += 1
         finally:
-            ctx.set_option("engine", 1); ctx.set_option("chunk_points", 0); ctx.set_cluster_size(0)
+            ctx.set_option("chunk_points", 0); ctx.set_option("threads", 256)
     assert checked >= 25

@@ -14,13 +14,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrackdlo_b200.so")
 
-ST_NOT_CONVERGED, ST_SINGULAR, ST_TOO_FEW_NODES, ST_EMPTY_CLOUD, ST_TRAVERSE_UB, ST_PRE_NOT_CONVERGED = 1, 2, 4, 8, 16, 32
+ST_NOT_CONVERGED, ST_SINGULAR, ST_TOO_FEW_NODES, ST_EMPTY_CLOUD, ST_TRAVERSE_UB, ST_PRE_NOT_CONVERGED, ST_INVALID_INPUT = 1, 2, 4, 8, 16, 32, 64
 
 ABI_SYMBOLS = [
     "tdlo_create", "tdlo_destroy", "tdlo_last_error", "tdlo_version",
     "tdlo_cpd_lle_batched", "tdlo_cpd_lle_batched_device",
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
-    "tdlo_last_launch_info", "tdlo_set_cluster_size", "tdlo_profile_phases", "tdlo_set_option",
+    "tdlo_last_launch_info", "tdlo_synchronize", "tdlo_profile_phases", "tdlo_set_option",
     "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences", "tdlo_tracking_error_batched", "tdlo_tracking_error_batched_device",
 ]
 
@@ -44,14 +44,15 @@ class TrackParamsC(C.Structure):
 class CpdBatchC(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("node_stride", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("X", "x_offsets", "n_nodes", "Y", "sigma2", "priors", "n_priors",
-                                           "n_visible", "H", "W", "iters", "status")]
+                                           "n_visible", "H", "W", "iters", "status")] + \
+               [("priors_stride", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TrackBatchC(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("n_nodes", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "sigma2", "geodesic_coord", "visible",
                                            "visible_offsets", "visible_ext", "visible_ext_offsets", "H_pre",
-                                           "guide_nodes", "priors", "n_priors", "iters", "status", "state")]
+                                           "guide_nodes", "priors", "n_priors", "iters", "status", "state", "packed_results")]
 
 
 class VisBatchC(C.Structure):
@@ -136,7 +137,7 @@ def load_library():
         lib.tdlo_tracking_step_batched.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC)]
         lib.tdlo_tracking_step_batched_device.argtypes = [C.c_void_p, C.POINTER(TrackBatchC), C.POINTER(TrackParamsC), C.c_void_p]
         lib.tdlo_last_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
-        lib.tdlo_set_cluster_size.argtypes = [C.c_void_p, C.c_int32]
+        lib.tdlo_synchronize.argtypes = [C.c_void_p]
         lib.tdlo_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         lib.tdlo_profile_phases.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         lib.tdlo_tracking_error_batched.argtypes = [C.c_void_p, C.POINTER(ErrBatchC)]
@@ -187,44 +188,50 @@ class Context:
         if rc != 0:
             raise TdloError(f"{what} failed ({rc}): {self.lib.tdlo_last_error(self.h).decode()}")
 
-    def set_cluster_size(self, c):
-        self._check(self.lib.tdlo_set_cluster_size(self.h, c), "tdlo_set_cluster_size")
+    def synchronize(self):
+        """tdlo_synchronize: waits for the last *_device call; raises if the kernel's watchdog gave up."""
+        self._check(self.lib.tdlo_synchronize(self.h), "tdlo_synchronize")
 
-    OPTIONS = {"engine": 1, "chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5}
+    OPTIONS = {"chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5, "watchdog_ms": 6}
 
     def set_option(self, name, value):
-        """tdlo_set_option: engine (1 task queue / 0 cluster), chunk_points, truncation, inflight, threads."""
+        """tdlo_set_option: chunk_points, truncation, inflight, threads, watchdog_ms."""
         self._check(self.lib.tdlo_set_option(self.h, self.OPTIONS[name], float(value)), f"tdlo_set_option({name})")
 
     def profile_phases(self, enable=True):
         """Returns and resets the kernel's phase cycle counters; see tdlo_profile_phases."""
         cyc = (C.c_uint64 * 16)()
         self._check(self.lib.tdlo_profile_phases(self.h, int(enable), cyc), "tdlo_profile_phases")
-        names = ("setup", "dmin", "estep", "wait1", "assemble", "wait2", "solve", "update")  # others[x6]/[x7]: solver warp0 / warp1 busy cycles
         v = list(cyc)
-        return {"rank0": dict(zip(names, v[:8])), "others": dict(zip(names[:6] + ("solver_warp0_busy", "solver_warp1_busy"), v[8:16]))}
+        return {"cycles": dict(zip(self.PHASE_CYCLES, v[:10])), "counts": dict(zip(self.PHASE_COUNTS, v[10:16]))}
+
+    # slot meaning of tdlo_profile_phases (include/trackdlo_b200.h): thread-0 cycles summed over all CTAs, then counters
+    PHASE_CYCLES = ("queue_wait", "prune", "visibility_prepass", "estep", "start_call", "wave_glue", "mstep_gather_assemble",
+                    "solve", "update", "finish_call")
+    PHASE_COUNTS = ("estep_tasks", "tiles", "window_rows", "row_blocks", "warp_tile_loop_cycles", "end_of_task_reduction_cycles")
 
     def launch_info(self):
         info = (C.c_int32 * 8)()
         self.lib.tdlo_last_launch_info(self.h, info)
-        keys = ("cluster_size", "ctas", "threads", "smem_bytes", "tile_points", "launches", "ctas_per_sm", "sm_count")
+        keys = ("reserved", "ctas", "threads", "smem_bytes", "tile_points", "launches", "ctas_per_sm", "sm_count")
         return dict(zip(keys, list(info)))
 
     # ------------------------------------------------------------------ cpd_lle, host buffers
     def cpd_lle_batched(self, X, x_offsets, Y, sigma2, params: CpdParams, n_nodes=None, priors=None, n_priors=None,
                         n_visible=None, H=None):
-        """X [sum Mp,3], x_offsets [F+1], Y [F,S,3], sigma2 [F]  ->  dict(Y, sigma2, W, iters, status)."""
+        """X [sum Mp,3], x_offsets [F+1], Y [F,S,3], sigma2 [F], priors [F,PS,4] (PS = any stride >= max n_priors)
+        ->  dict(Y, sigma2, W, iters, status)."""
         X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
         Y = _np(Y, np.float64).copy(); F, S = Y.shape[0], Y.shape[1]
         s2 = _np(sigma2, np.float64).copy().reshape(F)
         W = np.zeros((F, S, 3)); iters = np.zeros(F, np.int32); status = np.zeros(F, np.int32)
         nn = None if n_nodes is None else _np(n_nodes, np.int32)
-        pr = None if priors is None else _np(priors, np.float64, (F, S, 4))
+        pr = None if priors is None else _np(priors, np.float64, (F, -1, 4))
         npr = None if n_priors is None else _np(n_priors, np.int32)
         nv = None if n_visible is None else _np(n_visible, np.int32)
         Hc = None if H is None else _np(H, np.float64, (F, S, S))
         b = CpdBatchC(F, S, _ptr(X), _ptr(xo), _ptr(nn), _ptr(Y), _ptr(s2), _ptr(pr), _ptr(npr), _ptr(nv), _ptr(Hc),
-                      _ptr(W), _ptr(iters), _ptr(status))
+                      _ptr(W), _ptr(iters), _ptr(status), 0 if pr is None else pr.shape[1], 0)
         pc = params.to_c()
         self._check(self.lib.tdlo_cpd_lle_batched(self.h, C.byref(b), C.byref(pc)), "tdlo_cpd_lle_batched")
         return dict(Y=Y, sigma2=s2, W=W, iters=iters, status=status)
@@ -249,11 +256,12 @@ class Context:
         Hc = None if H_pre is None else _np(H_pre, np.float64, (F, N, N))
         guide = np.zeros((F, N, 3)); pri = np.zeros((F, 2 * N, 4)); npri = np.zeros(F, np.int32)
         iters = np.zeros((F, 2), np.int32); status = np.zeros(F, np.int32); state = np.zeros(F, np.int32)
+        packed = np.zeros((F, 3 * N + 4))
         b = TrackBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(s2), _ptr(geo), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo),
-                        _ptr(Hc), _ptr(guide), _ptr(pri), _ptr(npri), _ptr(iters), _ptr(status), _ptr(state))
+                        _ptr(Hc), _ptr(guide), _ptr(pri), _ptr(npri), _ptr(iters), _ptr(status), _ptr(state), _ptr(packed))
         pc = params.to_c()
         self._check(self.lib.tdlo_tracking_step_batched(self.h, C.byref(b), C.byref(pc)), "tdlo_tracking_step_batched")
-        return dict(Y=Y, sigma2=s2, guide=guide, priors=pri, n_priors=npri, iters=iters, status=status, state=state)
+        return dict(Y=Y, sigma2=s2, guide=guide, priors=pri, n_priors=npri, iters=iters, status=status, state=state, packed=packed)
 
     # ------------------------------------------------------------------ visibility front-end (trackdlo_node.cpp:254-277, 346-360)
     def visibility_batched(self, X, x_offsets, Y, node_coord, visibility_threshold=0.008, d_vis=0.06):

@@ -2,7 +2,6 @@
 // Replaces the host-visible surface of trackdlo::cpd_lle / trackdlo::tracking_step
 // (trackdlo/include/trackdlo.h:81-102) for batches of independent frames.
 #include "../../include/trackdlo_b200.h"
-#include "tdlo_kernels.cuh"
 #include "tdlo_taskq.cuh"
 #include "tdlo_visibility.cuh"
 
@@ -28,34 +27,30 @@ struct tdlo_ctx {
     const int* cur_ready = nullptr; int cur_ready_frames = 0;
     // device staging for the host-pointer entry points
     double *d_X = nullptr, *d_Y = nullptr, *d_sigma2 = nullptr, *d_priors = nullptr, *d_H = nullptr, *d_W = nullptr;
-    double *d_rest = nullptr, *d_guide = nullptr, *d_priors_out = nullptr;
+    double *d_rest = nullptr, *d_guide = nullptr, *d_priors_out = nullptr, *d_packed = nullptr;
+    size_t priors_cap = 0;          // doubles in d_priors
     long long *d_xoff = nullptr, *d_visoff = nullptr, *d_extoff = nullptr;
     int *d_nnodes = nullptr, *d_npriors = nullptr, *d_nvis = nullptr, *d_iters = nullptr, *d_status = nullptr;
     int *d_vis = nullptr, *d_ext = nullptr, *d_npri_out = nullptr, *d_state = nullptr;
     // workspace
     double* d_Xc = nullptr;
     unsigned short* d_bkt = nullptr;
-    double* d_scratch = nullptr;
-    long long scratch_stride = 0;
-    int scratch_clusters = 0;
-    int* d_queue = nullptr;
+    double* d_exp_tab = nullptr;    // 2^(j/64), j = 0..63
     unsigned long long* d_prof = nullptr;   // phase cycle counters (enabled by tdlo_profile_phases)
     unsigned long long* d_prof_buf = nullptr;
-    int cluster_override = 0;
     // visibility front-end workspace
-    unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr, *d_vslice = nullptr; long long vslice_cap = 0;
+    unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr; long long* d_vslice = nullptr;
     double* d_vdmin = nullptr; int *d_vvis = nullptr, *d_vext = nullptr;
-    std::vector<int> h_vslice, h_vfirst;
     // task-queue engine (tdlo_taskq.cuh)
-    int engine = 1;                 // 1 = task queue (default), 0 = cluster-per-frame
     int tq_chunk = 0;               // raw points per chunk task (0 = automatic: 1024, or 2048 / 4096 for large batches)
     int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
+    double watchdog_ms = 20000.0;   // a CTA waiting longer than this for a task aborts the launch (0 = off)
+    cudaStream_t last_stream = nullptr; bool launched = false;
     double* d_fscratch = nullptr; long long fstride = 0;
     double *d_part = nullptr, *d_dminp = nullptr, *d_gath = nullptr; int* d_nkept = nullptr; double4* d_tsph = nullptr;
     unsigned long long* d_q = nullptr; unsigned qcap = 0; long long tq_chunks_cap = 0; int tq_alloc_chunk = 0;
-    long long points_hint = 0;      // points per frame of the current host call (0 = unknown)
     int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     char err[512] = {0};
 };
@@ -88,9 +83,9 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     void* ptrs[] = {ctx->d_X, ctx->d_Y, ctx->d_sigma2, ctx->d_priors, ctx->d_H, ctx->d_W, ctx->d_rest, ctx->d_guide,
-                    ctx->d_priors_out, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
+                    ctx->d_priors_out, ctx->d_packed, ctx->d_xoff, ctx->d_visoff, ctx->d_extoff, ctx->d_nnodes, ctx->d_npriors,
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
-                    ctx->d_Xc, ctx->d_bkt, ctx->d_scratch, ctx->d_queue, ctx->d_prof_buf,
+                    ctx->d_Xc, ctx->d_bkt, ctx->d_exp_tab, ctx->d_prof_buf,
                     ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph,
                     ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -131,9 +126,6 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     ctx->max_nodes = max_nodes;
     ctx->max_points = max_points_total;
     const size_t F = max_frames, N = max_nodes, P = (size_t)max_points_total;
-    const Scr sc = scr_layout(max_nodes);
-    ctx->scratch_stride = sc.total;
-    ctx->scratch_clusters = std::min<long long>((long long)ctx->sm_count * 2, (long long)max_frames);
 #define CKC(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e2_ = (call);                                                                   \
@@ -148,8 +140,8 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     CKC(dalloc(&ctx->d_ready, 1));
-    CKC(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ready_vals), 16 * sizeof(int)));
-    for (int i = 0; i < 16; i++) ctx->h_ready_vals[i] = i;
+    CKC(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ready_vals), 32 * sizeof(int)));     // [0..15] constants, [20] abort flag read-back
+    for (int i = 0; i < 32; i++) ctx->h_ready_vals[i] = i < 16 ? i : 0;
     CKC(dalloc(&ctx->d_X, P * 3));
     CKC(dalloc(&ctx->d_Xc, P * 3));
     CKC(dalloc(&ctx->d_bkt, P));
@@ -157,6 +149,7 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(dalloc(&ctx->d_Y, F * N * 3));
     CKC(dalloc(&ctx->d_sigma2, F));
     CKC(dalloc(&ctx->d_priors, F * N * 4));
+    ctx->priors_cap = F * N * 4;
     CKC(dalloc(&ctx->d_W, F * N * 3));
     CKC(dalloc(&ctx->d_rest, F * N));
     CKC(dalloc(&ctx->d_guide, F * N * 3));
@@ -172,22 +165,14 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(dalloc(&ctx->d_ext, F * N));
     CKC(dalloc(&ctx->d_npri_out, F));
     CKC(dalloc(&ctx->d_state, F));
-    CKC(dalloc(&ctx->d_scratch, (size_t)ctx->scratch_stride * ctx->scratch_clusters));
-    CKC(dalloc(&ctx->d_queue, 1));
     CKC(dalloc(&ctx->d_prof_buf, 16));
     // exp table 2^(j/64)
     double tab[64];
     for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
-    CKC(cudaMemcpyToSymbol(c_exp_tab, tab, sizeof(tab)));
+    CKC(dalloc(&ctx->d_exp_tab, 64));
+    CKC(cudaMemcpy(ctx->d_exp_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
 #undef CKC
     *out = ctx;
-    return TDLO_OK;
-}
-
-extern "C" int tdlo_set_cluster_size(tdlo_ctx* ctx, int32_t c) {
-    if (!ctx) return TDLO_ERR_INVALID;
-    if (!(c == 0 || c == 1 || c == 2 || c == 4 || c == 8 || c == 16)) return fail(ctx, TDLO_ERR_INVALID, "cluster size must be 0,1,2,4,8,16");
-    ctx->cluster_override = c;
     return TDLO_OK;
 }
 
@@ -200,16 +185,13 @@ extern "C" int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]) {
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
-typedef void (*kern_t)(const KArgs);
-
-static int pick_tile(int nmax, int budget) {
-    int best = 0;
-    for (int t = 32; t <= kMaxThreads; t += 32)
-        if (smem_layout(nmax, t).total <= budget) best = t;
-    return best;
+// kernel variants, one translation unit each (tdlo_tq_inst_*.cu): <node passes, threads, resident CTAs>
+namespace tdlo {
+#define TDLO_TQ_DECL(NAME) cudaError_t NAME##_prepare(int smem, int* occ); cudaError_t NAME##_launch(int grid, int smem, cudaStream_t s, const TqArgs& t);
+TDLO_TQ_DECL(tq_2_224_3) TDLO_TQ_DECL(tq_2_256_2) TDLO_TQ_DECL(tq_4_256_2) TDLO_TQ_DECL(tq_8_256_2)
+#undef TDLO_TQ_DECL
 }
-
-typedef void (*tq_kern_t)(const TqArgs);
+struct TqVariant { int npass, threads; cudaError_t (*prepare)(int, int*); cudaError_t (*launch)(int, int, cudaStream_t, const TqArgs&); };
 
 // Task-queue engine: one persistent launch, grid = SMs x resident CTAs, no clusters.
 static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
@@ -256,26 +238,20 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
         ctx->tq_alloc_chunk = chunk;
     }
     // kernel variants: <node passes, threads, resident CTAs>; the shared-memory layout is sized for 32*passes nodes
-    tq_kern_t kern;
-    int npass;
-    if (nmax <= 64) {
-        npass = 2;
-        if (threads <= 224) kern = tdlo_tq_kernel<2, 224, 3>;
-        else kern = tdlo_tq_kernel<2, 256, 2>;
-    }
-    else if (nmax <= 128) { npass = 4; kern = tdlo_tq_kernel<4, 256, 2>; }
-    else { npass = 8; kern = tdlo_tq_kernel<8, 256, 2>; }
-    const int threads_eff = (nmax <= 64 && threads <= 224) ? 224 : 256;
+    static const TqVariant kVariants[] = {{2, 224, tq_2_224_3_prepare, tq_2_224_3_launch}, {2, 256, tq_2_256_2_prepare, tq_2_256_2_launch},
+                                          {4, 256, tq_4_256_2_prepare, tq_4_256_2_launch}, {8, 256, tq_8_256_2_prepare, tq_8_256_2_launch}};
+    const TqVariant& kv = kVariants[nmax <= 64 ? (threads <= 224 ? 0 : 1) : (nmax <= 128 ? 2 : 3)];
+    const int npass = kv.npass, threads_eff = kv.threads;
     const TqSmemL L = tq_smem_layout(32 * npass, threads_eff / 32);
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads_eff, L.total));
+    CK(kv.prepare(L.total, &occ));
     if (occ < 1) return fail(ctx, TDLO_ERR_CUDA, "task-queue kernel does not fit (smem %d B, %d threads)", L.total, threads_eff);
     const int grid = ctx->sm_count * occ;
     TqArgs t;
     memset(&t, 0, sizeof(t));
     a.Xc = ctx->d_Xc; a.bkt = ctx->d_bkt; a.scr_nodes = ctx->max_nodes; a.prof = ctx->d_prof;
+    a.exp_tab = ctx->d_exp_tab; a.max_points = ctx->max_points;
     t.k = a;
     t.chunk = chunk;
     t.inflight = ctx->tq_inflight > 0 ? ctx->tq_inflight : std::max(grid / 2, 64);
@@ -287,81 +263,16 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.part_stride = 4 * ctx->max_nodes + 4;
     t.ready = ctx->cur_ready; t.ready_frames = ctx->cur_ready_frames;
     t.L = L;
+    t.watchdog_ns = (unsigned long long)(ctx->watchdog_ms * 1e6);
     CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));
-    CK(cudaMemcpyAsync(reinterpret_cast<int*>(ctx->d_q + 2), &t.inflight, sizeof(int), cudaMemcpyHostToDevice, stream));
-    kern<<<grid, threads_eff, L.total, stream>>>(t);
-    CK(cudaGetLastError());
+    ctx->last_stream = stream; ctx->launched = true;
+    CK(kv.launch(grid, L.total, stream, t));
     ctx->info[0] = 1; ctx->info[1] = grid; ctx->info[2] = threads_eff; ctx->info[3] = L.total; ctx->info[4] = chunk;
     ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
     return TDLO_OK;
 }
 
-static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream, long long points_per_frame_hint) {
-    if (ctx->engine == 1) return launch_tq(ctx, a, stream);
-    CK(cudaSetDevice(ctx->device));
-    const int nmax = a.nmax;
-    // ---- kernel variant + tile (= threads per CTA, one 32-point P slice per warp):
-    // <2,2>: Nn <= 64, two CTAs/SM; <4,1>: Nn <= 128; <8,1>: Nn <= 256.  Largest tile that fits.
-    const int budget2 = 113 * 1024, budget1 = 227 * 1024;
-    kern_t kern;
-    int tile, occ;
-    if (nmax <= 64) {
-        tile = pick_tile(nmax, budget2); occ = 2; kern = tdlo_em_kernel<2, 2>;
-        if (tile < 128) { tile = pick_tile(nmax, budget1); occ = 1; }
-    } else if (nmax <= 128) { kern = tdlo_em_kernel<4, 1>; tile = pick_tile(nmax, budget1); occ = 1; }
-    else { kern = tdlo_em_kernel<8, 1>; tile = pick_tile(nmax, budget1); occ = 1; }
-    if (tile < 64) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
-    const int smem = smem_layout(nmax, tile).total;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    // ---- cluster size
-    int C = ctx->cluster_override;
-    if (C == 0) {
-        const long long slots = (long long)ctx->sm_count * occ;
-        C = 1;
-        while (C < kMaxCluster && (long long)a.n_frames * (C * 2) <= slots) C *= 2;
-        if (points_per_frame_hint > 0) {          // do not split a frame finer than ~2 tiles per CTA
-            int cap = 1;
-            while (cap < kMaxCluster && (long long)cap * 2 * tile * 2 <= points_per_frame_hint) cap *= 2;
-            C = std::min(C, cap);
-        }
-    }
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    int max_clusters = 0;
-    for (;;) {
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(C, 1, 1);
-        cfg.blockDim = dim3(tile, 1, 1);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-        if (e == cudaSuccess && max_clusters > 0) break;
-        cudaGetLastError();
-        if (C == 1) return fail(ctx, TDLO_ERR_CUDA, "kernel does not fit (smem %d B, tile %d): %s", smem, tile, cudaGetErrorString(e));
-        C /= 2;
-    }
-    int n_clusters = std::min(std::min(a.n_frames, max_clusters), ctx->scratch_clusters);
-    if (n_clusters < 1) n_clusters = 1;
-    cfg.gridDim = dim3(n_clusters * C, 1, 1);
-    a.tile = tile;
-    a.L = smem_layout(nmax, tile);
-    a.Xc = ctx->d_Xc;
-    a.bkt = ctx->d_bkt;
-    a.scratch = ctx->d_scratch;
-    a.scratch_stride = ctx->scratch_stride;
-    a.queue = ctx->d_queue;
-    a.scr_nodes = ctx->max_nodes;
-    a.prof = ctx->d_prof;
-    CK(cudaMemsetAsync(ctx->d_queue, 0, sizeof(int), stream));
-    CK(cudaLaunchKernelEx(&cfg, kern, a));
-    ctx->info[0] = C; ctx->info[1] = n_clusters * C; ctx->info[2] = tile; ctx->info[3] = smem; ctx->info[4] = tile;
-    ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
-    return TDLO_OK;
-}
+static int launch(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) { return launch_tq(ctx, a, stream); }
 
 static CpdP to_dev(const tdlo_cpd_params& p) {
     CpdP d;
@@ -395,10 +306,12 @@ extern "C" int tdlo_cpd_lle_batched_device(tdlo_ctx* ctx, const tdlo_cpd_batch* 
     a.X = b->X; a.x_off = reinterpret_cast<const long long*>(b->x_offsets);
     a.n_nodes = b->n_nodes; a.Y = b->Y; a.sigma2 = b->sigma2;
     a.priors = b->priors; a.n_priors = b->n_priors; a.n_visible = b->n_visible; a.H = b->H;
+    a.priors_stride = b->priors_stride > 0 ? b->priors_stride : b->node_stride;
+    if (b->priors_stride < 0) return fail(ctx, TDLO_ERR_INVALID, "priors_stride must be >= 0");
     a.W = b->W; a.iters = b->iters; a.status = b->status;
     a.p0 = to_dev(*p);
     a.p1 = a.p0;
-    return launch(ctx, a, (cudaStream_t)stream, ctx->points_hint);
+    return launch(ctx, a, (cudaStream_t)stream);
 }
 
 extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track_batch* b, const tdlo_track_params* p, void* stream) {
@@ -424,6 +337,7 @@ extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track
     a.vis = b->visible; a.vis_off = reinterpret_cast<const long long*>(b->visible_offsets);
     a.ext = b->visible_ext; a.ext_off = reinterpret_cast<const long long*>(b->visible_ext_offsets);
     a.guide_out = b->guide_nodes; a.priors_out = b->priors; a.n_priors_out = b->n_priors; a.state_out = b->state;
+    a.packed_out = b->packed_results;
     // pre-processing call: cpd_lle(X, guide, s2, beta_pre, lambda_pre, lle_weight, mu, max_iter, tol, true)
     // with the header defaults alpha=0, k_vis=0, visibility_threshold=0.01 (trackdlo.cpp:927, trackdlo.h:91-95)
     a.p0.beta = p->beta_pre_proc; a.p0.lambda = p->lambda_pre_proc; a.p0.gamma = p->lle_weight; a.p0.mu = p->mu;
@@ -433,7 +347,7 @@ extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track
     a.p1.beta = p->beta; a.p1.lambda = p->lambda; a.p1.gamma = p->lle_weight; a.p1.mu = p->mu; a.p1.tol = p->tol;
     a.p1.alpha = p->alpha; a.p1.k_vis = p->k_vis; a.p1.tau = p->visibility_threshold; a.p1.prune_radius = p->prune_radius;
     a.p1.max_iter = p->max_iter; a.p1.include_lle = 0;
-    return launch(ctx, a, (cudaStream_t)stream, ctx->points_hint);
+    return launch(ctx, a, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -442,6 +356,25 @@ extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track
 #define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
 #define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream))
 
+// The persistent kernel's watchdog (tdlo_taskq.cuh: tq_watchdog) leaves a flag behind instead of hanging the caller:
+// queue its read-back behind the kernel, synchronise, and turn it into an error.
+static int sync_and_check(tdlo_ctx* ctx, cudaStream_t stream) {
+    int* h_abort = ctx->h_ready_vals + 20;
+    if (ctx->launched && ctx->d_q) CK(cudaMemcpyAsync(h_abort, reinterpret_cast<int*>(ctx->d_q + 3) + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (ctx->launched && *h_abort) {
+        *h_abort = 0;
+        return fail(ctx, TDLO_ERR_CUDA, "watchdog: the task queue made no progress for %.0f ms (lost task or missing upload); results of this call are invalid", ctx->watchdog_ms);
+    }
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_synchronize(tdlo_ctx* ctx) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return sync_and_check(ctx, ctx->last_stream);
+}
+
 // Uploads the concatenated point clouds.  With the task-queue engine and a batch worth splitting, the upload runs in
 // (up to) 8 groups of frames on the copy stream, each followed by a progress flag; the persistent kernel starts right
 // away on the main stream and a frame's first task waits for its group's flag, so that the transfer of the later
@@ -449,7 +382,7 @@ extern "C" int tdlo_tracking_step_batched_device(tdlo_ctx* ctx, const tdlo_track
 static int upload_points(tdlo_ctx* ctx, const double* X, const int64_t* x_offsets, int F) {
     const long long total = x_offsets[F];
     ctx->cur_ready = nullptr; ctx->cur_ready_frames = 0;
-    const int G = (ctx->engine == 1 && F >= 16 && total >= 200000) ? 8 : 1;
+    const int G = (F >= 16 && total >= 200000) ? 8 : 1;
     if (G == 1) {
         if (total > 0) H2D(ctx->d_X, X, (size_t)total * 3 * sizeof(double));
         return TDLO_OK;
@@ -482,7 +415,12 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     if (b->n_frames == 0) return TDLO_OK;
     if (b->node_stride < 4 || b->node_stride > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "node_stride %d outside [4,%d]", b->node_stride, ctx->max_nodes);
     if (!b->X || !b->x_offsets || !b->Y || !b->sigma2) return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2 are required");
+    { int rcp = check_params(ctx, p->mu, p->beta, p->max_iter, p->prune_radius); if (rcp) return rcp; }   // before any copy is queued
     const size_t F = b->n_frames, S = b->node_stride;
+    const size_t PS = b->priors_stride > 0 ? (size_t)b->priors_stride : S;
+    if (b->priors_stride < 0 || PS > 4u * TDLO_MAX_NODES) return fail(ctx, TDLO_ERR_INVALID, "priors_stride %d outside [0,%d]", b->priors_stride, 4 * TDLO_MAX_NODES);
+    if (b->priors && b->n_priors) for (size_t f = 0; f < F; f++) if (b->n_priors[f] < 0 || (size_t)b->n_priors[f] > PS)
+        return fail(ctx, TDLO_ERR_INVALID, "n_priors[%zu] = %d outside [0, priors_stride = %zu]", f, b->n_priors[f], PS);
     const long long total = b->x_offsets[F];
     if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
     for (size_t f = 0; f < F; f++) if (b->x_offsets[f + 1] < b->x_offsets[f]) return fail(ctx, TDLO_ERR_INVALID, "x_offsets not monotone");
@@ -494,7 +432,16 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     H2D(ctx->d_Y, b->Y, F * S * 3 * sizeof(double));
     H2D(ctx->d_sigma2, b->sigma2, F * sizeof(double));
     if (b->n_nodes) H2D(ctx->d_nnodes, b->n_nodes, F * sizeof(int));
-    if (b->priors) H2D(ctx->d_priors, b->priors, F * S * 4 * sizeof(double));
+    if (b->priors) {
+        if (PS * 4 * (size_t)ctx->max_frames > ctx->priors_cap) {     // longer prior lists than one row per node: grow the staging buffer
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_priors) cudaFree(ctx->d_priors);
+            ctx->d_priors = nullptr; ctx->priors_cap = 0;
+            CK(dalloc(&ctx->d_priors, PS * 4 * (size_t)ctx->max_frames));
+            ctx->priors_cap = PS * 4 * (size_t)ctx->max_frames;
+        }
+        H2D(ctx->d_priors, b->priors, F * PS * 4 * sizeof(double));
+    }
     if (b->n_priors) H2D(ctx->d_npriors, b->n_priors, F * sizeof(int));
     if (b->n_visible) H2D(ctx->d_nvis, b->n_visible, F * sizeof(int));
     if (b->H) H2D(ctx->d_H, b->H, F * S * S * sizeof(double));
@@ -507,18 +454,15 @@ extern "C" int tdlo_cpd_lle_batched(tdlo_ctx* ctx, const tdlo_cpd_batch* b, cons
     d.n_visible = b->n_visible ? ctx->d_nvis : nullptr;
     d.H = b->H ? ctx->d_H : nullptr;
     d.W = ctx->d_W; d.iters = ctx->d_iters; d.status = ctx->d_status;
-    ctx->points_hint = total / (long long)F;
     int rc = tdlo_cpd_lle_batched_device(ctx, &d, p, ctx->stream);
-    ctx->points_hint = 0;
     { int rcj = upload_points_join(ctx); if (!rc) rc = rcj; }
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }   // no copy from the caller's buffers left in flight
     D2H(b->Y, ctx->d_Y, F * S * 3 * sizeof(double));
     D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));
     if (b->W) D2H(b->W, ctx->d_W, F * S * 3 * sizeof(double));
     if (b->iters) D2H(b->iters, ctx->d_iters, F * sizeof(int));
     if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return TDLO_OK;
+    return sync_and_check(ctx, ctx->stream);
 }
 
 extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch* b, const tdlo_track_params* p) {
@@ -530,6 +474,8 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (!b->X || !b->x_offsets || !b->Y || !b->sigma2 || !b->geodesic_coord || !b->visible || !b->visible_offsets ||
         !b->visible_ext || !b->visible_ext_offsets)
         return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, sigma2, geodesic_coord and both visibility lists are required");
+    { int rcp = check_params(ctx, p->mu, p->beta, p->max_iter, p->prune_radius); if (rcp) return rcp; }   // before any copy is queued
+    if (!(p->beta_pre_proc > 0.0)) return fail(ctx, TDLO_ERR_INVALID, "beta_pre_proc must be > 0");
     const size_t F = b->n_frames, N = b->n_nodes;
     const long long total = b->x_offsets[F];
     if (b->x_offsets[0] != 0) return fail(ctx, TDLO_ERR_INVALID, "x_offsets[0] must be 0");
@@ -565,11 +511,14 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     d.H_pre = b->H_pre ? ctx->d_H : nullptr;
     d.guide_nodes = ctx->d_guide; d.priors = ctx->d_priors_out; d.n_priors = ctx->d_npri_out;
     d.iters = ctx->d_iters; d.status = ctx->d_status; d.state = ctx->d_state;
-    ctx->points_hint = total / (long long)F;
+    d.packed_results = nullptr;
+    if (b->packed_results) {
+        if (!ctx->d_packed) CK(dalloc(&ctx->d_packed, (size_t)ctx->max_frames * (3 * (size_t)ctx->max_nodes + 4)));
+        d.packed_results = ctx->d_packed;
+    }
     int rc = tdlo_tracking_step_batched_device(ctx, &d, p, ctx->stream);
-    ctx->points_hint = 0;
     { int rcj = upload_points_join(ctx); if (!rc) rc = rcj; }
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }   // no copy from the caller's buffers left in flight
     D2H(b->Y, ctx->d_Y, F * N * 3 * sizeof(double));
     D2H(b->sigma2, ctx->d_sigma2, F * sizeof(double));
     if (b->guide_nodes) D2H(b->guide_nodes, ctx->d_guide, F * N * 3 * sizeof(double));
@@ -578,8 +527,8 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
     if (b->iters) D2H(b->iters, ctx->d_iters, F * 2 * sizeof(int));
     if (b->status) D2H(b->status, ctx->d_status, F * sizeof(int));
     if (b->state) D2H(b->state, ctx->d_state, F * sizeof(int));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return TDLO_OK;
+    if (b->packed_results) D2H(b->packed_results, ctx->d_packed, F * (3 * N + 4) * sizeof(double));
+    return sync_and_check(ctx, ctx->stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -588,47 +537,36 @@ extern "C" int tdlo_tracking_step_batched(tdlo_ctx* ctx, const tdlo_track_batch*
 static int vis_workspace(tdlo_ctx* ctx) {
     if (ctx->d_vbits) return TDLO_OK;
     const size_t F = ctx->max_frames, N = ctx->max_nodes;
-    ctx->vslice_cap = ctx->max_points / VIS_SLICE + ctx->max_frames + 1;
     CK(dalloc(&ctx->d_vbits, F * N));
     CK(dalloc(&ctx->d_vtmp, 2 * F * N));
     CK(dalloc(&ctx->d_vcnt, 2 * F));
-    CK(dalloc(&ctx->d_vslice, 2 * (size_t)ctx->vslice_cap));
+    CK(dalloc(&ctx->d_vslice, F + 1));
     return TDLO_OK;
 }
 
-// x_off_host: host copy of the offsets (the slice table is built on the host; the device entry point reads the
-// offsets back once -- they are a few KB)
-static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, const long long* x_off_host, cudaStream_t stream) {
+// Stream-ordered: the slice table is built on the device (no read-back of the offsets).
+static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, cudaStream_t stream) {
     int rc = vis_workspace(ctx);
     if (rc) return rc;
     const int F = b->n_frames, N = b->n_nodes;
-    std::vector<int>& sl = ctx->h_vslice;          // kept alive in the context: the uploads below are asynchronous
-    std::vector<int>& first = ctx->h_vfirst;
-    sl.clear(); first.clear();
-    for (int f = 0; f < F; f++) {
-        const long long m = x_off_host[f + 1] - x_off_host[f];
-        for (long long s = 0; s * VIS_SLICE < m; s++) { sl.push_back(f); first.push_back((int)s); }
-    }
-    const int ns = (int)first.size();
-    if (ns > ctx->vslice_cap) return fail(ctx, TDLO_ERR_INVALID, "visibility: %d slices exceed capacity %lld", ns, ctx->vslice_cap);
     VisArgs a;
     a.n_frames = F; a.n_nodes = N;
     a.X = b->X; a.x_off = reinterpret_cast<const long long*>(b->x_offsets); a.Y = b->Y; a.node_coord = b->node_coord;
     a.tau = b->visibility_threshold; a.d_vis = b->d_vis;
     a.dmin2_bits = ctx->d_vbits; a.tmp_vis = ctx->d_vtmp; a.tmp_ext = ctx->d_vtmp + (size_t)ctx->max_frames * ctx->max_nodes;
     a.counts = ctx->d_vcnt; a.dmin_out = b->dmin;
+    a.slice_start = ctx->d_vslice; a.max_points = ctx->max_points;
     a.vis = b->visible; a.vis_off = reinterpret_cast<long long*>(b->visible_offsets);
     a.ext = b->visible_ext; a.ext_off = reinterpret_cast<long long*>(b->visible_ext_offsets);
     CK(cudaMemsetAsync(ctx->d_vbits, 0x7f, (size_t)F * N * sizeof(unsigned long long), stream));   // 0x7f7f... = 1.4e306
-    if (ns > 0) {
-        CK(cudaMemcpyAsync(ctx->d_vslice, sl.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(ctx->d_vslice + ctx->vslice_cap, first.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        tdlo_vis_dmin_kernel<<<ns, 256, 0, stream>>>(a, ctx->d_vslice, ctx->d_vslice + ctx->vslice_cap);
-    }
+    const long long max_slices = ctx->max_points / VIS_SLICE + F;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(max_slices, (long long)ctx->sm_count * 8));
+    tdlo_vis_slices_kernel<<<1, 256, 0, stream>>>(a);
+    tdlo_vis_dmin_kernel<<<grid, 256, 0, stream>>>(a);
     tdlo_vis_lists_kernel<<<(F + 63) / 64, 64, 0, stream>>>(a);
     tdlo_vis_compact_kernel<<<1, 256, 0, stream>>>(a);
     CK(cudaGetLastError());
-    ctx->info[5] = ns > 0 ? 3 : 2;
+    ctx->info[5] = 4;
     return TDLO_OK;
 }
 
@@ -647,10 +585,7 @@ extern "C" int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batc
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     if (b->n_frames == 0) return TDLO_OK;
-    std::vector<long long> xo((size_t)b->n_frames + 1);
-    CK(cudaMemcpyAsync(xo.data(), b->x_offsets, xo.size() * sizeof(long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    return vis_launch(ctx, b, xo.data(), (cudaStream_t)stream);
+    return vis_launch(ctx, b, (cudaStream_t)stream);
 }
 
 extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
@@ -676,7 +611,7 @@ extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
     d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.node_coord = ctx->d_rest;
     d.dmin = ctx->d_vdmin; d.visible = ctx->d_vvis; d.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
     d.visible_ext = ctx->d_vext; d.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
-    rc = vis_launch(ctx, &d, reinterpret_cast<const long long*>(b->x_offsets), ctx->stream);
+    rc = vis_launch(ctx, &d, ctx->stream);
     if (rc) return rc;
     if (b->dmin) D2H(b->dmin, ctx->d_vdmin, F * N * sizeof(double));
     D2H(b->visible_offsets, ctx->d_visoff, (F + 1) * sizeof(long long));
@@ -777,7 +712,7 @@ extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, cons
         v.visibility_threshold = p->visibility_threshold; v.d_vis = b->d_vis;
         v.visible = ctx->d_vvis; v.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
         v.visible_ext = ctx->d_vext; v.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
-        rc = vis_launch(ctx, &v, xo.data(), ctx->stream);
+        rc = vis_launch(ctx, &v, ctx->stream);
         if (rc) return rc;
         tdlo_track_batch d;
         memset(&d, 0, sizeof(d));
@@ -788,26 +723,20 @@ extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, cons
         d.visible_ext = ctx->d_vext; d.visible_ext_offsets = reinterpret_cast<const int64_t*>(ctx->d_extoff);
         d.guide_nodes = ctx->d_guide; d.priors = ctx->d_priors_out; d.n_priors = ctx->d_npri_out;
         d.iters = ctx->d_iters; d.status = ctx->d_status; d.state = ctx->d_state;
-        ctx->points_hint = xo[S] / S;
         rc = tdlo_tracking_step_batched_device(ctx, &d, p, ctx->stream);
-        ctx->points_hint = 0;
-        if (rc) return rc;
+            if (rc) return rc;
         if (b->Y_traj) D2H(b->Y_traj + (size_t)t * SN * 3, ctx->d_Y, SN * 3 * sizeof(double));
         if (b->iters_traj) D2H(b->iters_traj + (size_t)t * S * 2, ctx->d_iters, (size_t)S * 2 * sizeof(int));
         if (b->status_traj) D2H(b->status_traj + (size_t)t * S, ctx->d_status, (size_t)S * sizeof(int));
     }
     D2H(b->Y, ctx->d_Y, SN * 3 * sizeof(double));
     D2H(b->sigma2, ctx->d_sigma2, (size_t)S * sizeof(double));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return TDLO_OK;
+    return sync_and_check(ctx, ctx->stream);
 }
 
 extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
     if (!ctx) return TDLO_ERR_INVALID;
     switch (option) {
-        case TDLO_OPT_ENGINE:
-            if (value != 0.0 && value != 1.0) return fail(ctx, TDLO_ERR_INVALID, "engine must be 0 (cluster) or 1 (task queue)");
-            ctx->engine = (int)value; return TDLO_OK;
         case TDLO_OPT_CHUNK_POINTS: {
             const int c = (int)value;
             if (c != 0 && (c < 256 || c > (1 << 20) || (c % 32))) return fail(ctx, TDLO_ERR_INVALID, "chunk must be 0 (automatic) or a multiple of 32 in [256, 2^20]");
@@ -824,12 +753,14 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             if (t != 224 && t != 256) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256 (2 CTAs/SM)");
             ctx->tq_threads = t; return TDLO_OK;
         }
+        case TDLO_OPT_WATCHDOG_MS:
+            if (!(value >= 0.0)) return fail(ctx, TDLO_ERR_INVALID, "watchdog must be >= 0 ms (0 = off)");
+            ctx->watchdog_ms = value; return TDLO_OK;
         default: return fail(ctx, TDLO_ERR_INVALID, "unknown option %d", option);
     }
 }
 
-// Development aid: enable (and read back / reset) the per-phase cycle counters of the kernel.
-// cycles[0..7]: cluster rank 0 {setup, dmin pre-pass, E-step, wait, M-step, wait}; [8..15]: other ranks.
+// Development aid: enable (and read back / reset) the per-phase cycle counters of the kernel (slot meaning: header).
 extern "C" int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]) {
     if (!ctx) return TDLO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

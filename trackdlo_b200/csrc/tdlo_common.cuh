@@ -1,78 +1,36 @@
-// Device side of the B200-native TrackDLO registration path (sm_100a).
-//
-// One thread-block CLUSTER owns one frame for its whole life: prune -> set-up -> all EM
-// iterations of cpd_lle (trackdlo/src/trackdlo.cpp:161-441), and in tracking mode the full
-// tracking_step (trackdlo.cpp:900-999: pre-processing registration, traverse_euclidean, main
-// registration) without returning to the host.  Clusters pull frames from an atomic queue
-// (persistent scheduling), so data-dependent iteration counts (trackdlo.cpp:424-428) balance
-// automatically.  The Nn x Mp affinity matrix P is never written to HBM: each CTA streams its
-// slice of the frame's points in tiles, keeps one P tile in shared memory and reduces it to
-// P1 / PX partial sums in registers.
+// Device-side building blocks of the B200-native TrackDLO registration path (sm_100a), shared by the task-queue
+// engine (tdlo_taskq.cuh): parameters and frame arguments, the fp64 exp(-z), the prune + counting sort of a chunk of
+// points (trackdlo/src/trackdlo.cpp:177-195), the dense solvers that stand in for
+// completeOrthogonalDecomposition().solve (trackdlo.cpp:415), the LLE weights (:92-159) and traverse_euclidean
+// (:584-898, utils.cpp:172-241).
 //
 // Everything is fp64 (the reference is MatrixXd end to end; the parity gate is 1e-5 on W).
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdint.h>
 #include <math.h>
 
-namespace cg = cooperative_groups;
-
 namespace tdlo {
 
-constexpr int kMaxThreads = 256;
-constexpr int kMaxCluster = 16;
 constexpr int kMaxNodes = 256;
 
 // status bits (mirror include/trackdlo_b200.h)
 constexpr int ST_NOT_CONVERGED = 1, ST_SINGULAR = 2, ST_TOO_FEW_NODES = 4, ST_EMPTY = 8, ST_TRAVERSE_UB = 16,
-              ST_PRE_NOT_CONVERGED = 32;
+              ST_PRE_NOT_CONVERGED = 32, ST_BAD_INPUT = 64;
 
 struct CpdP {
     double beta, lambda, gamma, mu, tol, alpha, k_vis, tau, prune_radius;
     int max_iter, include_lle;
 };
 
-// ------------------------------------------------------------------------------------------
-// shared memory layout (bytes)
-// ------------------------------------------------------------------------------------------
-struct SmemL {
-    int tab, node4, wbuf, y0, s, vw, yext, jd, hy0, p1, px, wsol, tnew, pacc, red, gjbuf, prow, used, ptile, total;
-};
-__host__ __device__ inline SmemL smem_layout(int N, int tile) {
-    SmemL l;
-    int o = 0;
-    l.tab = o; o += 64 * 8;
-    l.node4 = o; o += N * 32;
-    l.wbuf = o; o += tile * 32;
-    l.y0 = o; o += 3 * N * 8;
-    l.s = o; o += N * 8;
-    l.vw = o; o += N * 8;
-    l.yext = o; o += 3 * N * 8;
-    l.jd = o; o += N * 8;
-    l.hy0 = o; o += 3 * N * 8;
-    l.p1 = o; o += N * 8;
-    l.px = o; o += 3 * N * 8;
-    l.wsol = o; o += 3 * N * 8;
-    l.tnew = o; o += 3 * N * 8;
-    l.pacc = o; o += 4 * N * 8;
-    l.red = o; o += 64 * 8;
-    l.gjbuf = o; o += 132 * 8;
-    l.prow = o; o += N * 4;
-    l.used = o; o += N * 4;
-    o = (o + 31) & ~31;
-    l.ptile = o; o += (tile / 32) * N * 33 * 8;      // one [N][33] P slice per warp
-    l.total = o;
-    return l;
-}
-
 struct KArgs {
     int mode;            // 0 = batched cpd_lle, 1 = batched tracking_step
     int n_frames;
-    int node_stride;     // row stride of Y / priors / W / H (nodes)
-    int tile;            // points per tile == blockDim.x
-    int nmax;            // largest node count in the batch (sizes shared memory)
+    int node_stride;     // row stride of Y / W / H (nodes)
+    int priors_stride;   // rows per frame of `priors` (mode 0)
+    int nmax;            // largest node count in the batch (selects the kernel variant)
+    long long max_points;   // capacity of Xc / bkt / the per-chunk arrays: frames whose offsets exceed it are refused
     // frame data (device pointers)
     const double* X; const long long* x_off;
     const int* n_nodes;
@@ -85,51 +43,20 @@ struct KArgs {
     const int* vis; const long long* vis_off;
     const int* ext; const long long* ext_off;
     double* guide_out; double* priors_out; int* n_priors_out; int* state_out;
+    double* packed_out;  // optional [n_frames][3*node_stride + 4]: {Y, sigma2, iters_pre, iters_main, status} per frame (one all-gather)
     CpdP p0;             // mode 0: the call's params; mode 1: pre-processing registration
     CpdP p1;             // mode 1: main registration
     // workspace
     double* Xc;          // compacted points, same indexing as X
     unsigned short* bkt; // nearest-node bucket per raw point (sort key), same indexing as X
-    double* scratch;     // per-cluster scratch
-    long long scratch_stride;   // doubles per cluster
-    int* queue;          // frame queue counter
     int scr_nodes;       // node capacity the scratch layout was sized for
-    unsigned long long* prof;   // optional [16] phase cycle counters (rank 0: 0..7, other ranks: 8..15)
-    SmemL L;             // shared-memory layout, computed by the host (keeps address arithmetic out of the kernel)
+    unsigned long long* prof;   // optional [16] phase cycle counters
+    const double* exp_tab;      // [64] 2^(j/64), filled by the host at context creation
 };
 
-__constant__ double c_exp_tab[64];   // 2^(j/64), filled by the host
-
-// ------------------------------------------------------------------------------------------
-// per-cluster global scratch layout (doubles); N = scr_nodes
-// ------------------------------------------------------------------------------------------
-struct Scr {
-    long long G, HG, H, AB, PART, DMIN, GATH, STATE, TRV, PRI, GUIDE, CTL, total;
-};
-__host__ __device__ inline Scr scr_layout(int N) {
-    Scr s;
-    long long o = 0, n2 = (long long)N * N;
-    s.G = o; o += n2;
-    s.HG = o; o += n2;
-    s.H = o; o += n2;
-    s.AB = o; o += (long long)N * (N + 4);
-    s.PART = o; o += (long long)kMaxCluster * (4 * N + 4);
-    s.DMIN = o; o += (long long)kMaxCluster * N;
-    s.GATH = o; o += kMaxCluster * 2;
-    s.STATE = o; o += 3 * N + 8;
-    s.TRV = o; o += 2LL * (N + 2) * 4;
-    s.PRI = o; o += (2LL * N + 4) * 4;
-    s.GUIDE = o; o += 3 * N;
-    s.CTL = o; o += 8;
-    s.total = (o + 15) & ~15LL;
-    return s;
-}
-
+// the shared-memory arrays prune_sort_slice works in
 struct Smem {
-    double* tab; double4* node4; double4* wbuf;
-    double *y0, *s, *vw, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *pacc, *red, *gjbuf;
-    int *prow, *used;
-    double* ptile;
+    double4* node4; double* red; double* ptile;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -191,7 +118,7 @@ __device__ __forceinline__ double dist2(double ax, double ay, double az, double 
 // bkt: global temp, one uint16 per raw point (nearest node, 0xffff = pruned).
 // Returns the number of kept points (uniform over the block); *sum_out gets the block sum.
 // ------------------------------------------------------------------------------------------
-__device__ int prune_sort_slice(const Smem& sm, const double* __restrict__ Xraw, long long r0, long long r1,
+static __device__ int prune_sort_slice(const Smem& sm, const double* __restrict__ Xraw, long long r0, long long r1,
                                 double* __restrict__ Xc, unsigned short* __restrict__ bkt, int Nn, double radius,
                                 double* sum_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
@@ -253,257 +180,6 @@ __device__ int prune_sort_slice(const Smem& sm, const double* __restrict__ Xraw,
     return count;
 }
 
-// ------------------------------------------------------------------------------------------
-// Visibility pre-pass: per-node min squared distance to this CTA's points (trackdlo.cpp:279-296).
-// Result (per-CTA partial) is written to dmin_out[0..Nn).
-// ------------------------------------------------------------------------------------------
-__device__ void dmin_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn, double* dmin_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, tile = blockDim.x;
-    double* wmin = sm.ptile;                   // [nw][Nn], P tile is idle here
-    for (int i = tid; i < nw * Nn; i += tile) wmin[i] = 1e300;
-    __syncthreads();
-    for (int base = 0; base < n_local; base += tile) {
-        const int n = base + tid;
-        const bool valid = n < n_local;
-        double x = 0, y = 0, z = 0;
-        if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
-        for (int j = 0; j < Nn; j++) {
-            const double4 q = sm.node4[j];
-            double d2 = dist2(q.x, q.y, q.z, x, y, z);
-            if (!valid) d2 = 1e300;
-            // warp min of a non-negative double: order == order of its bit pattern
-            const unsigned hi = (unsigned)__double2hiint(d2);
-            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-            const unsigned lo = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
-            const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
-            if (lane == 0) {
-                const double m = __hiloint2double((int)mh, (int)ml);
-                double* slot = wmin + warp * Nn + j;
-                if (m < *slot) *slot = m;
-            }
-        }
-    }
-    __syncthreads();
-    for (int j = tid; j < Nn; j += tile) {
-        double m = wmin[j];
-        for (int w = 1; w < nw; w++) m = fmin(m, wmin[w * Nn + j]);
-        __stcg(dmin_out + j, m);
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused E-step over this CTA's slice (trackdlo.cpp:278-389): distances -> arg-max node ->
-// geodesic distances -> P -> (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.
-// Every WARP is autonomous: it takes 32 points at a time (lane = point), writes their P columns
-// into its private shared-memory slice pt[node][33] (phase A), then switches to lane = node and
-// accumulates P1/PX for its nodes over those 32 points in registers (phase B).  Only __syncwarp
-// separates the phases, so the warps of a CTA overlap their phases freely and no block barrier
-// sits in the hot loop.  NPASS = ceil(Nn / 32) node passes in phase B (compile time).
-// part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
-// ------------------------------------------------------------------------------------------
-template <int NPASS, bool VIS>
-__device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n_local, int Nn,
-                            double sigma2, double c_norm, double rscale, double* part_out) {
-    constexpr int RS = 33;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
-    double* __restrict__ pt = sm.ptile + warp * (Nn * RS);
-    double4* __restrict__ wb = sm.wbuf + warp * 32;
-    double* __restrict__ pcol = pt + lane;
-    const double* __restrict__ tab = sm.tab;
-    double acc[NPASS][4];
-#pragma unroll
-    for (int ps = 0; ps < NPASS; ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
-    double sxx = 0.0;
-    const double uflow = 1490.2 * sigma2;      // cheap pre-test: below this exp(-0.5*d2/sigma2) cannot underflow to 0
-
-    for (int base = warp * 32; base < n_local; base += nw * 32) {
-        const int n = base + lane;
-        const bool valid = n < n_local;
-        double x = 0, y = 0, z = 0;
-        if (valid) { x = Xc[(long long)n * 3]; y = Xc[(long long)n * 3 + 1]; z = Xc[(long long)n * 3 + 2]; }
-
-        // ---- nearest node (== arg-max of the Gaussian P of trackdlo.cpp:298-310).
-        // Exact pruning of the search range: with c = the point of lane 0 and rho = max_lane |x - c|, a node m
-        // with |Y_m - c| > min_m' |Y_m' - c| + 2 rho is strictly farther from EVERY point of this warp than the
-        // node nearest to c (triangle inequality), so it can be neither the arg-min nor tie with it.  The scan
-        // covers the contiguous index range [ja, jb] spanned by the surviving nodes -> same first-minimum as
-        // the full scan.  The points are sorted by nearest node, so the range is a handful of nodes.
-        int ja, jb;
-        {
-            const double cx = __shfl_sync(0xffffffffu, x, 0), cy = __shfl_sync(0xffffffffu, y, 0), cz = __shfl_sync(0xffffffffu, z, 0);
-            const double r2 = valid ? dist2(x, y, z, cx, cy, cz) : 0.0;
-            const unsigned rh = __reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(r2));
-            const unsigned rl = __reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(r2) == rh ? (unsigned)__double2loint(r2) : 0u);
-            const double rho = sqrt(__hiloint2double((int)rh, (int)rl));
-            double dc[NPASS];
-            double dloc = 1e300;
-#pragma unroll
-            for (int ps = 0; ps < NPASS; ps++) {
-                const int m = lane + 32 * ps;
-                dc[ps] = 1e300;
-                if (m < Nn) { const double4 q = sm.node4[m]; dc[ps] = sqrt(dist2(q.x, q.y, q.z, cx, cy, cz)); }
-                dloc = fmin(dloc, dc[ps]);
-            }
-            const unsigned dh = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(dloc));
-            const unsigned dl = __reduce_min_sync(0xffffffffu, (unsigned)__double2hiint(dloc) == dh ? (unsigned)__double2loint(dloc) : 0xffffffffu);
-            const double lim = (__hiloint2double((int)dh, (int)dl) + 2.0 * rho) * (1.0 + 1e-12) + 1e-300;
-            ja = Nn; jb = -1;
-#pragma unroll
-            for (int ps = 0; ps < NPASS; ps++) {
-                const unsigned mk = __ballot_sync(0xffffffffu, dc[ps] <= lim);
-                if (mk) { if (ja == Nn) ja = 32 * ps + __ffs(mk) - 1; jb = 32 * ps + 31 - __clz(mk); }
-            }
-        }
-        double best = 1e300;
-        int a = ja;
-        {
-            int j = ja;
-            for (; j + 3 <= jb; j += 4) {
-                const double4 q0 = sm.node4[j], q1 = sm.node4[j + 1], q2 = sm.node4[j + 2], q3 = sm.node4[j + 3];
-                const double e0 = dist2(q0.x, q0.y, q0.z, x, y, z), e1 = dist2(q1.x, q1.y, q1.z, x, y, z);
-                const double e2 = dist2(q2.x, q2.y, q2.z, x, y, z), e3 = dist2(q3.x, q3.y, q3.z, x, y, z);
-                if (e0 < best) { best = e0; a = j; }
-                if (e1 < best) { best = e1; a = j + 1; }
-                if (e2 < best) { best = e2; a = j + 2; }
-                if (e3 < best) { best = e3; a = j + 3; }
-            }
-            for (; j <= jb; j++) {
-                const double4 q = sm.node4[j];
-                const double d2 = dist2(q.x, q.y, q.z, x, y, z);
-                if (d2 < best) { best = d2; a = j; }
-            }
-        }
-        // whole column underflows to 0 in the reference -> maxCoeff returns index 0
-        if (best > uflow && (-0.5 * best) / sigma2 < -745.1332191019412) a = 0;
-        int q1 = a - 1; if (q1 == -1) q1 = 2;
-        int q2 = a + 1; if (q2 == Nn) q2 = Nn - 3;
-        double da, d1, d2n;
-        { const double4 q = sm.node4[a];  da  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        { const double4 q = sm.node4[q1]; d1  = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        { const double4 q = sm.node4[q2]; d2n = sqrt(dist2(q.x, q.y, q.z, x, y, z)); }
-        const bool pick1 = d1 < d2n;                     // trackdlo.cpp:324-329
-        const int b = pick1 ? q1 : q2;
-        const double db = pick1 ? d1 : d2n;
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        const double dlo = a < b ? da : db, dhi = a < b ? db : da;
-        // scaled geodesic coordinate: t = sqrt(0.5/sigma2) * (|s_j - s_ref| + d_ref)
-        const double alo = sm.node4[lo].w + dlo * rscale;        //  s'_lo + d'_lo  (minus s'_j)
-        const double ahi = dhi * rscale - sm.node4[hi].w;        //  d'_hi - s'_hi  (plus  s'_j)
-
-        // ---- node window of this warp: outside [jlo, jhi] every P entry of these 32 points is EXACTLY 0 in
-        // the reference (exp underflows for -0.5*geo/sigma2 < -745.13), so those rows are skipped.  A lane
-        // needs j <= lo while s'_j > alo - T and j >= hi while s'_j < T - ahi (T^2 = 745.2); [lo, hi] itself
-        // is always kept (the end quirk puts P = 1 between them).  The points are sorted by nearest node,
-        // so the union over the warp stays narrow once sigma2 is small.
-        int jlo, jhi;
-        {
-            const double T = 27.298351598585583;              // sqrt(745.2)
-            double mlo = valid ? alo : 1e300, mhi = valid ? ahi : 1e300;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-                mhi = fmin(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
-            }
-            const int lomin = __reduce_min_sync(0xffffffffu, valid ? lo : Nn);
-            const int himax = __reduce_max_sync(0xffffffffu, valid ? hi : -1);
-            const double thr_lo = mlo - T, thr_hi = T - mhi;
-            jlo = Nn; jhi = -1;
-            for (int c = 0; c < Nn; c += 32) {
-                const int j = c + lane;
-                const double sj = j < Nn ? sm.node4[j].w : 0.0;
-                const unsigned m1 = __ballot_sync(0xffffffffu, j < Nn && sj > thr_lo);
-                const unsigned m2 = __ballot_sync(0xffffffffu, j < Nn && sj < thr_hi);
-                if (m1 && jlo == Nn) jlo = c + __ffs(m1) - 1;
-                if (m2) jhi = c + 31 - __clz(m2);
-            }
-            jlo = min(jlo, lomin); jhi = max(jhi, himax);
-        }
-
-        // ---- phase A: P column (trackdlo.cpp:332-354, 358-375).  Four nodes per trip: all shared-memory
-        // loads of a trip precede its stores, so the four exp chains are independent and interleave.
-        double colsum = 0.0;
-        {
-            const double4* nd = sm.node4;
-            const double* vw = sm.vw;
-            double* pc = pcol + jlo * RS;
-            int j = jlo;
-            for (; j + 3 <= jhi; j += 4) {
-                const double s0 = nd[j].w, s1 = nd[j + 1].w, s2 = nd[j + 2].w, s3 = nd[j + 3].w;
-                double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
-                if (VIS) { v0 = vw[j]; v1 = vw[j + 1]; v2 = vw[j + 2]; v3 = vw[j + 3]; }
-                const double t0 = (j <= lo) ? (alo - s0) : (ahi + s0);
-                const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
-                const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
-                const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
-                double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
-                if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
-                colsum += (p0 + p1) + (p2 + p3);
-                pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3;
-                pc += 4 * RS;
-            }
-            for (; j <= jhi; j++) {
-                const double sj = nd[j].w;
-                const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
-                double p = exp_neg(t * t, tab);
-                if (VIS) p *= vw[j];
-                colsum += p;
-                *pc = p;
-                pc += RS;
-            }
-        }
-        if (hi - lo == 2) {                              // row strictly between lo and hi keeps geodesic 0 (end quirk)
-            const int jb = lo + 1;
-            const double pn = VIS ? sm.vw[jb] : 1.0;
-            colsum += pn - pcol[jb * RS];
-            pcol[jb * RS] = pn;
-        }
-        const double den = colsum + c_norm;              // trackdlo.cpp:379 / 382
-        const double w = valid ? 1.0 / den : 0.0;
-        sxx = fma(colsum * w, x * x + y * y + z * z, sxx);   // Pt1_n * |x_n|^2 (trackdlo.cpp:418)
-        wb[lane] = make_double4(w, w * x, w * y, w * z);
-        __syncwarp();
-
-        // ---- phase B: lane = node; P1 / PX over this warp's 32 points (trackdlo.cpp:387-389).
-        // Lanes whose node lies outside the window are masked off; a pass with no node inside is skipped.
-#pragma unroll
-        for (int ps = 0; ps < NPASS; ps++) {
-            const int m = lane + 32 * ps;
-            if (m >= jlo && m <= jhi) {
-                const double* __restrict__ prow = pt + m * RS;
-#pragma unroll 8
-                for (int nn = 0; nn < 32; nn++) {
-                    const double p = prow[nn];
-                    const double4 w4 = wb[nn];
-                    acc[ps][0] = fma(p, w4.x, acc[ps][0]); acc[ps][1] = fma(p, w4.y, acc[ps][1]);
-                    acc[ps][2] = fma(p, w4.z, acc[ps][2]); acc[ps][3] = fma(p, w4.w, acc[ps][3]);
-                }
-            }
-        }
-        __syncwarp();
-    }
-
-    // ---- cross-warp reduction in a fixed order (deterministic)
-    __syncthreads();
-    double* __restrict__ racc = sm.ptile;                 // [nw][Nn][4]; the P slices are dead now
-#pragma unroll
-    for (int ps = 0; ps < NPASS; ps++) {
-        const int m = lane + 32 * ps;
-        if (m < Nn) {
-            double* dst = racc + ((long long)warp * Nn + m) * 4;
-            dst[0] = acc[ps][0]; dst[1] = acc[ps][1]; dst[2] = acc[ps][2]; dst[3] = acc[ps][3];
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < 4 * Nn; i += nt) {
-        double v = 0.0;
-        for (int w = 0; w < nw; w++) v += racc[w * 4 * Nn + i];
-        __stcg(part_out + i, v);
-    }
-    const double sx = block_sum(sxx, sm.red);
-    if (tid == 0) __stcg(part_out + 4 * Nn, sx);
-    __syncthreads();
-}
 
 // ------------------------------------------------------------------------------------------
 // Gauss-Jordan elimination with implicit partial (row) pivoting on the augmented system
@@ -511,7 +187,7 @@ __device__ void estep_slice(const Smem& sm, const double* __restrict__ Xc, int n
 // (trackdlo.cpp:415) for the full-rank A of this path.  Block-cooperative; W -> wsol[n][3].
 // Returns non-zero (uniform) if a zero / non-finite pivot was met.
 // ------------------------------------------------------------------------------------------
-__device__ int gj_solve(double* AB, int n, int ld, int* prow, int* used, double* rpiv_slot, double* wsol) {
+static __device__ int gj_solve(double* AB, int n, int ld, int* prow, int* used, double* rpiv_slot, double* wsol) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int ncol = n + 3;
     for (int i = tid; i < n; i += nt) used[i] = 0;
@@ -592,7 +268,7 @@ __device__ __forceinline__ void gj_pick(double v0, double v1, bool ok0, bool ok1
 // compiler emits LDS/STS with 32-bit addresses).
 // pivot == false: the caller guarantees a symmetric positive definite A (elimination in natural order is
 // stable, every pivot is positive); the search is skipped and the pivot warp's chain is ~3x shorter.
-__device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __restrict__ gj, int* __restrict__ pivs,
+static __device__ int gj_solve_small(double* __restrict__ AB, int n, int ld, double* __restrict__ gj, int* __restrict__ pivs,
                               double* __restrict__ wsol, const bool pivot, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int ncol = n + 3;
@@ -721,7 +397,7 @@ __device__ __forceinline__ double rcp_fast(double x) {          // ~1 ulp recipr
 }
 
 template <int CW, bool PIVOT>
-__device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, double* wsol) {   // no __restrict__: buf is written by other threads
+static __device__ int gj_solve_regs(const double* AB, int n, int ld, double* buf, double* wsol) {   // no __restrict__: buf is written by other threads
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nt = blockDim.x, nwarp = nt >> 5;
     const int ncol = n + 3;
     double* mcol = buf;                 // [2][64]
@@ -841,7 +517,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 }
 
 template <int NB>
-__device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double* wsol) {
+static __device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double* wsol) {
     constexpr int LDP = NB + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
     double* Lp = work;                       // [n][LDP] panel (rows k0.. of columns k0..k0+nb)
@@ -1008,7 +684,7 @@ __device__ int chol_solve_blocked(double* A, int n, int ld, double* work, double
 // produce identical bits (the 6x6 Gram matrices are rank 3; their inverse is rounding noise).
 // Writes row i of E = I - L into E[i*ldE + ...] (row must be pre-zeroed).
 // ------------------------------------------------------------------------------------------
-__device__ int lle_lu6(double* a, int nb, int* piv) {
+static __device__ int lle_lu6(double* a, int nb, int* piv) {
     int sign = 1;
     for (int k = 0; k < nb; k++) {
         int p = k;
@@ -1034,7 +710,7 @@ __device__ int lle_lu6(double* a, int nb, int* piv) {
     return sign;
 }
 
-__device__ void lle_row(const double* __restrict__ y0 /*[n][3]*/, int M, int i, double* Erow) {
+static __device__ void lle_row(const double* __restrict__ y0 /*[n][3]*/, int M, int i, double* Erow) {
     int nbr[6];
     int nb = 0;
     const int k = 3;
@@ -1092,7 +768,7 @@ struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 ld3(const double* g, int i) { return {g[i * 3], g[i * 3 + 1], g[i * 3 + 2]}; }
 __device__ __forceinline__ double vdist(V3 a, V3 b) { return sqrt(dist2(a.x, a.y, a.z, b.x, b.y, b.z)); }
 
-__device__ bool is_between(V3 x, V3 a, V3 b) {
+static __device__ bool is_between(V3 x, V3 a, V3 b) {
     const double xs[3] = {x.x, x.y, x.z}, as[3] = {a.x, a.y, a.z}, bs[3] = {b.x, b.y, b.z};
     bool in_bound = true;
     for (int i = 0; i < 3; i++) {
@@ -1102,7 +778,7 @@ __device__ bool is_between(V3 x, V3 a, V3 b) {
     return in_bound;
 }
 
-__device__ int line_sphere(V3 A, V3 B, V3 C, double radius, V3* out) {
+static __device__ int line_sphere(V3 A, V3 B, V3 C, double radius, V3* out) {
     const double a = dist2(A.x, A.y, A.z, B.x, B.y, B.z);
     const double b = 2 * ((B.x - A.x) * (A.x - C.x) + (B.y - A.y) * (A.y - C.y) + (B.z - A.z) * (A.z - C.z));
     const double c = dist2(A.x, A.y, A.z, C.x, C.y, C.z) - radius * radius;
@@ -1125,7 +801,7 @@ __device__ int line_sphere(V3 A, V3 B, V3 C, double radius, V3* out) {
 }
 
 // scans segments i = from, from+dir, ... while (dir>0 ? i+1 <= bound : i >= bound); returns yielding i or -1
-__device__ int pursue(const double* guide, int from, int dir, int bound, V3& centre, double look) {
+static __device__ int pursue(const double* guide, int from, int dir, int bound, V3& centre, double look) {
     for (int i = from; dir > 0 ? (i + 1 <= bound) : (i >= bound); i += dir) {
         const V3 A = ld3(guide, i), B = ld3(guide, i + dir);
         V3 xs[2];
@@ -1146,7 +822,7 @@ __device__ __forceinline__ void emit4(double* out, int& cnt, double idx, V3 p) {
 }
 
 // returns number of pairs written to out ([<= G+1][4]); *err |= bits on reference-UB paths
-__device__ int traverse_euclidean(const double* geo, int G, const double* guide, int R, const int* vis, int V,
+static __device__ int traverse_euclidean(const double* geo, int G, const double* guide, int R, const int* vis, int V,
                                   int alignment, int align_idx, double* out, int* err) {
     int cnt = 0;
     if (R == 1) { emit4(out, cnt, vis[0], ld3(guide, 0)); return cnt; }
@@ -1211,452 +887,6 @@ __device__ int traverse_euclidean(const double* geo, int G, const double* guide,
         }
     }
     return cnt;
-}
-
-// ------------------------------------------------------------------------------------------
-// One cpd_lle call executed by the whole cluster (trackdlo.cpp:161-441).
-// All CTAs execute the same sequence of cluster barriers.  Returns the status mask (uniform).
-// Yio: global [Nn][3] in/out.  sigma2_out / Wout / iters_out may be null.
-// ------------------------------------------------------------------------------------------
-template <int NPASS>
-__device__ int cpd_run(cg::cluster_group& cluster, const Smem& sm, const KArgs& a, double* cscr,
-                       const double* __restrict__ Xraw, long long m0, double* __restrict__ Xc,
-                       double* Yio, int Nn, double sigma2_in, double* sigma2_out, const CpdP& p,
-                       const double* priors, int n_priors, int n_visible, const double* Hext, int hstride,
-                       double* Wout, int* iters_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
-    const int rank = (int)cluster.block_rank();
-    const int C = (int)cluster.num_blocks();
-    const Scr sc = scr_layout(a.scr_nodes);
-    double* gG = cscr + sc.G;
-    double* gHG = cscr + sc.HG;
-    double* gH = cscr + sc.H;
-    double* gPART = cscr + sc.PART;
-    double* gDMIN = cscr + sc.DMIN;
-    double* gGATH = cscr + sc.GATH;
-    double* gSTATE = cscr + sc.STATE;
-    const int ld = Nn + 3;
-    const bool ab_in_smem = (long long)Nn * (Nn + 3) <= (long long)(a.tile / 32) * a.nmax * 33;
-    double* AB = ab_in_smem ? sm.ptile : (cscr + sc.AB);
-
-    if (Nn < 4) {                         // reference indexes rows 2 and Nn-3 (trackdlo.cpp:313-321)
-        if (rank == 0 && tid == 0) { if (iters_out) *iters_out = 0; }
-        return ST_TOO_FEW_NODES;
-    }
-
-    // ---- Y -> shared (Y0 and current Y), arc-length coordinates s (trackdlo.cpp:203, 216-223)
-    for (int i = tid; i < 3 * Nn; i += nt) sm.y0[i] = Yio[i];
-    __syncthreads();
-    for (int j = tid; j < Nn; j += nt) sm.node4[j] = make_double4(sm.y0[3 * j], sm.y0[3 * j + 1], sm.y0[3 * j + 2], 0.0);
-    if (tid == 0) {
-        double cur = 0.0;
-        sm.s[0] = 0.0;
-        for (int i = 0; i < Nn - 1; i++) {
-            cur += sqrt(dist2(sm.y0[3 * i + 3], sm.y0[3 * i + 4], sm.y0[3 * i + 5], sm.y0[3 * i], sm.y0[3 * i + 1], sm.y0[3 * i + 2]));
-            sm.s[i + 1] = cur;
-        }
-    }
-    __syncthreads();
-
-    // ---- prune + compaction of this CTA's slice (trackdlo.cpp:177-195)
-    const long long per = (m0 + C - 1) / C;
-    long long r0 = per * rank, r1 = r0 + per;
-    if (r0 > m0) r0 = m0;
-    if (r1 > m0) r1 = m0;
-    double sum_local;
-    const int n_local = prune_sort_slice(sm, Xraw, r0, r1, Xc, a.bkt + (Xraw - a.X) / 3, Nn, p.prune_radius, &sum_local);
-    if (tid == 0) { __stcg(gGATH + 2 * rank, (double)n_local); __stcg(gGATH + 2 * rank + 1, sum_local); }
-    const double* Xloc = Xc + r0 * 3;
-
-    // ---- rank 0: G, LLE products, priors (trackdlo.cpp:225-260)
-    if (rank == 0) {
-        const double beta = p.beta;
-        for (int idx = tid; idx < Nn * Nn; idx += nt) {
-            const int i = idx / Nn, j = idx - i * Nn;
-            const double dd = fabs(sm.s[i] - sm.s[j]);
-            gG[idx] = 1 / (2 * beta * 2 * beta) * exp(-sqrt(2.0) * dd / beta) * (2 * dd + sqrt(2.0) * beta);
-        }
-        for (int i = tid; i < Nn; i += nt) sm.jd[i] = 0.0;
-        for (int i = tid; i < 3 * Nn; i += nt) sm.yext[i] = sm.y0[i];
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < n_priors; k++) {
-                const int idx = (int)priors[k * 4];
-                if (idx < 0 || idx >= Nn) continue;
-                sm.jd[idx] = 1.0;
-                sm.yext[idx * 3] = priors[k * 4 + 1]; sm.yext[idx * 3 + 1] = priors[k * 4 + 2]; sm.yext[idx * 3 + 2] = priors[k * 4 + 3];
-            }
-        }
-        if (p.include_lle) {
-            if (Hext) {
-                for (int idx = tid; idx < Nn * Nn; idx += nt) { const int i = idx / Nn, j = idx - i * Nn; gH[idx] = Hext[(long long)i * hstride + j]; }
-            } else {
-                double* E = cscr + sc.AB;                              // dense E = I - L
-                for (int idx = tid; idx < Nn * Nn; idx += nt) E[idx] = 0.0;
-                __syncthreads();
-                for (int i = tid; i < Nn; i += nt) lle_row(sm.y0, Nn, i, E + (long long)i * Nn);
-                __syncthreads();
-                for (int idx = tid; idx < Nn * Nn; idx += nt) {        // H = E^T E, k ascending, band only
-                    const int r = idx / Nn, c = idx - r * Nn;
-                    double s = 0.0;
-                    int klo = (r > c ? r : c) - 3, khi = (r < c ? r : c) + 3;
-                    if (klo < 0) klo = 0;
-                    if (khi > Nn - 1) khi = Nn - 1;
-                    for (int k = klo; k <= khi; k++) s = __dadd_rn(s, __dmul_rn(E[(long long)k * Nn + r], E[(long long)k * Nn + c]));
-                    gH[idx] = s;
-                }
-            }
-            __syncthreads();
-            for (int idx = tid; idx < Nn * Nn; idx += nt) {            // HG = H G
-                const int i = idx / Nn, j = idx - i * Nn;
-                double s = 0.0;
-                for (int k = 0; k < Nn; k++) s = fma(gH[(long long)i * Nn + k], gG[(long long)k * Nn + j], s);
-                gHG[idx] = s;
-            }
-            for (int idx = tid; idx < 3 * Nn; idx += nt) {             // H Y0
-                const int i = idx / 3, d = idx - 3 * i;
-                double s = 0.0;
-                for (int k = 0; k < Nn; k++) s = fma(gH[(long long)i * Nn + k], sm.y0[3 * k + d], s);
-                sm.hy0[idx] = s;
-            }
-        }
-        __syncthreads();
-    }
-
-    cluster.sync();                                                    // (S) gather prune results
-    long long Mp = 0;
-    double sumd2 = 0.0;
-    for (int r = 0; r < C; r++) { Mp += (long long)__ldcg(gGATH + 2 * r); sumd2 += __ldcg(gGATH + 2 * r + 1); }
-    if (Mp == 0) {
-        if (rank == 0 && tid == 0) { if (iters_out) *iters_out = 0; }
-        cluster.sync();
-        return ST_EMPTY;
-    }
-    double sigma2 = sigma2_in;
-    if (sigma2 == 0) sigma2 = sumd2 / (3.0 * (double)Nn * (double)Mp);   // trackdlo.cpp:271-273
-    const bool use_vis = (n_visible != Nn) && (n_visible > 0) && (p.k_vis != 0);   // trackdlo.cpp:358
-    const bool have_priors = n_priors > 0;
-
-    int status = 0, iters = 0;
-    // optional phase timers (thread 0 of every CTA): 0 setup, 1 dmin, 2 estep, 3 wait after estep, 4 mstep, 5 wait after mstep
-    long long tprev = a.prof ? clock64() : 0;
-#define TDLO_TICK(slot)                                                                                   \
-    if (a.prof && tid == 0) { const long long tn_ = clock64(); atomicAdd(a.prof + (rank ? 8 : 0) + (slot), (unsigned long long)(tn_ - tprev)); tprev = tn_; }
-    for (int it = 0; it < p.max_iter; it++) {
-        iters = it + 1;
-        const double rscale = sqrt(0.5 / sigma2);
-        for (int j = tid; j < Nn; j += nt) sm.node4[j].w = sm.s[j] * rscale;
-        const double c_gauss = pow(2 * M_PI * sigma2, 1.5) * p.mu / (1 - p.mu);
-        double c_norm = c_gauss * (double)Nn / (double)Mp;             // trackdlo.cpp:300
-        __syncthreads();
-        TDLO_TICK(0)
-        if (use_vis) {
-            dmin_slice(sm, Xloc, n_local, Nn, gDMIN + rank * Nn);
-            cluster.sync();                                            // (V)
-            for (int j = tid; j < Nn; j += nt) {
-                double m = __ldcg(gDMIN + j);
-                for (int r = 1; r < C; r++) m = fmin(m, __ldcg(gDMIN + r * Nn + j));
-                double dm = sqrt(m);
-                if (dm <= p.tau) dm = 0.0;                              // trackdlo.cpp:291-293
-                sm.vw[j] = exp(-p.k_vis * dm);                          // trackdlo.cpp:365
-            }
-            __syncthreads();
-            if (tid == 0) { double t = 0.0; for (int j = 0; j < Nn; j++) t += sm.vw[j]; sm.red[40] = t; }
-            __syncthreads();
-            const double tot = sm.red[40];
-            for (int j = tid; j < Nn; j += nt) sm.vw[j] = sm.vw[j] / tot;   // trackdlo.cpp:372
-            c_norm = c_gauss / (double)Mp;                              // trackdlo.cpp:378
-            __syncthreads();
-            TDLO_TICK(1)
-            estep_slice<NPASS, true>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
-        } else {
-            estep_slice<NPASS, false>(sm, Xloc, n_local, Nn, sigma2, c_norm, rscale, gPART + rank * (4 * Nn + 4));
-        }
-        TDLO_TICK(2)
-        cluster.sync();                                                // (1) partial sums visible
-        TDLO_TICK(3)
-
-        if (rank == 0) {
-            // ---- gather partials in rank order
-            for (int i = tid; i < 4 * Nn; i += nt) {
-                double v = 0.0;
-                for (int r = 0; r < C; r++) v += __ldcg(gPART + r * (4 * Nn + 4) + i);
-                const int m = i >> 2, k = i & 3;
-                if (k == 0) sm.p1[m] = v; else sm.px[3 * m + k - 1] = v;
-            }
-            double sxx = 0.0;
-            for (int r = 0; r < C; r++) sxx += __ldcg(gPART + r * (4 * Nn + 4) + 4 * Nn);
-            __syncthreads();
-            // ---- assemble [A | B] (trackdlo.cpp:392-413)
-            const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
-            // Without LLE, A = D G + ls I with D = diag(P1 + alpha J) is similar to the SPD matrix
-            // D^1/2 G D^1/2 + ls I (G is a Matern-3/2 kernel of the arc length): solve that one without
-            // pivoting, (D^1/2 G D^1/2 + ls I) Z = D^-1/2 B, W = D^1/2 Z.  Rows with D_i = 0 have B_i = 0 and give
-            // W_i = 0 in both forms.  Same conditioning as A.
-            const bool spd = !p.include_lle && ab_in_smem && Nn <= 64 && nt >= 64;
-            if (spd) {
-                for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
-                __syncthreads();
-            }
-            for (int idx = tid; idx < Nn * Nn; idx += nt) {
-                const int i = idx / Nn, j = idx - i * Nn;
-                const double g = gG[idx];
-                double v;
-                if (spd) v = sm.tnew[i] * g * sm.tnew[j] + (i == j ? ls : 0.0);
-                else {
-                    v = sm.p1[i] * g + (i == j ? ls : 0.0);
-                    if (p.include_lle) v += sg * gHG[idx];
-                    if (have_priors) v += p.alpha * sm.jd[i] * g;
-                }
-                AB[(long long)i * ld + j] = v;
-            }
-            for (int idx = tid; idx < 3 * Nn; idx += nt) {
-                const int i = idx / 3, d = idx - 3 * i;
-                double v = sm.px[idx] - sm.p1[i] * sm.y0[idx];
-                if (p.include_lle) v -= sg * sm.hy0[idx];
-                if (have_priors) v += p.alpha * (sm.yext[idx] - sm.y0[idx]);
-                if (spd) { const double sd = sm.tnew[i]; v = sd > 0.0 ? v / sd : 0.0; }
-                AB[(long long)i * ld + Nn + d] = v;
-            }
-            __syncthreads();
-            TDLO_TICK(4)
-            int sing;
-            if (ab_in_smem && Nn <= 64 && nt >= 64) {
-                double sdreg[3];
-                if (spd) for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sdreg[t] = sm.tnew[i / 3];   // tnew is reused below
-                sing = gj_solve_small(sm.ptile, Nn, ld, sm.gjbuf, sm.prow, sm.wsol, !spd, a.prof);
-                if (spd) {
-                    for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sm.wsol[i] *= sdreg[t];
-                    __syncthreads();
-                }
-            } else sing = gj_solve(AB, Nn, ld, sm.prow, sm.used, sm.red + 41, sm.wsol);
-            if (sing) status |= ST_SINGULAR;
-            TDLO_TICK(6)
-            // ---- T = Y0 + G W (trackdlo.cpp:417)
-            for (int i = warp; i < Nn; i += nw) {
-                double ax = 0.0, ay = 0.0, az = 0.0;
-                for (int k = lane; k < Nn; k += 32) {
-                    const double g = gG[(long long)i * Nn + k];
-                    ax = fma(g, sm.wsol[3 * k], ax); ay = fma(g, sm.wsol[3 * k + 1], ay); az = fma(g, sm.wsol[3 * k + 2], az);
-                }
-                ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-                if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
-            }
-            __syncthreads();
-            // ---- sigma2 update and convergence test (trackdlo.cpp:418-431)
-            if (warp == 0) {
-                double np = 0.0, trPXT = 0.0, trTPT = 0.0, moved = 0.0;
-                for (int m = lane; m < Nn; m += 32) {
-                    const double tx = sm.tnew[3 * m], ty = sm.tnew[3 * m + 1], tz = sm.tnew[3 * m + 2];
-                    const double p1 = sm.p1[m];
-                    np += p1;
-                    trPXT += sm.px[3 * m] * tx + sm.px[3 * m + 1] * ty + sm.px[3 * m + 2] * tz;
-                    trTPT += p1 * (tx * tx + ty * ty + tz * tz);
-                    const double4 yc = sm.node4[m];
-                    moved += sqrt(dist2(yc.x, yc.y, yc.z, tx, ty, tz));
-                }
-                np = warp_sum(np); trPXT = warp_sum(trPXT); trTPT = warp_sum(trTPT); moved = warp_sum(moved);
-                if (lane == 0) {
-                    const double s2new = (sxx - 2 * trPXT + trTPT) / (np * 3);
-                    const bool done = (moved / Nn) < p.tol;
-                    int fin = 0;
-                    if (done) fin = 1;
-                    else if (it == p.max_iter - 1) { fin = 1; status |= ST_NOT_CONVERGED; }
-                    __stcg(gSTATE + 3 * Nn, s2new);
-                    __stcg(gSTATE + 3 * Nn + 1, (double)fin);
-                    __stcg(gSTATE + 3 * Nn + 2, (double)status);
-                }
-            }
-            for (int i = tid; i < 3 * Nn; i += nt) __stcg(gSTATE + i, sm.tnew[i]);
-        }
-        TDLO_TICK(7)
-        cluster.sync();                                                // (2) new state visible
-        TDLO_TICK(5)
-        for (int j = tid; j < Nn; j += nt) {
-            const double s = sm.node4[j].w;
-            sm.node4[j] = make_double4(__ldcg(gSTATE + 3 * j), __ldcg(gSTATE + 3 * j + 1), __ldcg(gSTATE + 3 * j + 2), s);
-        }
-        sigma2 = __ldcg(gSTATE + 3 * Nn);
-        const int fin = (int)__ldcg(gSTATE + 3 * Nn + 1);
-        status = (int)__ldcg(gSTATE + 3 * Nn + 2);
-        __syncthreads();
-        if (fin) break;
-    }
-
-#undef TDLO_TICK
-    // ---- results (rank 0)
-    if (rank == 0) {
-        for (int j = tid; j < Nn; j += nt) {
-            const double4 q = sm.node4[j];
-            Yio[3 * j] = q.x; Yio[3 * j + 1] = q.y; Yio[3 * j + 2] = q.z;
-        }
-        if (Wout && p.max_iter > 0) for (int i = tid; i < 3 * Nn; i += nt) Wout[i] = sm.wsol[i];
-        if (tid == 0) {
-            if (sigma2_out) *sigma2_out = sigma2;
-            if (iters_out) *iters_out = iters;
-        }
-    }
-    // make Yio visible to the whole cluster (tracking mode reads it back) and protect scratch reuse
-    __threadfence();
-    cluster.sync();
-    return status;
-}
-
-// ------------------------------------------------------------------------------------------
-// The persistent kernel.
-// ------------------------------------------------------------------------------------------
-template <int NPASS, int MINB>
-__global__ void __launch_bounds__(kMaxThreads, MINB) tdlo_em_kernel(const KArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int rank = (int)cluster.block_rank();
-    const int C = (int)cluster.num_blocks();
-    const int cluster_id = blockIdx.x / C;
-
-    const SmemL& L = a.L;
-    Smem sm;
-    sm.tab = reinterpret_cast<double*>(smem_raw + L.tab);
-    sm.node4 = reinterpret_cast<double4*>(smem_raw + L.node4);
-    sm.wbuf = reinterpret_cast<double4*>(smem_raw + L.wbuf);
-    sm.y0 = reinterpret_cast<double*>(smem_raw + L.y0);
-    sm.s = reinterpret_cast<double*>(smem_raw + L.s);
-    sm.vw = reinterpret_cast<double*>(smem_raw + L.vw);
-    sm.yext = reinterpret_cast<double*>(smem_raw + L.yext);
-    sm.jd = reinterpret_cast<double*>(smem_raw + L.jd);
-    sm.hy0 = reinterpret_cast<double*>(smem_raw + L.hy0);
-    sm.p1 = reinterpret_cast<double*>(smem_raw + L.p1);
-    sm.px = reinterpret_cast<double*>(smem_raw + L.px);
-    sm.wsol = reinterpret_cast<double*>(smem_raw + L.wsol);
-    sm.tnew = reinterpret_cast<double*>(smem_raw + L.tnew);
-    sm.pacc = reinterpret_cast<double*>(smem_raw + L.pacc);
-    sm.red = reinterpret_cast<double*>(smem_raw + L.red);
-    sm.gjbuf = reinterpret_cast<double*>(smem_raw + L.gjbuf);
-    sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
-    sm.used = reinterpret_cast<int*>(smem_raw + L.used);
-    sm.ptile = reinterpret_cast<double*>(smem_raw + L.ptile);
-
-    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];
-    __syncthreads();
-
-    double* cscr = a.scratch + (long long)cluster_id * a.scratch_stride;
-    const Scr sc = scr_layout(a.scr_nodes);
-    int* ctl = reinterpret_cast<int*>(cscr + sc.CTL);
-
-    for (;;) {
-        if (rank == 0 && tid == 0) __stcg(ctl, atomicAdd(a.queue, 1));
-        cluster.sync();
-        const int f = __ldcg(ctl);
-        cluster.sync();
-        if (f >= a.n_frames) break;
-
-        const long long x0 = a.x_off[f], m0 = a.x_off[f + 1] - x0;
-        const double* Xraw = a.X + x0 * 3;
-        double* Xc = a.Xc + x0 * 3;
-
-        if (a.mode == 0) {
-            const int Nn = a.n_nodes ? a.n_nodes[f] : a.node_stride;
-            const long long ys = (long long)f * a.node_stride;
-            const int st = cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, a.Y + ys * 3, Nn, a.sigma2[f], a.sigma2 + f, a.p0,
-                                        a.priors ? a.priors + ys * 4 : nullptr,
-                                        (a.priors && a.n_priors) ? a.n_priors[f] : 0,
-                                        a.n_visible ? a.n_visible[f] : 0,
-                                        a.H ? a.H + ys * a.node_stride : nullptr, a.node_stride,
-                                        a.W ? a.W + ys * 3 : nullptr, a.iters ? a.iters + f : nullptr);
-            if (rank == 0 && tid == 0 && a.status) a.status[f] = st;
-        } else {
-            // ---------------- tracking_step (trackdlo.cpp:900-999)
-            const int Nn = a.node_stride;
-            double* Yf = a.Y + (long long)f * Nn * 3;
-            const int* vis = a.vis + a.vis_off[f];
-            const int nvis = (int)(a.vis_off[f + 1] - a.vis_off[f]);
-            const int* ext = a.ext + a.ext_off[f];
-            const int V = (int)(a.ext_off[f + 1] - a.ext_off[f]);
-            double* guide = a.guide_out ? a.guide_out + (long long)f * Nn * 3 : cscr + sc.GUIDE;
-            double* pri = a.priors_out ? a.priors_out + (long long)f * 2 * Nn * 4 : cscr + sc.PRI;
-            const double* geo = a.rest + (long long)f * Nn;
-            int st = 0;
-            // guide nodes (trackdlo.cpp:913-921)
-            if (rank == 0) {
-                for (int i = tid; i < 3 * V; i += nt) {
-                    const int r = i / 3, d = i - 3 * r;
-                    guide[i] = (V != Nn) ? Yf[ext[r] * 3 + d] : Yf[i];
-                }
-                __threadfence();
-            }
-            cluster.sync();
-            // pre-processing registration (trackdlo.cpp:925-927); sigma2 copy is discarded
-            const int st_pre = cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, guide, V, a.sigma2[f], nullptr, a.p0,
-                                            nullptr, 0, 0, a.H ? a.H + (long long)f * Nn * Nn : nullptr, Nn,
-                                            nullptr, a.iters ? a.iters + 2 * f : nullptr);
-            if (st_pre & ST_NOT_CONVERGED) st |= ST_PRE_NOT_CONVERGED;
-            st |= st_pre & ~ST_NOT_CONVERGED;
-            int* ictl = ctl + 2;
-            if (rank == 0 && tid == 0) {
-                int err = 0, state = 0, np = 0;
-                double* trv = cscr + sc.TRV;
-                if (st_pre & (ST_TOO_FEW_NODES | ST_EMPTY)) {
-                    state = -1;
-                } else if (V == Nn) {
-                    state = 0;
-                    double* v1 = trv;
-                    double* v2 = trv + (Nn + 2) * 4;
-                    const int n1 = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, v1, &err);
-                    const int n2 = traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, v2, &err);
-                    // v2 is emitted tail -> head; the reference reverses it (trackdlo.cpp:942): v2r[j] = v2[n2-1-j]
-                    for (int i = 0; i < Nn; i++) {
-                        const int j2 = i - (Nn - n2);
-                        const double* first2 = v2 + (n2 - 1) * 4;
-                        if (i < first2[0] && i < n1) { for (int t = 0; t < 4; t++) pri[np * 4 + t] = v1[i * 4 + t]; np++; }
-                        else if (i > v1[(n1 - 1) * 4] && j2 >= 0 && j2 < n2) {
-                            const double* s2 = v2 + (n2 - 1 - j2) * 4;
-                            for (int t = 0; t < 4; t++) pri[np * 4 + t] = s2[t];
-                            np++;
-                        } else if (i < n1 && j2 >= 0 && j2 < n2) {
-                            const double* s2 = v2 + (n2 - 1 - j2) * 4;
-                            for (int t = 0; t < 4; t++) pri[np * 4 + t] = (v1[i * 4 + t] + s2[t]) / 2.0;
-                            np++;
-                        } else err |= 4;
-                    }
-                } else if (ext[0] == 0 && ext[V - 1] == Nn - 1) {
-                    state = 1;
-                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, pri, &err);
-                    np += traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, pri + np * 4, &err);
-                } else if (ext[0] == 0) {
-                    state = 2;
-                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 0, -1, pri, &err);
-                } else if (ext[V - 1] == Nn - 1) {
-                    state = 3;
-                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 1, -1, pri, &err);
-                } else {
-                    state = 4;
-                    int align = -1;
-                    double moved = 999999;
-                    for (int i = 0; i < nvis; i++) {
-                        if (i >= V) { err |= 8; break; }
-                        const double dd = vdist(ld3(Yf, vis[i]), ld3(guide, i));
-                        if (dd < moved) { moved = dd; align = i; }
-                    }
-                    np = traverse_euclidean(geo, Nn, guide, V, ext, V, 2, align, pri, &err);
-                }
-                if (a.state_out) a.state_out[f] = state;
-                if (a.n_priors_out) a.n_priors_out[f] = np;
-                __stcg(ictl, np);
-                __stcg(ictl + 1, err);
-                __threadfence();
-            }
-            cluster.sync();
-            const int np = __ldcg(ictl);
-            if (__ldcg(ictl + 1)) st |= ST_TRAVERSE_UB;
-            if (!(st & (ST_TOO_FEW_NODES | ST_EMPTY))) {
-                // main registration (trackdlo.cpp:998)
-                st |= cpd_run<NPASS>(cluster, sm, a, cscr, Xraw, m0, Xc, Yf, Nn, a.sigma2[f], a.sigma2 + f, a.p1,
-                                   pri, np, V, nullptr, Nn, a.W ? a.W + (long long)f * Nn * 3 : nullptr,
-                                   a.iters ? a.iters + 2 * f + 1 : nullptr);
-            }
-            if (rank == 0 && tid == 0 && a.status) a.status[f] = st;
-        }
-    }
 }
 
 }  // namespace tdlo

@@ -15,7 +15,7 @@
 // Everything is fp64 (the reference is MatrixXd end to end).
 #pragma once
 
-#include "tdlo_kernels.cuh"
+#include "tdlo_common.cuh"
 
 namespace tdlo {
 
@@ -105,17 +105,18 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
 }
 
 struct TqArgs {
-    KArgs k;                         // frame data + parameters (same meaning as in the cluster engine)
+    KArgs k;                         // frame data + parameters
     int chunk;                       // raw points per chunk task
     int inflight;                    // frames started at launch; one more starts whenever a frame completes
     double zcut;                     // Gaussian truncation: entries exp(-z), z > zcut, are skipped (745.2 = exact zeros only)
-    unsigned long long* qctl;        // [0] head ticket, [1] tail, [2] next frame (int), [3] frames done (int)
+    unsigned long long* qctl;        // [0] head ticket, [1] tail, [2] ints {next frame, start tickets}, [3] ints {frames done, abort flag}
     unsigned long long* qslots; unsigned qmask;
     double* fscratch; long long fstride;   // per-frame scratch
     double* part; double* dminp; double* gath; int* nkept;   // per global chunk
     double4* tsph;                   // per tile of 32 sorted points: bounding sphere {centre = first point, radius}; [chunk id][chunk/32]
     int part_stride;                 // doubles per chunk in `part`
     const int* ready; int ready_frames;   // optional: frames [0, *ready * ready_frames) have their points uploaded (pipelined H2D)
+    unsigned long long watchdog_ns;  // a CTA that waits longer than this for a task / an upload aborts the launch (0 = never)
     TqSmemL L;
 };
 
@@ -160,7 +161,7 @@ __device__ __forceinline__ unsigned long long tq_word(unsigned long long ticket,
 }
 // Publishes n tasks (type, frame, chunk 0..n-1).  Called by all threads of the CTA after the data the tasks
 // read has been written; contains the fences and a barrier.
-__device__ void tq_push(const TqArgs& a, TqSm& sm, int type, int frame, int n) {
+static __device__ void tq_push(const TqArgs& a, TqSm& sm, int type, int frame, int n) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = atomicAdd(a.qctl + 1, (unsigned long long)n);
@@ -172,16 +173,38 @@ __device__ void tq_push(const TqArgs& a, TqSm& sm, int type, int frame, int n) {
     }
     __syncthreads();
 }
+// Watchdog for the spin loops: a waiter polls it every 1024 spins.  Returns true when the launch is to be abandoned --
+// because another CTA said so, or because this wait has exceeded a.watchdog_ns (a task lost, an upload that never
+// came): sets the abort flag, which the host turns into TDLO_ERR_CUDA instead of a hung caller.
+__device__ __forceinline__ unsigned long long tq_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool tq_watchdog(const TqArgs& a, unsigned long long& t0) {
+    int* abort_flag = reinterpret_cast<int*>(a.qctl + 3) + 1;
+    if (ld_acquire_s32(abort_flag)) return true;
+    if (!a.watchdog_ns) return false;
+    const unsigned long long now = tq_now_ns();
+    if (!t0) { t0 = now; return false; }
+    if (now - t0 > a.watchdog_ns) { atomicExch(abort_flag, 1); return true; }
+    return false;
+}
 // Takes the next ticket and waits for its task.  Returns the slot word (uniform over the CTA).
-__device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
+static __device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned long long t = atomicAdd(a.qctl, 1ull);
         const unsigned long long lap = (t / ((unsigned long long)a.qmask + 1ull) + 1ull) & 0xffffffull;
         const unsigned long long* slot = a.qslots + (t & a.qmask);
         unsigned long long v = ld_acquire_u64(slot);
-        unsigned ns = 64;
-        while ((v >> 40) != lap) { __nanosleep(ns); if (ns < 512) ns <<= 1; v = ld_acquire_u64(slot); }
+        unsigned ns = 64, spins = 0;
+        unsigned long long t0 = 0;
+        while ((v >> 40) != lap) {
+            __nanosleep(ns); if (ns < 512) ns <<= 1;
+            v = ld_acquire_u64(slot);
+            if ((++spins & 1023u) == 0 && tq_watchdog(a, t0)) { v = (lap << 40) | ((unsigned long long)TK_EXIT << 37); break; }
+        }
         *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = v;
     }
     __syncthreads();
@@ -191,7 +214,7 @@ __device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
 }
 // A chunk task (or the set-up) of frame f is complete.  Returns true (uniform) for the LAST arriver of the
 // wave, which then owns the frame until it publishes the next wave.
-__device__ bool tq_arrive(TqSm& sm, int* ctl) {
+static __device__ bool tq_arrive(TqSm& sm, int* ctl) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -226,7 +249,7 @@ __device__ __forceinline__ double warp_min_pos_ub(double v) {
 // Bounding spheres of the chunk's tiles (32 consecutive sorted points): centre = the tile's first point,
 // radius = an upper bound of the largest distance to it.  The points do not move during a registration,
 // so this is done once per call, right after the prune/sort; the E-step uses it to prune its node searches.
-__device__ void tq_tile_spheres(const double* __restrict__ Xc, int n_local, double4* __restrict__ sph) {
+static __device__ void tq_tile_spheres(const double* __restrict__ Xc, int n_local, double4* __restrict__ sph) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int base = warp * 32; base < n_local; base += nw * 32) {
         const int n = base + lane < n_local ? base + lane : base;
@@ -245,16 +268,19 @@ __device__ __forceinline__ double sqrt_ub(double x) {
 }
 
 // ------------------------------------------------------------------------------------------
-// E-step over one chunk (trackdlo.cpp:278-389); see estep_slice in tdlo_kernels.cuh for the maths.
-// Differences: (1) the P tile of a warp has a fixed 32 node rows -- the node WINDOW of the warp's 32 points
-// (everything outside is exactly 0 / below the truncation) is processed in blocks of 32 rows, recomputing
-// the exponentials of later blocks (only the first, wide iterations of a registration need more than one);
-// (2) phase B splits the lanes into (node row, point group) so that a narrow window still uses all 32
-// lanes; (3) window and search bounds use single-REDUX conservative bounds.
+// Fused E-step over one chunk (trackdlo.cpp:278-389): distances -> arg-max node -> geodesic distances -> P ->
+// (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.  Every WARP is autonomous: it takes 32 sorted
+// points at a time (lane = point), writes their P columns into its private shared-memory tile (phase A), then
+// accumulates P1 / PX of the tile's node rows in registers (phase B).  Only __syncwarp inside the tile loop.
+// (1) The P tile of a warp has a fixed 32 node rows -- the node WINDOW of the warp's 32 points (everything outside
+// is exactly 0 / below the truncation) is processed in blocks of 32 rows, recomputing the exponentials of later
+// blocks (only the first, wide iterations of a registration need more than one); (2) phase B splits the lanes into
+// (node row, point group) so that a narrow window still uses all 32 lanes; (3) window and search bounds use
+// single-REDUX conservative bounds.
 // part_out: [Nn][4] = {P1, PX.x, PX.y, PX.z}, then [4*Nn] = sum_n Pt1_n |x_n|^2.
 // ------------------------------------------------------------------------------------------
 template <int NPASS, bool VIS, int NW>
-__device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, const double4* __restrict__ sph, int n_local, int Nn,
+static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, const double4* __restrict__ sph, int n_local, int Nn,
                                double sigma2, double c_norm, double rscale, double zcut, double* part_out,
                                unsigned long long* prof) {
     constexpr int RS = TQ_RS;
@@ -302,8 +328,9 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
             }
         }
 
-        // ---- nearest node: exact bounding-sphere pruning of the scan range (see estep_slice); the sphere of the
-        // tile {centre c, radius rho} comes from the prune pass
+        // ---- nearest node: exact bounding-sphere pruning of the scan range: a node farther from the tile's sphere
+        // {centre c, radius rho} (from the prune pass) than the nearest centre distance + 2 rho cannot be nearest to any
+        // of the 32 points
         int ja, jb;
         {
             double dc[NPASS];
@@ -511,7 +538,7 @@ __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, co
 // sphere already exceeds the best distance found so far cannot improve it.
 // ------------------------------------------------------------------------------------------
 template <int NPASS>
-__device__ void tq_dmin_chunk(const TqSm& sm, const double* __restrict__ Xc, int n_local, int Nn, double* dmin_out) {
+static __device__ void tq_dmin_chunk(const TqSm& sm, const double* __restrict__ Xc, int n_local, int Nn, double* dmin_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const double4* __restrict__ nd = sm.node4;
     double best[NPASS];                                   // lane owns nodes lane + 32 ps
@@ -608,7 +635,7 @@ __device__ __forceinline__ double* tq_pri(const TqArgs& a, const TqFrame& fr) {
 // start_call: set-up of one cpd_lle call (trackdlo.cpp:197-260) + publication of its PRUNE wave.
 // Returns the next action for this CTA.
 // ------------------------------------------------------------------------------------------
-__device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int stage) {
+static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int stage) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const KArgs& k = a.k;
     const CpdP& p = tq_params(a, stage);
@@ -617,10 +644,46 @@ __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int s
     const TqScr& sc = fr.sc;
     if (a.ready && stage == 0) {           // points of this frame still in flight on the copy stream? (host-buffer entry points)
         if (tid == 0) {
-            unsigned ns = 256;
-            while ((long long)ld_acquire_s32(a.ready) * a.ready_frames <= f) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+            unsigned ns = 256, spins = 0;
+            unsigned long long t0 = 0;
+            while ((long long)ld_acquire_s32(a.ready) * a.ready_frames <= f) {
+                __nanosleep(ns); if (ns < 4096) ns <<= 1;
+                if ((++spins & 1023u) == 0 && tq_watchdog(a, t0)) break;
+            }
         }
         __syncthreads();
+    }
+    // ---- the caller's arrays are device memory nobody has looked at yet (device-pointer entry points): refuse a frame
+    // whose offsets / counts / indices would make this kernel write outside the context's workspace
+    if (stage == 0) {
+        if (tid == 0) {
+            bool bad = false;
+            const long long x0 = k.x_off[f], x1 = k.x_off[f + 1];
+            if (x0 < 0 || x1 < x0 || x1 > k.max_points) bad = true;
+            if (k.mode == 0) {
+                const int nn = k.n_nodes ? k.n_nodes[f] : k.node_stride;
+                if (nn < 0 || nn > k.node_stride) bad = true;
+            } else {
+                const int N = k.node_stride;
+                const long long V = k.ext_off[f + 1] - k.ext_off[f], nv = k.vis_off[f + 1] - k.vis_off[f];
+                if (V < 0 || V > N || nv < 0 || nv > N) bad = true;
+                else {
+                    const int* ext = k.ext + k.ext_off[f];
+                    const int* vis = k.vis + k.vis_off[f];
+                    for (int i = 0; i < (int)V; i++) if (ext[i] < 0 || ext[i] >= N || (i > 0 && ext[i] <= ext[i - 1])) bad = true;
+                    for (int i = 0; i < (int)nv; i++) if (vis[i] < 0 || vis[i] >= N) bad = true;
+                }
+            }
+            sm.bcast[1] = bad;
+            if (bad) {
+                fr.ctl[FC_STAGE] = 0; fr.ctl[FC_ITER] = 0; fr.ctl[FC_NN] = 0; fr.ctl[FC_NCHUNK] = 0; fr.ctl[FC_NPRI] = 0;
+                fr.ctl[FC_STATUS] = ST_BAD_INPUT; fr.ctl[FC_STPRE] = 0;
+            }
+        }
+        __syncthreads();
+        const bool bad = sm.bcast[1] != 0;
+        __syncthreads();
+        if (bad) return A_FINISH_CALL;
     }
     int Nn, n_priors = 0, n_visible = 0;
     const double* priors = nullptr;
@@ -629,8 +692,9 @@ __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int s
     if (k.mode == 0) {
         Nn = k.n_nodes ? k.n_nodes[f] : k.node_stride;
         const long long ys = (long long)f * k.node_stride;
-        priors = k.priors ? k.priors + ys * 4 : nullptr;
+        priors = k.priors ? k.priors + (long long)f * k.priors_stride * 4 : nullptr;
         n_priors = (k.priors && k.n_priors) ? k.n_priors[f] : 0;
+        n_priors = n_priors < 0 ? 0 : (n_priors > k.priors_stride ? k.priors_stride : n_priors);    // never past the frame's rows
         n_visible = k.n_visible ? k.n_visible[f] : 0;
         Hext = k.H ? k.H + ys * k.node_stride : nullptr;
     } else {
@@ -751,7 +815,7 @@ __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int s
 // ------------------------------------------------------------------------------------------
 // after_prune: gather the kept counts, sigma2 init (trackdlo.cpp:263-273)
 // ------------------------------------------------------------------------------------------
-__device__ int tq_after_prune(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+static __device__ int tq_after_prune(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     const int tid = threadIdx.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const CpdP& p = tq_params(a, stage);
@@ -776,7 +840,7 @@ __device__ int tq_after_prune(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
 // ------------------------------------------------------------------------------------------
 // begin_iter: per-iteration header (scaled arc lengths, outlier constant) and the next wave
 // ------------------------------------------------------------------------------------------
-__device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+static __device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
@@ -799,7 +863,7 @@ __device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
 }
 
 // after_dmin: visibility weights (trackdlo.cpp:291-293, 358-375), then the E-step wave
-__device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+static __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const CpdP& p = tq_params(a, stage);
@@ -825,7 +889,7 @@ __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
 // ------------------------------------------------------------------------------------------
 // m_step (trackdlo.cpp:392-438): run by the CTA that completed the frame's E-step wave.
 // ------------------------------------------------------------------------------------------
-__device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long& tprev) {
+static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long& tprev) {
     unsigned long long* prof = a.k.prof;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
@@ -917,11 +981,14 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
     __syncthreads();
     const double sxx = sm.red[42];
 
-    // ---- assemble [A | B] (trackdlo.cpp:392-413); SPD form without LLE (see cpd_run)
+    // ---- assemble [A | B] (trackdlo.cpp:392-413).  Without LLE, A = D'G + cI (D' = diag(P1 + alpha J), c = lambda sigma2)
+    // is similar to the SPD matrix D'^1/2 G D'^1/2 + cI: solve that for Z = D'^-1/2 W (rows with D' = 0 have B = 0)
     const double ls = p.lambda * sigma2, sg = sigma2 * p.gamma;
     const bool small = ab_in_smem && Nn <= 64;
-    const int chol_nb = (!small && !p.include_lle) ? ((long long)Nn * 20 + Nn + 64 <= (long long)a.L.chol_doubles ? 16 : ((long long)Nn * 12 + Nn + 64 <= (long long)a.L.chol_doubles ? 8 : 0)) : 0;
-    const bool spd = !p.include_lle && (small || chol_nb > 0);
+    const int chol_nb = (!small && !p.include_lle && !(have_priors && p.alpha < 0.0)) ? ((long long)Nn * 20 + Nn + 64 <= (long long)a.L.chol_doubles ? 16 : ((long long)Nn * 12 + Nn + 64 <= (long long)a.L.chol_doubles ? 8 : 0)) : 0;
+    // (a negative alpha would put a negative number under the square root: the reference's generic solve accepts it, so
+    // does the pivoted path here)
+    const bool spd = !p.include_lle && !(have_priors && p.alpha < 0.0) && (small || chol_nb > 0);
     if (spd) {
         for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
         __syncthreads();
@@ -1032,14 +1099,14 @@ __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, long long&
 // finish_call: results of one cpd_lle call; in tracking mode the glue between the pre-processing and the
 // main registration (trackdlo.cpp:929-998).
 // ------------------------------------------------------------------------------------------
-__device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int& next_stage) {
+static __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int& next_stage) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const KArgs& k = a.k;
     const int f = fr.f;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN);
     const int status = __ldcg(fr.ctl + FC_STATUS), iters = __ldcg(fr.ctl + FC_ITER);
     const CpdP& p = tq_params(a, stage);
-    const bool ran = !(status & (ST_TOO_FEW_NODES | ST_EMPTY));
+    const bool ran = !(status & (ST_TOO_FEW_NODES | ST_EMPTY | ST_BAD_INPUT));
     double* Yio = tq_yio(a, fr, stage);
     const double* gN4 = fr.scr + fr.sc.NODE4;
     if (ran) for (int i = tid; i < 3 * Nn; i += nt) Yio[i] = __ldcg(gN4 + 4 * (i / 3) + (i % 3));
@@ -1054,7 +1121,7 @@ __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int&
     }
     const int N = k.node_stride;
     if (stage == 0) {
-        if (tid == 0 && k.iters) k.iters[2 * f] = ran ? iters : 0;
+        if (tid == 0) { if (k.iters) k.iters[2 * f] = ran ? iters : 0; fr.ctl[FC_ITPRE] = ran ? iters : 0; }
         __threadfence();
         __syncthreads();
         if (tid == 0) {
@@ -1128,6 +1195,12 @@ __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int&
         __syncthreads();
         if (go) { next_stage = 1; return A_START_CALL; }
         if (tid == 0) { if (k.status) k.status[f] = __ldcg(fr.ctl + FC_STPRE); if (k.iters) k.iters[2 * f + 1] = 0; }
+        if (k.packed_out) {                 // frame not run: nodes unchanged
+            double* rec = k.packed_out + (long long)f * (3 * N + 4);
+            const double* Yf = k.Y + (long long)f * N * 3;
+            for (int i = tid; i < 3 * N; i += nt) rec[i] = Yf[i];
+            if (tid == 0) { rec[3 * N] = k.sigma2[f]; rec[3 * N + 1] = 0.0; rec[3 * N + 2] = 0.0; rec[3 * N + 3] = (double)__ldcg(fr.ctl + FC_STPRE); }
+        }
         return A_FRAME_DONE;
     }
     // stage 1: main registration done
@@ -1136,6 +1209,16 @@ __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int&
         if (ran) k.sigma2[f] = __ldcg(fr.scal + FS_SIGMA2);
         if (k.iters) k.iters[2 * f + 1] = ran ? iters : 0;
         if (k.status) k.status[f] = status | __ldcg(fr.ctl + FC_STPRE);
+    }
+    if (k.packed_out) {                     // one contiguous record per frame: what a multi-GPU caller all-gathers
+        double* rec = k.packed_out + (long long)f * (3 * N + 4);
+        const double* Yf = k.Y + (long long)f * N * 3;
+        for (int i = tid; i < 3 * N; i += nt) rec[i] = ran ? __ldcg(gN4 + 4 * (i / 3) + (i % 3)) : Yf[i];
+        if (tid == 0) {
+            rec[3 * N] = ran ? __ldcg(fr.scal + FS_SIGMA2) : k.sigma2[f];
+            rec[3 * N + 1] = (double)__ldcg(fr.ctl + FC_ITPRE); rec[3 * N + 2] = ran ? (double)iters : 0.0;
+            rec[3 * N + 3] = (double)(status | __ldcg(fr.ctl + FC_STPRE));
+        }
     }
     return A_FRAME_DONE;
 }
@@ -1173,14 +1256,23 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
     sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
     sm.used = reinterpret_cast<int*>(smem_raw + L.used);
     sm.ab = reinterpret_cast<double*>(smem_raw + L.ab);
-    for (int i = tid; i < 64; i += nt) sm.tab[i] = c_exp_tab[i];          // 2^(i/64)
+    for (int i = tid; i < 64; i += nt) sm.tab[i] = a.k.exp_tab[i];          // 2^(i/64)
     __syncthreads();
 
-    int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [2] frames done
+    int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [1] start tickets, [2] frames done, [3] abort flag
     unsigned long long* prof = a.k.prof;
     long long tprev = prof ? clock64() : 0;
     int action = A_NONE, af = 0, astage = 0;
-    if ((int)blockIdx.x < a.inflight && (int)blockIdx.x < a.k.n_frames) { action = A_START_CALL; af = blockIdx.x; astage = 0; }
+    // The first `inflight` CTAs to get here each CLAIM a frame from the shared counter (not "frame = blockIdx.x"): a CTA
+    // that becomes resident late (MPS, a debugger, a shared GPU) can then never restart a frame somebody else already ran.
+    if (tid == 0) {
+        int nf = -1;
+        if (atomicAdd(qi + 1, 1) < a.inflight) { nf = atomicAdd(qi, 1); if (nf >= a.k.n_frames) nf = -1; }
+        sm.bcast[1] = nf;
+    }
+    __syncthreads();
+    { const int nf = sm.bcast[1]; if (nf >= 0) { action = A_START_CALL; af = nf; astage = 0; } }
+    __syncthreads();
 
     for (;;) {
         // ---- continuations owned by this CTA
@@ -1237,7 +1329,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
         }
         __syncthreads();
         if (type == TK_PRUNE) {
-            Smem os;                                              // view for prune_sort_slice (cluster engine helper)
+            Smem os;
             os.node4 = sm.node4; os.ptile = sm.ptile; os.red = sm.red;
             double sum_local;
             const int kept = prune_sort_slice(os, fr.Xraw, r0, r1, fr.Xc, a.k.bkt + (fr.Xraw - a.k.X) / 3, Nn,

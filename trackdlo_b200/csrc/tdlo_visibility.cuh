@@ -2,13 +2,15 @@
 //   shortest node-to-point distances           trackdlo/src/trackdlo_node.cpp:254-277
 //   visible_nodes (sorted) / visible_nodes_extended (d_vis rule)   trackdlo_node.cpp:346-360
 // The self-occlusion raster (:280-343) is out of scope: every node counts as not self-occluded.
-// Three small kernels: (1) per-node min squared distance, point slices x frames, combined with atomicMin on the
-// bit pattern (non-negative doubles order like their bits); (2) per frame: sqrt, threshold, the two lists at a
-// fixed stride + their lengths; (3) one CTA: exclusive scan of the lengths -> CSR offsets, compaction.  The CSR
-// outputs are exactly the visibility inputs of tdlo_tracking_step_batched_device.
+// Four small kernels, no host round trip (the device-pointer entry point is fully stream-ordered):
+// (0) one CTA: slice table = exclusive scan of ceil(Mp_f / VIS_SLICE) over the frames; (1) per-node min squared
+// distance, a fixed grid of CTAs striding over the (frame, slice) pairs, combined with atomicMin on the bit pattern
+// (non-negative doubles order like their bits); (2) per frame: sqrt, threshold, the two lists at a fixed stride +
+// their lengths; (3) one CTA: exclusive scan of the lengths -> CSR offsets, compaction.  The CSR outputs are exactly
+// the visibility inputs of tdlo_tracking_step_batched_device.
 #pragma once
 
-#include "tdlo_kernels.cuh"
+#include "tdlo_common.cuh"
 
 namespace tdlo {
 
@@ -21,38 +23,73 @@ struct VisArgs {
     int* tmp_vis; int* tmp_ext;       // [F][N] workspace
     int* counts;                      // [F][2] workspace
     double* dmin_out;                 // optional [F][N]
+    long long* slice_start;           // [F+1] workspace: first global slice of every frame
+    long long max_points;             // capacity: frames whose offsets exceed it contribute no slices
     int* vis; long long* vis_off; int* ext; long long* ext_off;
 };
 
 constexpr int VIS_SLICE = 4096;       // points per CTA of kernel 1
 
-__global__ void __launch_bounds__(256) tdlo_vis_dmin_kernel(const VisArgs a, const int* slice_frame, const int* slice_first) {
-    __shared__ double4 nd[kMaxNodes];
-    const int f = slice_frame[blockIdx.x];
-    const long long x0 = a.x_off[f], m0 = a.x_off[f + 1] - x0;
-    const long long p0 = (long long)slice_first[blockIdx.x] * VIS_SLICE;
-    const long long p1 = p0 + VIS_SLICE < m0 ? p0 + VIS_SLICE : m0;
-    const int N = a.n_nodes, tid = threadIdx.x, lane = tid & 31;
-    for (int j = tid; j < N; j += blockDim.x) nd[j] = make_double4(a.Y[((long long)f * N + j) * 3], a.Y[((long long)f * N + j) * 3 + 1], a.Y[((long long)f * N + j) * 3 + 2], 0.0);
+__global__ void __launch_bounds__(256) tdlo_vis_slices_kernel(const VisArgs a) {
+    __shared__ long long part[256];
+    __shared__ long long run;
+    const int tid = threadIdx.x, F = a.n_frames;
+    if (tid == 0) { run = 0; a.slice_start[0] = 0; }
     __syncthreads();
-    const double* X = a.X + x0 * 3;
-    for (long long base = p0 + (tid & ~31); base < p1; base += blockDim.x) {
-        const long long n = base + lane;
-        const bool valid = n < p1;
-        double x = 0, y = 0, z = 0;
-        if (valid) { x = __ldg(X + n * 3); y = __ldg(X + n * 3 + 1); z = __ldg(X + n * 3 + 2); }
-        for (int j = 0; j < N; j++) {
-            const double4 q = nd[j];
-            const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
-            // same operation order as the reference's (Y.row(m) - X.row(n)).norm(), no fused multiply-add
-            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (!valid) d2 = 1e300;
-            const unsigned hi = (unsigned)__double2hiint(d2);
-            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-            const unsigned lw = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
-            const unsigned ml = __reduce_min_sync(0xffffffffu, lw);
-            if (lane == 0) atomicMin(a.dmin2_bits + (long long)f * N + j, ((unsigned long long)mh << 32) | ml);
+    for (int f0 = 0; f0 < F; f0 += 256) {
+        const int f = f0 + tid;
+        long long ns = 0;
+        if (f < F) {
+            const long long x0 = a.x_off[f], x1 = a.x_off[f + 1];
+            if (x0 >= 0 && x1 >= x0 && x1 <= a.max_points) ns = (x1 - x0 + VIS_SLICE - 1) / VIS_SLICE;
         }
+        part[tid] = ns;
+        __syncthreads();
+        if (tid == 0) { long long r = run; for (int i = 0; i < 256; i++) { const long long v = part[i]; part[i] = r; r += v; } run = r; }
+        __syncthreads();
+        if (f < F) a.slice_start[f + 1] = part[tid] + ns;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) tdlo_vis_dmin_kernel(const VisArgs a) {
+    __shared__ double4 nd[kMaxNodes];
+    __shared__ int s_f;
+    const int N = a.n_nodes, tid = threadIdx.x, lane = tid & 31, F = a.n_frames;
+    const long long total = a.slice_start[F];
+    for (long long sl = blockIdx.x; sl < total; sl += gridDim.x) {
+        if (tid == 0) {                                            // frame of this slice: last f with slice_start[f] <= sl
+            int lo = 0, hi = F - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.slice_start[mid] <= sl) lo = mid; else hi = mid - 1; }
+            s_f = lo;
+        }
+        __syncthreads();
+        const int f = s_f;
+        const long long x0 = a.x_off[f], m0 = a.x_off[f + 1] - x0;
+        const long long p0 = (sl - a.slice_start[f]) * VIS_SLICE;
+        const long long p1 = p0 + VIS_SLICE < m0 ? p0 + VIS_SLICE : m0;
+        for (int j = tid; j < N; j += blockDim.x) nd[j] = make_double4(a.Y[((long long)f * N + j) * 3], a.Y[((long long)f * N + j) * 3 + 1], a.Y[((long long)f * N + j) * 3 + 2], 0.0);
+        __syncthreads();
+        const double* X = a.X + x0 * 3;
+        for (long long base = p0 + (tid & ~31); base < p1; base += blockDim.x) {
+            const long long n = base + lane;
+            const bool valid = n < p1;
+            double x = 0, y = 0, z = 0;
+            if (valid) { x = __ldg(X + n * 3); y = __ldg(X + n * 3 + 1); z = __ldg(X + n * 3 + 2); }
+            for (int j = 0; j < N; j++) {
+                const double4 q = nd[j];
+                const double dx = q.x - x, dy = q.y - y, dz = q.z - z;
+                // same operation order as the reference's (Y.row(m) - X.row(n)).norm(), no fused multiply-add
+                double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (!valid) d2 = 1e300;
+                const unsigned hi = (unsigned)__double2hiint(d2);
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned lw = (hi == mh) ? (unsigned)__double2loint(d2) : 0xffffffffu;
+                const unsigned ml = __reduce_min_sync(0xffffffffu, lw);
+                if (lane == 0) atomicMin(a.dmin2_bits + (long long)f * N + j, ((unsigned long long)mh << 32) | ml);
+            }
+        }
+        __syncthreads();
     }
 }
 

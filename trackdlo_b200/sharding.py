@@ -4,6 +4,10 @@ collective, one all-gather of the tracked node positions (+ sigma2, iters, statu
 Frames are independent problems (each carries its own X, Y, sigma2, visibility), so the EM loop
 itself never communicates; a single live sequence does not shard (frame t needs Y of t-1,
 trackdlo.cpp:998) -- that case is "replicas only".
+
+The payload of the collective is written by the persistent kernel's epilogue itself
+(tdlo_track_batch::packed_results: one contiguous record {Y, sigma2, iters_pre, iters_main, status} per frame),
+so a step is exactly two launches per rank: the registration kernel and the NCCL all-gather.
 """
 import torch
 import torch.distributed as dist
@@ -17,29 +21,28 @@ def shard_range(n_frames, rank, world):
     return lo, hi
 
 
-def all_gather_results(Y_local, sigma2_local, iters_local, status_local, n_frames):
-    """Every rank ends up with the full [F, Nn, 3] trajectory block.  Inputs are this rank's shard
-    (tensors on the rank's device, or CPU tensors under gloo).  Shards are padded to ceil(F/G)."""
-    world = dist.get_world_size()
+def record_width(n_nodes):
+    """Doubles per frame in tdlo_track_batch::packed_results."""
+    return 3 * n_nodes + 4
+
+
+def alloc_packed(n_frames, n_nodes, world, device):
+    """This rank's send buffer: ceil(F/G) records (ranks with fewer frames leave the tail zero)."""
     per = (n_frames + world - 1) // world
-    Nn = Y_local.shape[1]
-    dev = Y_local.device
+    return torch.zeros((per, record_width(n_nodes)), dtype=torch.float64, device=device)
 
-    def pad(t, shape, dtype):
-        out = torch.zeros(shape, dtype=dtype, device=dev)
-        out[: t.shape[0]] = t
-        return out
 
-    # one flat fp64 payload per rank: Y | sigma2 | iters | status  -> a single collective
-    width = Nn * 3 + 3
-    payload = torch.zeros((per, width), dtype=torch.float64, device=dev)
-    n = Y_local.shape[0]
-    payload[:n, : Nn * 3] = Y_local.reshape(n, Nn * 3)
-    payload[:n, Nn * 3] = sigma2_local
-    payload[:n, Nn * 3 + 1] = iters_local.to(torch.float64)
-    payload[:n, Nn * 3 + 2] = status_local.to(torch.float64)
-    gathered = torch.empty((world * per, width), dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(gathered, payload)
-    gathered = gathered[:n_frames]
-    Y = gathered[:, : Nn * 3].reshape(n_frames, Nn, 3)
-    return Y, gathered[:, Nn * 3], gathered[:, Nn * 3 + 1].to(torch.int32), gathered[:, Nn * 3 + 2].to(torch.int32)
+def all_gather_packed(packed_local, gathered=None):
+    """ONE collective: every rank ends up with all ranks' records, [world * per, 3 Nn + 4]."""
+    world = dist.get_world_size()
+    if gathered is None:
+        gathered = torch.empty((world * packed_local.shape[0], packed_local.shape[1]), dtype=packed_local.dtype, device=packed_local.device)
+    dist.all_gather_into_tensor(gathered, packed_local)
+    return gathered
+
+
+def unpack(gathered, n_frames, n_nodes):
+    """Records -> (Y [F, Nn, 3], sigma2 [F], iters [F, 2] int32, status [F] int32)."""
+    g = gathered[:n_frames]
+    w = 3 * n_nodes
+    return (g[:, :w].reshape(n_frames, n_nodes, 3), g[:, w], g[:, w + 1:w + 3].to(torch.int32), g[:, w + 3].to(torch.int32))
