@@ -7,16 +7,18 @@ tol=0, i.e. exactly 50 EM iterations in the pre-processing registration and 50 i
 A "step" is one batched call over the rank's 64 frames.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one JSON line)
-  python bench.py --impl reference [...]                         the CPU restatement of the reference
-                                                                 (oracle/, all host threads) on the same workload
+  python bench.py --impl reference [...]                         the reference's CPU implementation of the path on the
+                                                                 same 64-frame step, all host threads
 
-Keys: `value` = whole-job EM iterations/s with inputs resident in HBM (CUDA events on the launch
-stream, max over ranks); `e2e` = same metric through the host-buffer C-ABI call (pinned host
-buffers, H2D + kernel + D2H inside the timed region); `roofline` / `fp64` explain the kernel;
-`cpu_baseline` is the oracle timed on one host core on a bounded sample.
+Keys of our line: `value` = whole-job EM iterations/s with inputs resident in HBM (CUDA events on the launch stream,
+max over ranks); `e2e` = same metric through the host-buffer C-ABI call (pinned host buffers, H2D + kernel + D2H
+inside the timed region); `roofline` = the BINDING roofline of the persistent kernel (FP64: the path is 52 flop/B),
+algorithmic and hardware fraction; `roofline_hbm` = the HBM view north_star asks for; `phases` = where the kernel's
+cycles go; `parity_rel_err` = rank 0's frame 0 of the timed batch against the oracle; `cpu_baseline` = the oracle on
+ONE pinned host core; `extra_configs` = C1 / C3 / C4 shard / C5 shard (BASELINE.json configs[0], [2], [3], [4]) and
+the C4 strong-scaling line, timed device-resident with fewer steps.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -33,21 +35,26 @@ NODES, POINTS, FRAMES_PER_GPU, MAX_ITER = 50, 20000, 64, 50
 METRIC, UNIT = "em_iterations_per_sec", "EM iterations/s"
 WORKLOAD = ("C2: 64 frames/GPU x tracking_step (pre-proc cpd_lle with LLE + traverse_euclidean + main cpd_lle), "
             "Nn=50, Mp=20000, max_iter=50, tol=0 -> 100 EM iterations per frame")
-FP64_PEAK_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz; not in MEASURED_PEAKS.json
+Z_CUT = 100.0                       # TDLO_OPT_TRUNCATION default: affinity entries below exp(-100) of the column maximum are skipped
+FP64_PEAK_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
 FP64_PEAK_MEASURED_TFLOPS = 33.0    # dependent-free DFMA loop on this pool's B200 (scripts/micro/fp64pipe.cu,
-                                    # profiles/r1_fp64pipe_microbench.txt); DMMA shares the same pipe (37 TF/s alone)
+                                    # profiles/r1_fp64pipe_microbench.txt); MEASURED_PEAKS.json has no FP64 entry
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the persistent kernel from the committed ncu --set full
-    capture of this same command (profiles/ncu_traffic.json), per launch; None if no capture is recorded."""
+def bench_config(frames_per_step):
+    """Identical in both arms (the driver compares the two `config` objects)."""
+    return {"workload": WORKLOAD, "frames_per_step": frames_per_step, "nodes": NODES, "points_per_frame": POINTS,
+            "max_iter": MAX_ITER, "tol": 0.0, "l2": "flushed between timed steps (256 MiB write) on the GPU arm"}
+
+
+def ncu_capture():
+    """Numbers of the committed ncu --set full capture of this same command (profiles/ncu_traffic.json): DRAM bytes
+    per launch and the hardware pipe utilisation; {} if no capture is recorded."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["dram_bytes_per_launch"])
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def algorithmic_work(n_nodes, mp_raw, mp_kept, iters):
@@ -64,6 +71,18 @@ def load_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model}
 
 
 class ClockSampler:
@@ -110,13 +129,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(first_frame, n_frames):
+def make_workload(first_frame, n_frames, distinct=None, **kw):
+    """A batch in the C-ABI layout.  `distinct` < n_frames: only that many different frames are generated and the batch
+    repeats them (the host-side generator computes Nn x Mp distances per frame; the kernel does not care)."""
     from trackdlo_b200 import synth
-    return synth.make_batch(n_frames, first_frame=first_frame, n_nodes=NODES, n_points=POINTS)
+    kw.setdefault("n_nodes", NODES); kw.setdefault("n_points", POINTS)
+    if distinct is None or distinct >= n_frames:
+        return synth.make_batch(n_frames, first_frame=first_frame, **kw)
+    base = synth.make_batch(distinct, first_frame=first_frame, **kw)
+    idx = [i % distinct for i in range(n_frames)]
+    frames = [base["frames"][i] for i in idx]
+    cum = lambda key: np.concatenate([[0], np.cumsum([len(f[key]) for f in frames])]).astype(np.int64)
+    return dict(frames=frames, X=np.ascontiguousarray(np.concatenate([f["X"] for f in frames])), x_offsets=cum("X"),
+                Y=np.ascontiguousarray(np.stack([f["Y"] for f in frames])), rest=np.ascontiguousarray(np.stack([f["rest"] for f in frames])),
+                vis=np.concatenate([f["vis"] for f in frames]).astype(np.int32), vis_offsets=cum("vis"),
+                vis_ext=np.concatenate([f["vis_ext"] for f in frames]).astype(np.int32), vis_ext_offsets=cum("vis_ext"))
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference (oracle/), all host threads
+# reference arm: the reference's CPU implementation of the path, all host threads, the same 64-frame step
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -125,8 +156,8 @@ def run_reference(args):
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     cores = os.cpu_count() or 1
-    per_step = max(1, min(cores, FRAMES_PER_GPU))          # one frame per host thread, up to the C2 batch of 64
-    frames = make_workload(0, per_step)["frames"]
+    F = args.frames
+    frames = make_workload(0, F)["frames"]
     tp = oracle.TrackParams(max_iter=MAX_ITER, tol=0.0)
     oracle.lib()
 
@@ -134,7 +165,7 @@ def run_reference(args):
         r = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tp)
         return int(r["iters"].sum())
 
-    pool = ThreadPoolExecutor(max_workers=per_step)       # ctypes releases the GIL: true parallelism
+    pool = ThreadPoolExecutor(max_workers=min(cores, F))       # ctypes releases the GIL: true parallelism
     for _ in range(min(args.warmup, 1)):
         list(pool.map(one, frames))
     t0 = time.perf_counter(); iters = 0
@@ -142,41 +173,137 @@ def run_reference(args):
         iters += sum(pool.map(one, frames))
     dt = time.perf_counter() - t0
     val = iters / dt
-    sample = f"{per_step} frames/step (one per host thread) of the C2 workload, {args.steps} steps, tracking_step via oracle/liboracle.so (g++ -O3)"
+    hi = host_info()
+    sample = (f"{F} frames/step (the C2 step, identical to the GPU arm's) over {min(cores, F)} host threads, {args.steps} steps, tracking_step via "
+              "oracle/liboracle.so (g++ -std=c++17 -O3: the reference's flags)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "frames_per_sec": per_step * args.steps / dt,
-            "config": {"workload": WORKLOAD, "nodes": NODES, "points_per_frame": POINTS, "max_iter": MAX_ITER, "tol": 0.0,
-                       "frames_per_step": per_step},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": per_step, "kind": "port", "sample": sample},
+            "frames_per_sec": F * args.steps / dt,
+            "config": bench_config(F),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": min(cores, F), "kind": "port", "sample": sample, **hi},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference (Eigen/ROS) is not buildable here; this is the dependency-free C++17 restatement in oracle/ "
-                    "(omits the reference's per-call MatrixXd heap traffic, so it is faster than the true reference)"}
+            "note": "kind=port: the dependency-free C++17 restatement in oracle/ -- pinned against the reference's own sources compiled "
+                    "unmodified (oracle/_ref, tests/test_ref_pin.py); it omits the reference's per-call MatrixXd heap traffic, so it is "
+                    "FASTER than the reference build (5.5x faster than oracle/_ref on a C2 frame) and the ratio against it is conservative. "
+                    "The reference is single-threaded (trackdlo_node.cpp:643); this arm gives it every host thread"}
     print(json.dumps(line), flush=True)
     return 0
 
 
 def cpu_baseline_single_core(frames):
-    """Oracle on ONE host core (the reference is single-threaded: trackdlo_node.cpp:643), bounded sample."""
+    """Oracle on ONE pinned host core (the reference is single-threaded: trackdlo_node.cpp:643), bounded sample; plus the
+    reference's own sources (oracle/_ref, Eigen calls served by oracle/ref_shim) on one frame for scale."""
     import oracle
+    from oracle import ref
     tp = oracle.TrackParams(max_iter=MAX_ITER, tol=0.0)
     oracle.lib()
-    t0 = time.perf_counter(); iters = 0; n = 0
-    for f in frames:
-        r = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tp)
-        iters += int(r["iters"].sum()); n += 1
-        if time.perf_counter() - t0 > 12.0:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": iters / dt, "unit": UNIT, "cores": 1, "kind": "port", "frames_per_sec": n / dt,
-            "sample": f"{n} frame(s) of the C2 workload (tracking_step, 100 EM iterations each), {dt:.1f} s on one host core, "
-                      "oracle/liboracle.so (g++ -std=c++17 -O3, reference flags)"}
+    old = None
+    core = None
+    try:
+        old = os.sched_getaffinity(0)
+        core = sorted(old)[len(old) // 2]
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        old = None
+    try:
+        t0 = time.perf_counter(); iters = 0; n = 0
+        for f in frames:
+            r = oracle.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tp)
+            iters += int(r["iters"].sum()); n += 1
+            if time.perf_counter() - t0 > 12.0:
+                break
+        dt = time.perf_counter() - t0
+        refb = None
+        if ref.available():
+            f = frames[0]
+            tr = oracle.TrackParams(max_iter=5, tol=0.0)
+            t1 = time.perf_counter()
+            rr = ref.tracking_step(f["X"], f["Y"], 0.0, f["rest"], f["vis"], f["vis_ext"], tr)
+            d1 = time.perf_counter() - t1
+            refb = {"value": int(rr["iters"].sum()) / d1, "unit": UNIT, "cores": 1,
+                    "sample": "1 frame of the C2 workload, 5+5 EM iterations, oracle/_ref (unmodified trackdlo.cpp + utils.cpp; Eigen calls "
+                              "served by the eager stand-in oracle/ref_shim, i.e. NOT Eigen's speed)"}
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
+    return {"value": iters / dt, "unit": UNIT, "cores": 1, "kind": "port", "frames_per_sec": n / dt, "pinned_core": core, **host_info(),
+            "sample": f"{n} frame(s) of the C2 workload (tracking_step, 100 EM iterations each), {dt:.1f} s on one pinned host core, "
+                      "oracle/liboracle.so (g++ -std=c++17 -O3, the reference's flags)",
+            "reference_build": refb}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class DeviceBatch:
+    """A tracking_step batch resident in HBM + the pointers struct of the device entry point."""
+
+    def __init__(self, api, torch, dev, wl, n_nodes, packed_rows=None):
+        self.F = F = wl["Y"].shape[0]
+        self.n_nodes = n_nodes
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.d = {k: t(wl[k]) for k in ("X", "x_offsets", "Y", "rest", "vis", "vis_offsets", "vis_ext", "vis_ext_offsets")}
+        self.Y0 = self.d["Y"].clone()
+        self.s2 = torch.zeros(F, dtype=torch.float64, device=dev)
+        self.iters = torch.zeros(F, 2, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(F, dtype=torch.int32, device=dev)
+        self.state = torch.zeros(F, dtype=torch.int32, device=dev)
+        self.packed = None if packed_rows is None else torch.zeros(packed_rows, 3 * n_nodes + 4, dtype=torch.float64, device=dev)
+        d = self.d
+        self.batch = api.TrackBatchC(F, n_nodes, d["X"].data_ptr(), d["x_offsets"].data_ptr(), d["Y"].data_ptr(), self.s2.data_ptr(),
+                                     d["rest"].data_ptr(), d["vis"].data_ptr(), d["vis_offsets"].data_ptr(), d["vis_ext"].data_ptr(),
+                                     d["vis_ext_offsets"].data_ptr(), None, None, None, None,
+                                     self.iters.data_ptr(), self.status.data_ptr(), self.state.data_ptr(),
+                                     None if self.packed is None else self.packed.data_ptr())
+
+    def reset(self):
+        self.d["Y"].copy_(self.Y0); self.s2.zero_()
+
+
+def run_extra(api, torch, dist, dev, local_rank, rank, world, flush, name, frames, nodes, points, tp, steps, distinct=None, occlusion=0.0, total_frames=None):
+    """One of the other BASELINE configs, device-resident, `steps` timed steps after one warm-up; max over ranks."""
+    wl = make_workload(100000 * (rank + 1), frames, distinct=distinct, n_nodes=nodes, n_points=points, occlusion=occlusion)
+    ctx = api.Context(max_frames=frames, max_nodes=nodes, max_points_total=int(wl["x_offsets"][-1]), device=local_rank)
+    try:
+        db = DeviceBatch(api, torch, dev, wl, nodes)
+        stream = torch.cuda.current_stream()
+        tpc = tp.to_c()
+        evs = []
+        for s in range(steps + 1):
+            db.reset(); flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.tracking_step_batched_raw(db.batch, tpc, device=True, stream=stream.cuda_stream)
+            e1.record(stream)
+            if s > 0:
+                evs.append((e0, e1))
+        ctx.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        iters = int(db.iters.sum().item())
+        st = int(np.bitwise_or.reduce(db.status.cpu().numpy()))
+    finally:
+        ctx.close()
+    t = torch.tensor([ms, float(iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, iters_all = float(tm[0]), float(ts[1])
+    else:
+        iters_all = float(iters)
+    tot = frames * world
+    out = {"ms_per_step": ms, "frames_per_step": tot, "frames_per_sec": tot / (ms * 1e-3), "em_iterations_per_sec": iters_all / (ms * 1e-3),
+           "em_iterations_per_step": iters_all, "nodes": nodes, "points_per_frame": points, "max_iter": tp.max_iter, "tol": tp.tol,
+           "status_mask_or": st, "steps": steps}
+    if occlusion:
+        out["occlusion"] = occlusion
+    if distinct is not None and distinct < frames:
+        out["distinct_frames"] = distinct
+    if total_frames is not None:
+        out["scaling"] = "strong"
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -215,23 +342,12 @@ def run_ours(args):
     hb = api.TrackBatchC(F, NODES, h["X"].data_ptr(), h["x_offsets"].data_ptr(), h["Y"].data_ptr(), h_s2.data_ptr(),
                          h["rest"].data_ptr(), h["vis"].data_ptr(), h["vis_offsets"].data_ptr(), h["vis_ext"].data_ptr(),
                          h["vis_ext_offsets"].data_ptr(), None, h_guide.data_ptr(), h_pri.data_ptr(), h_npri.data_ptr(),
-                         h_iters.data_ptr(), h_status.data_ptr(), h_state.data_ptr())
+                         h_iters.data_ptr(), h_status.data_ptr(), h_state.data_ptr(), None)
     h2d = sum(h[k].numel() * h[k].element_size() for k in h) + h_s2.numel() * 8
     d2h = sum(t.numel() * t.element_size() for t in (h["Y"], h_s2, h_guide, h_pri, h_npri, h_iters, h_status, h_state))
 
-    d = {k: h[k].to(dev) for k in h}
-    d_Y0 = d["Y"].clone()
-    d_s2 = torch.zeros(F, dtype=torch.float64, device=dev)
-    d_guide = torch.zeros(F, NODES, 3, dtype=torch.float64, device=dev)
-    d_pri = torch.zeros(F, 2 * NODES, 4, dtype=torch.float64, device=dev)
-    d_npri = torch.zeros(F, dtype=torch.int32, device=dev)
-    d_iters = torch.zeros(F, 2, dtype=torch.int32, device=dev)
-    d_status = torch.zeros(F, dtype=torch.int32, device=dev)
-    d_state = torch.zeros(F, dtype=torch.int32, device=dev)
-    db = api.TrackBatchC(F, NODES, d["X"].data_ptr(), d["x_offsets"].data_ptr(), d["Y"].data_ptr(), d_s2.data_ptr(),
-                         d["rest"].data_ptr(), d["vis"].data_ptr(), d["vis_offsets"].data_ptr(), d["vis_ext"].data_ptr(),
-                         d["vis_ext_offsets"].data_ptr(), None, d_guide.data_ptr(), d_pri.data_ptr(), d_npri.data_ptr(),
-                         d_iters.data_ptr(), d_status.data_ptr(), d_state.data_ptr())
+    db = DeviceBatch(api, torch, dev, wl, NODES, packed_rows=F)        # packed: this rank's all-gather payload, written by the kernel
+    gathered = torch.empty(world * F, 3 * NODES + 4, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream()
 
@@ -241,15 +357,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def device_step(timed):
-        d["Y"].copy_(d_Y0); d_s2.zero_()                 # restore in/out state (outside the timed region)
+        db.reset()                                       # restore in/out state (outside the timed region)
         flush.zero_()                                    # L2 flush between timed iterations
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         ev0.record(stream)
-        ctx.tracking_step_batched_raw(db, tpc, device=True, stream=stream.cuda_stream)
-        if world > 1:                                    # the single all-gather of tracked nodes
-            sharding.all_gather_results(d["Y"], d_s2, d_iters[:, 1], d_status, total_frames)
+        ctx.tracking_step_batched_raw(db.batch, tpc, device=True, stream=stream.cuda_stream)
         ev1.record(stream)
-        return (ev0, ev1) if timed else None
+        if world > 1:                                    # the single all-gather of tracked nodes: one NCCL launch
+            sharding.all_gather_packed(db.packed, gathered)
+        ev2.record(stream)
+        return (ev0, ev1, ev2) if timed else None
 
     def host_step():
         h["Y"].copy_(h_Y0); h_s2.zero_()
@@ -267,12 +384,15 @@ def run_ours(args):
     barrier()
     evs = [device_step(True) for _ in range(args.steps)]
     barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    local_dev_ms = dev_ms
-    iters_np = d_iters.cpu().numpy()
-    status_np = d_status.cpu().numpy()
+    ctx.synchronize()                      # also reports a fired watchdog
+    dev_ms = sum(a.elapsed_time(c) for a, b, c in evs)
+    kern_ms_local = sum(a.elapsed_time(b) for a, b, c in evs)
+    gather_ms_local = sum(b.elapsed_time(c) for a, b, c in evs)
+    iters_np = db.iters.cpu().numpy()
+    status_np = db.status.cpu().numpy()
+    Y_dev = db.d["Y"].cpu().numpy()
     info = ctx.launch_info()
-    launches = args.steps * info["launches"]
+    launches = args.steps * (info["launches"] + (1 if world > 1 else 0))
 
     # ---------------- end-to-end timing through the host-buffer C-ABI call (`e2e`)
     for _ in range(2):
@@ -283,10 +403,32 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_iters = int(h_iters.numpy().sum())
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---------------- phases: one more step with the kernel's cycle counters on (outside every timed region)
+    ctx.profile_phases(True)
+    device_step(False)
+    ph = ctx.profile_phases(False)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
+
+    # ---------------- the other BASELINE configs (each rank its own shard; max over ranks)
+    extras = {}
+    if not args.no_extra:
+        specs = [
+            ("C1", dict(frames=1, nodes=30, points=2000, tp=api.TrackParams(max_iter=20, tol=0.0), steps=5)),
+            ("C3_fixed50", dict(frames=1, nodes=50, points=50000, occlusion=0.4, tp=api.TrackParams(max_iter=50, tol=0.0), steps=5)),
+            ("C3_converge", dict(frames=1, nodes=50, points=50000, occlusion=0.4, tp=api.TrackParams(), steps=5)),
+            ("C4_shard", dict(frames=512, nodes=50, points=20000, distinct=64, tp=api.TrackParams(), steps=3)),
+            ("C4_strong_4096", dict(frames=max(1, 4096 // world), nodes=50, points=20000, distinct=64, tp=api.TrackParams(), steps=2, total_frames=4096)),
+            ("C5_shard", dict(frames=8, nodes=200, points=100000, distinct=2, tp=api.TrackParams(max_iter=50, tol=0.0), steps=2)),
+        ]
+        for name, kw in specs:
+            try:
+                extras[name] = run_extra(api, torch, dist, dev, local_rank, rank, world, flush, name, **kw)
+            except Exception as e:          # an extra line must never take the headline down
+                extras[name] = {"error": repr(e)[:300]}
 
     if rank == 0:
         iters_per_step_rank = int(iters_np.sum())
@@ -302,37 +444,54 @@ def run_ours(args):
                 nn = len(wl["frames"][f]["vis_ext"]) if call == 0 else NODES
                 b, fl = algorithmic_work(nn, mp0, mp0, int(iters_np[f, call]))
                 alg_b += b; alg_f += fl
-        kern_s = local_dev_ms * 1e-3 / args.steps        # rank 0's own launch (one persistent kernel per step)
+        kern_s = kern_ms_local * 1e-3 / args.steps        # rank 0's own launch (one persistent kernel per step)
         peak, peak_src = load_peaks()
-        roof = None
-        fp64 = None
-        if kern_s:
-            ach = alg_b / kern_s / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic_bytes(),
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_b,
-                    "kernel": "tdlo_tq_kernel<2,256,2> (one persistent task-queue launch per step: prune, E-step chunks, M-steps, traversal)",
-                    "note": "the path is 52 flop/B at Nn=50 (SURVEY.md §8d): compute-side bound, HBM fraction is tiny by construction; "
-                            "see `fp64` for the FP64 fraction; the E-step is bound by the SMSP issue port (an FP64 instruction holds it ~2.3 cycles, "
-                            "profiles/r1_ilp_microbench.txt, DESIGN.md §7)"}
-            tf = alg_f / kern_s / 1e12
-            fp64 = {"achieved": tf, "peak": FP64_PEAK_MEASURED_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_MEASURED_TFLOPS,
-                    "peak_source": "measured DFMA loop (scripts/micro/fp64pipe.cu -> profiles/r1_fp64pipe_microbench.txt)",
-                    "frac_of_nominal": tf / FP64_PEAK_NOMINAL_TFLOPS, "nominal_peak": FP64_PEAK_NOMINAL_TFLOPS,
-                    "flop_model": "ALGORITHMIC flop, SURVEY.md §8d: 25*Nn*Mp per frame.iteration (+18*Nn*Mp0 per call); the kernel "
-                                  "skips affinity entries below exp(-z_cut) (exact zeros / far below one ulp), so executed flop are fewer"}
-        cpu = cpu_baseline_single_core(wl["frames"]) if world == 1 else None
+        cap = ncu_capture()
+        kname = "tdlo_tq_kernel<2,256,2> (one persistent task-queue launch per step: prune, E-step chunks, M-steps, traversal)"
+        tf = alg_f / kern_s / 1e12
+        roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_MEASURED_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_MEASURED_TFLOPS,
+                "traffic": cap.get("dram_bytes_per_launch"),
+                "peak_source": "fallback: MEASURED_PEAKS.json has no FP64 entry -> this pool's own dependent-free DFMA loop "
+                               "(scripts/micro/fp64pipe.cu, profiles/r1_fp64pipe_microbench.txt); nominal 37.2",
+                "frac_of_nominal": tf / FP64_PEAK_NOMINAL_TFLOPS, "nominal_peak": FP64_PEAK_NOMINAL_TFLOPS,
+                "algorithmic_flop_per_launch": alg_f, "kernel": kname, "z_cut": Z_CUT,
+                "hw_fp64_pipe_frac": cap.get("fp64_pipe_frac"), "hw_issue_active_frac": cap.get("issue_active_frac"), "hw_source": cap.get("source"),
+                "note": "ALGORITHMIC flop (SURVEY.md §8d: 25*Nn*Mp per frame.iteration + 18*Nn*Mp0 per call) over the kernel time: the path is 52 flop/B, so "
+                        "the FP64 pipe, not HBM, is the binding roofline.  The kernel skips affinity entries below exp(-z_cut) of the column maximum "
+                        "(exact zeros / far below one ulp), so the executed flop -- what hw_fp64_pipe_frac (ncu sm__pipe_fp64_cycles_active) sees -- are fewer"}
+        ach = alg_b / kern_s / 1e9
+        roof_hbm = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": cap.get("dram_bytes_per_launch"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_b, "kernel": kname,
+                    "note": "secondary view: points are read once per EM iteration from L2 (a frame is 480 KB), P is never materialised"}
+        cyc = ph["cycles"]; tot = float(sum(cyc.values())) or 1.0
+        phases = {"share_of_cta_cycles": {k: v / tot for k, v in cyc.items()}, "counts": ph["counts"],
+                  "note": "thread-0 cycles of every CTA of one extra, untimed step (tdlo_profile_phases); queue_wait = CTA idle waiting for a task"}
+        # parity of what was just timed: rank 0's frame 0 against the oracle
+        parity = None
+        cpu = None
+        if True:
+            import oracle
+            f0 = wl["frames"][0]
+            o = oracle.tracking_step(f0["X"], f0["Y"], 0.0, f0["rest"], f0["vis"], f0["vis_ext"], oracle.TrackParams(max_iter=MAX_ITER, tol=0.0))
+            parity = {"rel_err_Y": float(np.abs(Y_dev[0] - o["Y"]).max() / np.abs(o["Y"]).max()),
+                      "iters_match": [int(v) for v in iters_np[0]] == [int(v) for v in o["iters"]], "frame": 0,
+                      "against": "oracle/liboracle.so tracking_step on rank 0's frame 0 of the timed batch", "gate": 1e-5}
+        if world == 1:
+            cpu = cpu_baseline_single_core(wl["frames"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "frames_per_sec": F * world * args.steps / (dev_ms * 1e-3),
-                "config": {"workload": WORKLOAD, "frames_per_gpu": F, "nodes": NODES, "points_per_frame": POINTS,
-                           "max_iter": MAX_ITER, "tol": 0.0, "l2": "flushed between timed steps (256 MiB write)",
-                           "parallelism": f"frames sharded over {world} GPU(s), one all-gather of results per step" if world > 1 else "single GPU",
-                           "launch": info},
+                "config": bench_config(F),
+                "launch": {**info, "parallelism": f"frames sharded over {world} GPU(s), kernel-packed records, ONE all-gather per step" if world > 1 else "single GPU",
+                           "all_gather_ms_per_step": gather_ms / args.steps if world > 1 else 0.0},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps, "frames_per_sec": F * world * args.steps / (e2e_ms * 1e-3)},
                 "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roof, "fp64": fp64, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm, "phases": phases,
+                "parity_rel_err": parity["rel_err_Y"] if parity else None, "parity": parity,
+                "cpu_baseline": cpu,
+                "extra_configs": extras,
                 "status_mask_or": int(np.bitwise_or.reduce(status_np)),
                 "em_iterations_per_step": iters_per_step}
         print(json.dumps(line), flush=True)
@@ -349,6 +508,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs (C1/C3/C4/C5) lines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -357,7 +517,7 @@ def main():
         # convenience: relaunch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__), "--gpus", str(args.gpus),
-               "--steps", str(args.steps), "--warmup", str(args.warmup), "--frames", str(args.frames)]
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--frames", str(args.frames)] + (["--no-extra"] if args.no_extra else [])
         return subprocess.call(cmd)
     return run_ours(args)
 
