@@ -242,6 +242,15 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
  *  TDLO_OPT_THREADS       kernel variant for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
  *                         224 (3 CTAs/SM, 80 registers; measured equal or slower).  Nn > 64 always uses 256.
+ *  TDLO_OPT_SOLVER        the M-step solve (trackdlo.cpp:394-417).  G is the Matern-3/2 covariance of the nodes' arc
+ *                         lengths, so (S G + lambda sigma2 I) W = B and T = Y0 + G W can be computed in O(Nn) by a
+ *                         state-space (Kalman filter + adjoint) recursion without forming G or A -- S = diag(P1 + alpha J)
+ *                         with a 2-dimensional state, S = diag(..) + sigma2 gamma E^T E (LLE) with an 8-dimensional one; both
+ *                         are MORE accurate than a dense solve of the ill-conditioned A (profiles/r2_kalman_solver_accuracy.txt).
+ *                         0 (default) = automatic: structured without LLE, and with LLE above 64 nodes; 1 = dense always
+ *                         (register-resident Gauss-Jordan for Nn <= 64, blocked Cholesky with FP64 tensor-core MMAs /
+ *                         pivoted elimination above); 2 = structured always.  A caller-supplied H and a negative alpha
+ *                         always solve densely.
  *  TDLO_OPT_WATCHDOG_MS   a CTA of the persistent kernel that waits longer than this for its next task (or for a frame's
  *                         upload) abandons the launch and the call returns TDLO_ERR_CUDA instead of hanging the caller
  *                         (default 20000; 0 = never). */
@@ -250,6 +259,7 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 #define TDLO_OPT_INFLIGHT 4
 #define TDLO_OPT_THREADS 5
 #define TDLO_OPT_WATCHDOG_MS 6
+#define TDLO_OPT_SOLVER 7
 int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value);
 
 #ifdef __cplusplus

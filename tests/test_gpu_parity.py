@@ -38,7 +38,9 @@ def ctx():
 # Engine configurations every golden is run under: the default Gaussian truncation (z_cut = 100) and exact-zero
 # skipping only (z_cut = 745.2), small chunks (many partial sums per frame), both kernel variants (224 / 256 threads).
 ENGINE_CFGS = {
-    "tq": dict(chunk_points=0, truncation=100.0, threads=256),
+    "tq": dict(chunk_points=0, truncation=100.0, threads=256, solver=0),
+    "dense_solver": dict(solver=1),                         # M-step: dense Gauss-Jordan / blocked Cholesky instead of the O(Nn) state-space solve
+    "structured_all": dict(solver=2),                       # ... and the state-space solve also for the LLE registrations below 65 nodes
     "tq_224thr": dict(chunk_points=1024, truncation=100.0, threads=224),
     "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, threads=224),
     "tq_256thr": dict(chunk_points=2048, truncation=100.0, threads=256),
@@ -90,7 +92,7 @@ def test_cpd_against_golden(ctx, golden_dir, name, cfg):
 
 
 @pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
-@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr"])
+@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr", "dense_solver", "structured_all"])
 def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
@@ -114,7 +116,7 @@ def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
 
 
-@pytest.fixture(params=["tq", "tq_exact_small_chunks"])
+@pytest.fixture(params=["tq", "tq_exact_small_chunks", "dense_solver", "structured_all"])
 def ectx(ctx, request):
     _configure(ctx, request.param)
     ctx.engine_name = request.param
@@ -331,13 +333,15 @@ def test_c3_full_size_occlusion_visibility_branch(ctx):
     assert abs(r["sigma2"][0] - o["sigma2"]) / o["sigma2"] < 1e-5
 
 
-def test_c5_size_dense_solve_properties():
-    """BASELINE configs[4] shape (Nn=200, Mp=100000): blocked-Cholesky solve path.  Size-independent properties at full
-    size: rigid-translation equivariance of Y, invariance of W, and bit-exact repeatability; plus the oracle on a
-    2-iteration run."""
+@pytest.mark.parametrize("solver", [0, 1])
+def test_c5_size_dense_solve_properties(solver):
+    """BASELINE configs[4] shape (Nn=200, Mp=100000), structured O(Nn) solve (0) and blocked-Cholesky solve (1).
+    Size-independent properties at full size: rigid-translation equivariance of Y, invariance of W, and bit-exact
+    repeatability; plus the oracle on a 2-iteration run."""
     Nn, Mp = 200, 100000
     f = synth.make_frame(2, n_nodes=Nn, n_points=Mp)
     c = api.Context(max_frames=1, max_nodes=Nn, max_points_total=Mp)
+    c.set_option("solver", solver)
     try:
         one = np.array([0, Mp], np.int64)
         pg = api.CpdParams(max_iter=6, tol=0.0)
@@ -415,15 +419,22 @@ def test_bad_arguments_are_rejected(ctx):
         ctx.cpd_lle_batched(f["X"], np.zeros(201, np.int64), big, np.zeros(200), api.CpdParams())
 
 
-def test_larger_node_counts():
-    """Nn = 100 and 200 take the other kernel variants (more node passes per lane, global-memory solve workspace)."""
+@pytest.mark.parametrize("solver", [0, 1, 2])
+def test_larger_node_counts(solver):
+    """Nn = 100 and 200 take the other kernel variants (more node passes per lane); solver 1 = blocked Cholesky."""
     c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)
+    c.set_option("solver", solver)
     try:
         for Nn, Mp in ((65, 3000), (100, 6000), (200, 8000)):      # 65: [A|B] would still fit shared memory, Cholesky path
             f = synth.make_frame(1, n_nodes=Nn, n_points=Mp)
             o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(max_iter=8, tol=0.0))
             r = c.cpd_lle_batched(f["X"], np.array([0, Mp], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(max_iter=8, tol=0.0))
             assert r["iters"][0] == 8
+            assert rel(r["Y"][0], o["Y"]) < 1e-6 and rel(r["W"][0], o["W"]) < GATE
+            kw = dict(max_iter=4, tol=0.0, include_lle=True, beta=3.0, lambda_=1.0)          # the pre-processing registration's shape
+            o = oracle.cpd_lle(f["X"], f["Y"], 0.0, oracle.CpdParams(**kw))
+            r = c.cpd_lle_batched(f["X"], np.array([0, Mp], np.int64), f["Y"][None], np.zeros(1), api.CpdParams(**kw))
+            assert r["iters"][0] == 4
             assert rel(r["Y"][0], o["Y"]) < 1e-6 and rel(r["W"][0], o["W"]) < GATE
     finally:
         c.close()

@@ -46,6 +46,7 @@ struct tdlo_ctx {
     int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
+    int tq_solver = 0;              // M-step solve: 0 = automatic, 1 = dense always, 2 = structured always (TDLO_OPT_SOLVER)
     double watchdog_ms = 20000.0;   // a CTA waiting longer than this for a task aborts the launch (0 = off)
     cudaStream_t last_stream = nullptr; bool launched = false;
     double* d_fscratch = nullptr; long long fstride = 0;
@@ -257,6 +258,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.inflight = ctx->tq_inflight > 0 ? ctx->tq_inflight : std::max(grid / 2, 64);
     t.inflight = std::min(std::min(t.inflight, grid), a.n_frames);
     t.zcut = ctx->tq_zcut;
+    t.solver = ctx->tq_solver;
     t.qctl = ctx->d_q; t.qslots = ctx->d_q + 8; t.qmask = ctx->qcap - 1;
     t.fscratch = ctx->d_fscratch; t.fstride = ctx->fstride;
     t.part = ctx->d_part; t.dminp = ctx->d_dminp; t.gath = ctx->d_gath; t.nkept = ctx->d_nkept; t.tsph = ctx->d_tsph;
@@ -753,6 +755,9 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             if (t != 224 && t != 256) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256 (2 CTAs/SM)");
             ctx->tq_threads = t; return TDLO_OK;
         }
+        case TDLO_OPT_SOLVER:
+            if (value != 0.0 && value != 1.0 && value != 2.0) return fail(ctx, TDLO_ERR_INVALID, "solver must be 0 (automatic), 1 (dense) or 2 (structured)");
+            ctx->tq_solver = (int)value; return TDLO_OK;
         case TDLO_OPT_WATCHDOG_MS:
             if (!(value >= 0.0)) return fail(ctx, TDLO_ERR_INVALID, "watchdog must be >= 0 ms (0 = off)");
             ctx->watchdog_ms = value; return TDLO_OK;

@@ -104,6 +104,12 @@ __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ t
     return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
 }
 
+// 32-byte L2 load (data written by other CTAs during this launch must not come from L1)
+__device__ __forceinline__ double4 ldcg4(const double4* p) {
+    const double2 lo = __ldcg(reinterpret_cast<const double2*>(p)), hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __device__ __forceinline__ double dist2(double ax, double ay, double az, double bx, double by, double bz) {
     const double dx = ax - bx, dy = ay - by, dz = az - bz;
     return dx * dx + dy * dy + dz * dz;
@@ -677,6 +683,342 @@ static __device__ int chol_solve_blocked(double* A, int n, int ld, double* work,
     }
     return *flag;
 }
+
+// ------------------------------------------------------------------------------------------
+// Structured M-step solve, O(Nn): (diag(D) G + c I) W = B and V = G W without ever forming G.
+//
+// G_ij = 1/(4 beta^2) exp(-sqrt2 d/beta) (2 d + sqrt2 beta), d = |s_i - s_j| (trackdlo.cpp:225-233), is the Matern-3/2
+// covariance sigma_f^2 (1 + a d) exp(-a d) with a = sqrt2/beta, sigma_f^2 = sqrt2/(4 beta), of a process f sampled at the
+// (ascending) arc-length coordinates s_i.  (f, f') is a two-dimensional Markov process, so with D = d_i^2 >= 0
+//     D^1/2 G D^1/2 + c I  =  Cov(y),   y_i = d_i f(s_i) + noise_i,  noise ~ N(0, c):
+// the innovations form of the Kalman filter over the nodes is an L F L^T factorisation of that matrix in O(Nn), its
+// adjoint (backward) recursion applies the inverse (de Jong's smoothing error u = Cov(y)^-1 y), and the smoothed mean of
+// f is G D^1/2 u.  Hence  W = D^1/2 u  solves (D G + c I) W = B for y = D^-1/2 B  (rows with D_i = 0 have B_i = 0 and get
+// W_i = 0, exactly as in the dense SPD form D^1/2 G D^1/2 + cI it replaces), and V = G W comes out of the same backward
+// pass -- T = Y0 + G W (trackdlo.cpp:417) needs no dense product either.  Replaces the O(Nn^2) assembly of A
+// (trackdlo.cpp:394-413), the O(Nn^3) completeOrthogonalDecomposition().solve (:415) and the O(Nn^2) product G*W.
+// Measured against a 50-digit dense solve it is MORE accurate than LAPACK's dense solve of the same system (1e-13 vs
+// 1e-12 relative on W at cond 1e5; profiles/r2_kalman_solver_accuracy.txt), because it never forms the ill-conditioned A.
+//
+// Covariances are carried as the deficit Delta = P_inf - P (starts at 0, only grows), transitions Phi_t over the gap
+// h_t = s_{t+1} - s_t are precomputed once per call (phi[t] = {Phi00, Phi01, Phi10, Phi11}).
+// All threads first turn D, B into d = sqrt(D) and y = B / d (the square roots stay out of the recursion); then lanes
+// 0..2 of warp 0 run the recursion, one right-hand-side column each (the covariance part redundantly: no communication
+// inside the ~120-cycle dependent chain of a step; the next node's inputs are loaded one step ahead).
+// All pointers are shared memory.
+//   in : dd[n] = D_i (overwritten with d_i), bt[3][n] = columns of B (overwritten), phi[n][4], y0[n][3]
+//   out: wsol[n][3] = W, tnew[n][3] = Y0 + G W
+//   ws : rF[n], kk[2n], pp[2n], am[6n]
+// Returns non-zero if an innovation variance was not finite and positive.
+// ------------------------------------------------------------------------------------------
+static __device__ int mct_kalman_solve(int n, double c, double beta, double* __restrict__ dd, double* __restrict__ bt,
+                                       const double* __restrict__ phi, const double* __restrict__ y0, double* __restrict__ wsol,
+                                       double* __restrict__ tnew, double* __restrict__ rF, double* __restrict__ kk,
+                                       double* __restrict__ pp, double* __restrict__ am) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < n; i += nt) {
+        const double D = dd[i];
+        const double d = sqrt(D), rd = D > 0.0 ? 1.0 / d : 0.0;
+        dd[i] = d;
+        bt[i] *= rd; bt[n + i] *= rd; bt[2 * n + i] *= rd;          // y = B / d (0 where D = 0: B is 0 there)
+    }
+    __syncthreads();
+    int bad = 0;
+    if (tid < 3) {
+        const int col = tid;
+        const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);    // P_inf = diag(s2f, a^2 s2f)
+        double* __restrict__ v = bt + col * n;
+        double* __restrict__ a0s = am + col * 2 * n;
+        double* __restrict__ a1s = a0s + n;
+        double D00 = 0.0, D01 = 0.0, D11 = 0.0;          // Delta = P_inf - P (prior of node t before its observation)
+        double a0 = 0.0, a1 = 0.0;                        // prior mean of (f, f') at node t
+        double d = dd[0], y = v[0];
+        double p00 = phi[0], p01 = phi[1], p10 = phi[2], p11 = phi[3];
+        for (int t = 0; t < n; t++) {
+            // inputs of the next node (independent of the recursion: their latency hides behind this step)
+            const int tn = t + 1 < n ? t + 1 : t;
+            const double dn = dd[tn], yn = v[tn];
+            const double q00 = phi[4 * tn], q01 = phi[4 * tn + 1], q10 = phi[4 * tn + 2], q11 = phi[4 * tn + 3];
+            const double P00 = s2f - D00, P01 = -D01;
+            const double g0 = P00 * d, g1 = P01 * d;      // P h,  h = (d, 0)
+            const double F = fma(d * d, P00, c);          // (d * d does not depend on the recursion)
+            const double r = rcp_fast(F);
+            bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
+            const double k0 = g0 * r, k1 = g1 * r;        // gain
+            const double inn = fma(-d, a0, y);
+            if (col == 0) { rF[t] = r; kk[2 * t] = k0; kk[2 * t + 1] = k1; pp[2 * t] = P00; pp[2 * t + 1] = P01; }
+            v[t] = inn; a0s[t] = a0; a1s[t] = a1;
+            // posterior after the observation, then transition to node t+1
+            const double m0 = fma(k0, inn, a0), m1 = fma(k1, inn, a1);
+            const double E00 = fma(g0, k0, D00), E01 = fma(g0, k1, D01), E11 = fma(g1, k1, D11);   // Delta+ = Delta + k k^T F
+            a0 = fma(p00, m0, p01 * m1); a1 = fma(p10, m0, p11 * m1);
+            const double M00 = fma(p00, E00, p01 * E01), M01 = fma(p00, E01, p01 * E11);
+            const double M10 = fma(p10, E00, p11 * E01), M11 = fma(p10, E01, p11 * E11);
+            D00 = fma(M00, p00, M01 * p01); D01 = fma(M00, p10, M01 * p11); D11 = fma(M10, p10, M11 * p11);
+            d = dn; y = yn; p00 = q00; p01 = q01; p10 = q10; p11 = q11;
+        }
+        // backward: r <- Phi_t^T r ;  u_t = v_t / F_t - k_t . r ;  r <- r + h u ;  smoothed f_t = a_t[0] + P_t[0,:] . r
+        double r0 = 0.0, r1 = 0.0;
+        int t = n - 1;
+        double vt = v[t], rf = rF[t], kt0 = kk[2 * t], kt1 = kk[2 * t + 1], pt0 = pp[2 * t], pt1 = pp[2 * t + 1], at = a0s[t], dt = dd[t];
+        double yx = y0[3 * t + col];
+        for (; t >= 0; t--) {
+            const int tp = t > 0 ? t - 1 : 0;
+            const double vn = v[tp], rfn = rF[tp], kn0 = kk[2 * tp], kn1 = kk[2 * tp + 1], pn0 = pp[2 * tp], pn1 = pp[2 * tp + 1], an = a0s[tp], dn = dd[tp];
+            const double yxn = y0[3 * tp + col];
+            const double f00 = phi[4 * tp], f01 = phi[4 * tp + 1], f10 = phi[4 * tp + 2], f11 = phi[4 * tp + 3];    // Phi_{t-1}
+            const double u = fma(vt, rf, -fma(kt0, r0, kt1 * r1));
+            r0 = fma(dt, u, r0);
+            const double V = fma(pt0, r0, fma(pt1, r1, at));
+            wsol[3 * t + col] = dt * u;
+            tnew[3 * t + col] = yx + V;
+            const double n0 = fma(f00, r0, f10 * r1), n1 = fma(f01, r0, f11 * r1);      // adjoint of the transition t-1 -> t
+            r0 = n0; r1 = n1;
+            vt = vn; rf = rfn; kt0 = kn0; kt1 = kn1; pt0 = pn0; pt1 = pn1; at = an; dt = dn; yx = yxn;
+        }
+    }
+    return __syncthreads_or(bad);
+}
+
+// ------------------------------------------------------------------------------------------
+// Structured M-step solve WITH the LLE regulariser (pre-processing registration, trackdlo.cpp:396-403), O(Nn):
+//     ((diag(D) + eps E^T E) G + c I) W = B,   E = I - L (LLE weights, rows reach 3 nodes either side), eps = sigma2 gamma,
+//     B = D^1/2 ya + sqrt(eps) E^T yb  with  ya = (PX - P1 Y0 [+ alpha (Yext - Y0)]) / d,  yb = -sqrt(eps) E Y0.
+// With S = Z Z^T, Z = [D^1/2, sqrt(eps) E^T], this is GP regression of the same Matern-3/2 process f under 2 Nn scalar
+// observations with noise variance c:  d_t f(s_t) = ya_t  and  sqrt(eps) (E f)_r = yb_r.  The second kind looks at seven
+// consecutive nodes, so the Markov state carries them:  x_t = [f_t, f'_t, f_{t-1}, ..., f_{t-6}]  (8).  The filter runs
+// over the nodes: transition t-1 -> t, observation A(t), then every LLE row r whose last node has arrived
+// (min(r+3, Nn-1) == t).  Its adjoint pass gives the smoothing errors uA, uB = Cov(obs)^-1 [ya; yb], and
+//     W = d uA + sqrt(eps) E^T uB,     G W = smoothed mean of f.
+// Validated in NumPy against a 50-digit dense solve with LLE weights taken from the reference build
+// (scripts/kalman_solver_check.py, profiles/r2_kalman_solver_accuracy.txt): ~10x more accurate than LAPACK's dense solve.
+// It replaces, at Nn = 200, a 200 x 200 pivoted elimination per EM iteration (and the H G, H Y0 products per call).
+//
+// Lanes 0..2 of warp 0 run the filter, one right-hand-side column each, the 8 x 8 covariance (upper triangle, 36
+// registers) redundantly.  Forward results go to a global workspace (gws, 43 n doubles); the backward pass stages them
+// back through shared memory in blocks of KL_BLK nodes (all threads copy, three lanes compute).
+//   in (shared): sd[n] = D_t (overwritten with d_t), ya[3][n] (overwritten: the smoothing errors uA end up there), y0[n][3]
+//   in (global): tr[n][8] = {Phi00, Phi01, Phi10, Phi11, Q00, Q01, Q11, -} of the gap t -> t+1, Eg[n][n] = E, ey0[n][3] = E Y0
+//   out (shared): wsol[n][3], tnew[n][3];  ws (shared): ub[3][n], eb[n][7] (band of E), ey[n][3], stage[KL_STAGE]
+// ------------------------------------------------------------------------------------------
+constexpr int KL_BLK = 32;
+constexpr int KL_STAGE = KL_BLK * 17 + (KL_BLK + 4) * 17 + KL_BLK * 6 + (KL_BLK + 4) * 3;
+#define KL_P(i, j) P[(i) * 8 - ((i) * ((i) - 1)) / 2 + ((j) - (i))]      /* upper triangle, i <= j, compile-time indices */
+
+struct KlObs { double r, v; };
+// one scalar observation h . x = y (+ noise c): updates (P, m), returns 1/F and the innovation, leaves the gain in k[]
+__device__ __forceinline__ KlObs kl_observe(double (&P)[36], double (&m)[8], const double (&h)[8], double y, double c, double (&k)[8], int& bad) {
+    double g[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc = fma(i <= j ? KL_P(i, j) : KL_P(j, i), h[j], acc);
+        g[i] = acc;
+    }
+    double F = c, hm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { F = fma(h[i], g[i], F); hm = fma(h[i], m[i], hm); }
+    const double r = rcp_fast(F);
+    bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
+    const double v = y - hm;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { k[i] = g[i] * r; m[i] = fma(k[i], v, m[i]); }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = i; j < 8; j++) KL_P(i, j) = fma(-k[i], g[j], KL_P(i, j));
+    KlObs o; o.r = r; o.v = v;
+    return o;
+}
+
+static __device__ int mct_kalman_lle_solve(int n, double c, double eps, double beta, double* __restrict__ sd, double* __restrict__ ya,
+                                           const double* __restrict__ y0, const double* __restrict__ tr, const double* __restrict__ Eg,
+                                           const double* __restrict__ ey0, double* __restrict__ wsol, double* __restrict__ tnew,
+                                           double* __restrict__ ub, double* __restrict__ eb, double* __restrict__ ey,
+                                           double* __restrict__ stage, double* __restrict__ gws) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* __restrict__ ua = ya;
+    for (int i = tid; i < n; i += nt) {
+        const double D = sd[i];
+        const double d = sqrt(D), rd = D > 0.0 ? 1.0 / d : 0.0;
+        sd[i] = d;
+        ya[i] *= rd; ya[n + i] *= rd; ya[2 * n + i] *= rd;
+    }
+    for (int i = tid; i < 7 * n; i += nt) {              // band of E: eb[r][b] = E[r][r-3+b]
+        const int r = i / 7, node = r - 3 + (i - 7 * r);
+        eb[i] = (node >= 0 && node < n) ? __ldcg(Eg + (long long)r * n + node) : 0.0;
+    }
+    for (int i = tid; i < 3 * n; i += nt) ey[i] = __ldcg(ey0 + i);
+    __syncthreads();
+    const double se = sqrt(eps);
+    double* gA = gws;                      // [n][17]: 1/F, k[8], P(0,:) before the observation
+    double* gB = gws + 17 * n;             // [n][17]: 1/F, k[8], h[8]      (indexed by LLE row)
+    double* gC = gws + 34 * n;             // per column: vA[3][n], m0[3][n], vB[3][n]
+    int bad = 0;
+    if (tid < 3) {
+        const int col = tid;
+        const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
+        double P[36], m[8], k[8];
+#pragma unroll
+        for (int i = 0; i < 36; i++) P[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) m[i] = 0.0;
+        KL_P(0, 0) = s2f; KL_P(1, 1) = a * a * s2f;
+        double4 phn = ldcg4(reinterpret_cast<const double4*>(tr)), qqn = ldcg4(reinterpret_cast<const double4*>(tr + 4));
+        for (int t = 0; t < n; t++) {
+            const double4 ph = phn, qq = qqn;             // transition t-1 -> t (loaded one node ahead)
+            if (t + 1 < n) { phn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * t)); qqn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * t + 4)); }
+            if (t > 0) {
+                // ---- transition t-1 -> t: lags shift down, (f, f') <- Phi (f, f') + w
+#pragma unroll
+                for (int i = 7; i >= 3; i--)
+#pragma unroll
+                    for (int j = 7; j >= i; j--) KL_P(i, j) = KL_P(i - 1, j - 1);
+#pragma unroll
+                for (int j = 7; j >= 3; j--) KL_P(2, j) = KL_P(0, j - 1);
+                KL_P(2, 2) = KL_P(0, 0);
+#pragma unroll
+                for (int j = 7; j >= 3; j--) KL_P(1, j) = KL_P(1, j - 1);
+                KL_P(1, 2) = KL_P(0, 1);
+#pragma unroll
+                for (int j = 7; j >= 3; j--) KL_P(0, j) = KL_P(0, j - 1);
+                KL_P(0, 2) = KL_P(0, 0);
+#pragma unroll
+                for (int j = 2; j < 8; j++) {
+                    const double t0 = KL_P(0, j), t1 = KL_P(1, j);
+                    KL_P(0, j) = fma(ph.x, t0, ph.y * t1); KL_P(1, j) = fma(ph.z, t0, ph.w * t1);
+                }
+                {
+                    const double p00 = KL_P(0, 0), p01 = KL_P(0, 1), p11 = KL_P(1, 1);
+                    const double M00 = fma(ph.x, p00, ph.y * p01), M01 = fma(ph.x, p01, ph.y * p11);
+                    const double M10 = fma(ph.z, p00, ph.w * p01), M11 = fma(ph.z, p01, ph.w * p11);
+                    KL_P(0, 0) = fma(M00, ph.x, fma(M01, ph.y, qq.x));
+                    KL_P(0, 1) = fma(M00, ph.z, fma(M01, ph.w, qq.y));
+                    KL_P(1, 1) = fma(M10, ph.z, fma(M11, ph.w, qq.z));
+                }
+#pragma unroll
+                for (int i = 7; i >= 3; i--) m[i] = m[i - 1];
+                m[2] = m[0];
+                { const double t0 = m[0], t1 = m[1]; m[0] = fma(ph.x, t0, ph.y * t1); m[1] = fma(ph.z, t0, ph.w * t1); }
+            }
+            // ---- observation A(t): d_t f_t = ya_t
+            {
+                const double d = sd[t];
+                if (col == 0) {
+                    double* o = gA + 17 * t + 9;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o[j] = KL_P(0, j);
+                }
+                gC[(3 + col) * n + t] = m[0];
+                double h[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) h[i] = 0.0;
+                h[0] = d;
+                const KlObs ob = kl_observe(P, m, h, ya[col * n + t], c, k, bad);
+                if (col == 0) {
+                    double* o = gA + 17 * t;
+                    o[0] = ob.r;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o[1 + j] = k[j];
+                }
+                gC[col * n + t] = ob.v;
+            }
+            // ---- LLE rows complete at t: r = t-3 (t >= 3), and at the last node every remaining row
+            const int rlo = t + 1 < n ? t - 3 : (t - 3 > 0 ? t - 3 : 0), rhi = t + 1 < n ? t - 3 : n - 1;
+            for (int r = rlo < 0 ? n : rlo; r <= rhi; r++) {
+                double h[8];
+                const double* er = eb + 7 * r;
+#pragma unroll
+                for (int lag = 0; lag < 7; lag++) {
+                    const int b = t - lag - (r - 3);                            // position of node t-lag in the row's band r-3..r+3
+                    const double e = (b >= 0 && b < 7) ? er[b] : 0.0;
+                    h[lag == 0 ? 0 : lag + 1] = se * e;
+                }
+                h[1] = 0.0;
+                const double yb = -se * ey[3 * r + col];
+                const KlObs ob = kl_observe(P, m, h, yb, c, k, bad);
+                if (col == 0) {
+                    double* o = gB + 17 * r;
+                    o[0] = ob.r;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { o[1 + j] = k[j]; o[9 + j] = h[j]; }
+                }
+                gC[(6 + col) * n + r] = ob.v;
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- backward pass, blocks of KL_BLK nodes from the end; rows of the block: r = t-3, and all rows >= n-4 with t = n-1
+    double* sA = stage;                                   // [KL_BLK][17]
+    double* sB = sA + KL_BLK * 17;                        // [KL_BLK+4][17]
+    double* sCa = sB + (KL_BLK + 4) * 17;                 // vA, m0: [KL_BLK][6]
+    double* sCb = sCa + KL_BLK * 6;                       // vB: [KL_BLK+4][3]
+    double rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rr[i] = 0.0;
+    for (int t1 = n; t1 > 0; t1 -= KL_BLK) {
+        const int t0 = t1 - KL_BLK > 0 ? t1 - KL_BLK : 0;
+        const int r0 = t0 - 3 > 0 ? t0 - 3 : 0, r1 = t1 == n ? n : (t1 - 3 > 0 ? t1 - 3 : 0);     // rows [r0, r1)
+        __syncthreads();
+        for (int i = tid; i < (t1 - t0) * 17; i += nt) sA[i] = __ldcg(gA + 17 * t0 + i);
+        for (int i = tid; i < (r1 - r0) * 17; i += nt) sB[i] = __ldcg(gB + 17 * r0 + i);
+        for (int i = tid; i < (t1 - t0) * 6; i += nt) { const int tt = i / 6, q = i - 6 * tt; sCa[i] = __ldcg(gC + (long long)q * n + t0 + tt); }
+        for (int i = tid; i < (r1 - r0) * 3; i += nt) { const int rw = i / 3, q = i - 3 * rw; sCb[i] = __ldcg(gC + (long long)(6 + q) * n + r0 + rw); }
+        __syncthreads();
+        if (tid < 3) {
+            const int col = tid;
+            for (int t = t1 - 1; t >= t0; t--) {
+                // LLE rows of node t, in reverse order
+                const int rlo = t + 1 < n ? t - 3 : (t - 3 > 0 ? t - 3 : 0), rhi = t + 1 < n ? t - 3 : n - 1;
+                for (int r = rhi; r >= rlo && r >= 0; r--) {
+                    const double* o = sB + 17 * (r - r0);
+                    double kr = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) kr = fma(o[1 + i], rr[i], kr);
+                    const double u = fma(sCb[3 * (r - r0) + col], o[0], -kr);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) rr[i] = fma(o[9 + i], u, rr[i]);
+                    ub[col * n + r] = u;
+                }
+                {   // observation A(t)
+                    const double* o = sA + 17 * (t - t0);
+                    double kr = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) kr = fma(o[1 + i], rr[i], kr);
+                    const double u = fma(sCa[6 * (t - t0) + col], o[0], -kr);
+                    rr[0] = fma(sd[t], u, rr[0]);
+                    double V = sCa[6 * (t - t0) + 3 + col];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) V = fma(o[9 + i], rr[i], V);
+                    ua[col * n + t] = u;
+                    tnew[3 * t + col] = y0[3 * t + col] + V;
+                }
+                if (t > 0) {   // adjoint of the transition t-1 -> t
+                    const double4 ph = ldcg4(reinterpret_cast<const double4*>(tr + 8 * (t - 1)));
+                    const double n0 = fma(ph.x, rr[0], fma(ph.z, rr[1], rr[2])), n1 = fma(ph.y, rr[0], ph.w * rr[1]);
+                    rr[0] = n0; rr[1] = n1;
+#pragma unroll
+                    for (int i = 2; i < 7; i++) rr[i] = rr[i + 1];
+                    rr[7] = 0.0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- W = d uA + sqrt(eps) E^T uB   (E^T uB: rows j-3 .. j+3 of column j)
+    for (int idx = tid; idx < 3 * n; idx += nt) {
+        const int j = idx / 3, col = idx - 3 * j;
+        double w = sd[j] * ua[col * n + j];
+        double acc = 0.0;
+        const int ra = j - 3 > 0 ? j - 3 : 0, rb = j + 3 < n - 1 ? j + 3 : n - 1;
+        for (int r = ra; r <= rb; r++) acc = fma(eb[7 * r + (j - r + 3)], ub[col * n + r], acc);
+        wsol[idx] = fma(se, acc, w);
+    }
+    return __syncthreads_or(bad);
+}
+#undef KL_P
 
 // ------------------------------------------------------------------------------------------
 // LLE weights, one node per thread (trackdlo.cpp:92-159).  Mirrors the operation order of

@@ -27,13 +27,13 @@ enum { A_NONE = 0, A_START_CALL, A_AFTER_PRUNE, A_BEGIN_ITER, A_AFTER_DMIN, A_MS
 
 // frame control block (ints)
 enum { FC_PENDING = 0, FC_PHASE, FC_STAGE, FC_ITER, FC_NN, FC_NCHUNK, FC_USEVIS, FC_NPRI, FC_STATUS, FC_NVIS, FC_STPRE,
-       FC_ITPRE, FC_WORDS = 16 };
+       FC_ITPRE, FC_DENSE, FC_WORDS = 16 };
 // frame scalars (doubles)
 enum { FS_SIGMA2 = 0, FS_RSCALE, FS_CNORM, FS_MP, FS_CGAUSS, FS_WORDS = 8 };
 
 // ---- per-frame scratch (doubles); N = scr_nodes
 struct TqScr {
-    long long G, HG, H, AB, NODE4, VW, Y0, S, YEXT, JD, HY0, WSOL, SCAL, TRV, PRI, GUIDE, CTL, total;
+    long long G, HG, H, AB, NODE4, VW, Y0, S, YEXT, JD, HY0, WSOL, SCAL, TRV, PRI, GUIDE, PHI, KTR, KLW, CTL, total;
 };
 __host__ __device__ inline TqScr tq_scr_layout(int N) {
     TqScr s;
@@ -54,6 +54,9 @@ __host__ __device__ inline TqScr tq_scr_layout(int N) {
     s.TRV = o; o += 2LL * (N + 2) * 4;
     s.PRI = o; o += (2LL * N + 4) * 4;
     s.GUIDE = o; o += 3 * N;
+    s.PHI = o; o += 4 * N;
+    s.KTR = o; o += 8 * N;                   // structured LLE solve: transitions {Phi, Q} of every gap
+    s.KLW = o; o += 43LL * N + 16;            // ... and its forward-pass workspace
     s.CTL = o; o += FC_WORDS / 2;
     s.total = (o + 15) & ~15LL;
     return s;
@@ -100,7 +103,10 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     l.ab = o;
     l.ab_doubles = (e_end - o) / 8;
     l.chol_doubles = (e_end - l.yext) / 8;
-    l.total = e_end;
+    // the structured LLE solve (mct_kalman_lle_solve) needs 17 N + KL_STAGE doubles from yext on: more than the E-step
+    // view at N = 256
+    const int k_end = l.yext + (17 * N + KL_STAGE + 8) * 8;
+    l.total = e_end > k_end ? e_end : k_end;
     return l;
 }
 
@@ -109,6 +115,8 @@ struct TqArgs {
     int chunk;                       // raw points per chunk task
     int inflight;                    // frames started at launch; one more starts whenever a frame completes
     double zcut;                     // Gaussian truncation: entries exp(-z), z > zcut, are skipped (745.2 = exact zeros only)
+    int solver;                      // M-step solve: 0 = automatic (structured O(Nn) state-space solve without LLE, and with LLE above 64 nodes),
+                                     // 1 = dense always, 2 = structured always
     unsigned long long* qctl;        // [0] head ticket, [1] tail, [2] ints {next frame, start tickets}, [3] ints {frames done, abort flag}
     unsigned long long* qslots; unsigned qmask;
     double* fscratch; long long fstride;   // per-frame scratch
@@ -132,11 +140,6 @@ struct TqSm {
 #define TQ_TICK(slot)                                                                                   \
     if (prof && threadIdx.x == 0) { const long long tn_ = clock64(); atomicAdd(prof + (slot), (unsigned long long)(tn_ - tprev)); tprev = tn_; }
 
-// 32-byte L2 load (data written by other CTAs during this launch must not come from L1)
-__device__ __forceinline__ double4 ldcg4(const double4* p) {
-    const double2 lo = __ldcg(reinterpret_cast<const double2*>(p)), hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-    return make_double4(lo.x, lo.y, hi.x, hi.y);
-}
 
 // ------------------------------------------------------------------------------------------
 // queue
@@ -752,15 +755,46 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     // the PRUNE wave only needs node4: publish it now, do the rest of the set-up meanwhile
     tq_push(a, sm, TK_PRUNE, f, n_chunks);
 
-    // ---- G, priors, LLE products (trackdlo.cpp:225-260)
+    // ---- G, priors, LLE products (trackdlo.cpp:225-260).  The dense kernel matrix is only built when a dense solve
+    // will use it (LLE regulariser, negative alpha, or the dense solver selected); the structured solve needs the
+    // transitions of the Matern-3/2 state over the gaps h_t = s_{t+1} - s_t instead (mct_kalman_solve).
     double* gG = scr + sc.G;
     double* gHG = scr + sc.HG;
     double* gH = scr + sc.H;
     const double beta = p.beta;
-    for (int idx = tid; idx < Nn * Nn; idx += nt) {
-        const int i = idx / Nn, j = idx - i * Nn;
-        const double dd = fabs(sm.s[i] - sm.s[j]);
-        gG[idx] = 1 / (2 * beta * 2 * beta) * exp(-sqrt(2.0) * dd / beta) * (2 * dd + sqrt(2.0) * beta);
+    // 0 = structured without LLE, 2 = structured with LLE (needs the weights E themselves: not with a caller-supplied H),
+    // 1 = dense (also for a negative alpha, which the state-space form -- a square root of P1 + alpha J -- cannot take)
+    int smode = 1;
+    if (a.solver != 1 && !(n_priors > 0 && p.alpha < 0.0)) {
+        if (!p.include_lle) smode = 0;
+        else if (!Hext && (a.solver == 2 || Nn > 64)) smode = 2;
+    }
+    const bool dense = smode == 1;
+    if (tid == 0) fr.ctl[FC_DENSE] = smode;
+    if (dense) {
+        for (int idx = tid; idx < Nn * Nn; idx += nt) {
+            const int i = idx / Nn, j = idx - i * Nn;
+            const double dd = fabs(sm.s[i] - sm.s[j]);
+            gG[idx] = 1 / (2 * beta * 2 * beta) * exp(-sqrt(2.0) * dd / beta) * (2 * dd + sqrt(2.0) * beta);
+        }
+    } else {
+        // Phi(h) = e^{-ah} [[1 + ah, h], [-a^2 h, 1 - ah]],  Q(h) = P_inf - Phi P_inf Phi^T,  P_inf = sigma_f^2 diag(1, a^2)
+        double* gPhi = scr + sc.PHI;
+        double* gTr = scr + sc.KTR;
+        const double ak = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
+        for (int t = tid; t + 1 < Nn; t += nt) {
+            const double h = fabs(sm.s[t + 1] - sm.s[t]), x = ak * h, e = exp(-x);
+            const double p00 = e * (1.0 + x), p01 = e * h, p10 = -e * ak * x, p11 = e * (1.0 - x);
+            if (smode == 0) { gPhi[4 * t] = p00; gPhi[4 * t + 1] = p01; gPhi[4 * t + 2] = p10; gPhi[4 * t + 3] = p11; }
+            else {
+                const double e2 = e * e;
+                gTr[8 * t] = p00; gTr[8 * t + 1] = p01; gTr[8 * t + 2] = p10; gTr[8 * t + 3] = p11;
+                gTr[8 * t + 4] = s2f * (1.0 - e2 * (1.0 + 2.0 * x + 2.0 * x * x));
+                gTr[8 * t + 5] = s2f * 2.0 * ak * x * x * e2;
+                gTr[8 * t + 6] = s2f * ak * ak * (1.0 - e2 * (1.0 - 2.0 * x + 2.0 * x * x));
+                gTr[8 * t + 7] = 0.0;
+            }
+        }
     }
     double* gJD = scr + sc.JD;
     double* gYE = scr + sc.YEXT;
@@ -775,7 +809,22 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
             gYE[idx * 3] = priors[kk * 4 + 1]; gYE[idx * 3 + 1] = priors[kk * 4 + 2]; gYE[idx * 3 + 2] = priors[kk * 4 + 3];
         }
     }
-    if (p.include_lle) {
+    if (smode == 2) {
+        // structured LLE solve: the weights themselves (E = I - L, dense rows, zero outside i-3..i+3) and E Y0
+        double* E = scr + sc.AB;
+        for (int idx = tid; idx < Nn * Nn; idx += nt) E[idx] = 0.0;
+        __syncthreads();
+        for (int i = tid; i < Nn; i += nt) lle_row(sm.y0, Nn, i, E + (long long)i * Nn);
+        __syncthreads();
+        double* gEY = scr + sc.HY0;
+        for (int idx = tid; idx < 3 * Nn; idx += nt) {
+            const int i = idx / 3, d = idx - 3 * i;
+            const int ka = i - 3 > 0 ? i - 3 : 0, kb = i + 3 < Nn - 1 ? i + 3 : Nn - 1;
+            double sacc = 0.0;
+            for (int kk = ka; kk <= kb; kk++) sacc = fma(E[(long long)i * Nn + kk], sm.y0[3 * kk + d], sacc);
+            gEY[idx] = sacc;
+        }
+    } else if (p.include_lle) {
         if (Hext) {
             for (int idx = tid; idx < Nn * Nn; idx += nt) { const int i = idx / Nn, j = idx - i * Nn; gH[idx] = Hext[(long long)i * hstride + j]; }
         } else {
@@ -903,6 +952,8 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
     const double* gG = scr + sc.G;
     const double* gHG = scr + sc.HG;
     const int ld = Nn + 3;
+    const int smode = __ldcg(fr.ctl + FC_DENSE);
+    const bool dense = smode == 1;
     // [A|B] in shared memory only for the register-resident solvers (Nn <= 64); the blocked Cholesky keeps it in global
     // scratch (its shared workspace reuses the whole tail of the region)
     const bool ab_in_smem = Nn <= 64 && (long long)Nn * ld <= (long long)a.L.ab_doubles;
@@ -969,7 +1020,7 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
         }
     }
     // G -> shared (behind [A|B]) when it fits: used by the assembly and by T = Y0 + G W
-    const bool g_in_smem = ab_in_smem && (long long)Nn * ld + (long long)Nn * Nn <= (long long)a.L.ab_doubles;
+    const bool g_in_smem = dense && ab_in_smem && (long long)Nn * ld + (long long)Nn * Nn <= (long long)a.L.ab_doubles;
     double* sG = sm.ab + Nn * ld;
     if (g_in_smem) {
         double gv[20];                                            // Nn^2 <= 4096 <= 20 * 224
@@ -980,6 +1031,69 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
     }
     __syncthreads();
     const double sxx = sm.red[42];
+    int sing;
+    if (!dense) {
+        // ---- structured path (no LLE): D = P1 + alpha J, B = PX - P1 Y0 + alpha (Yext - Y0) (trackdlo.cpp:407-412), then the
+        // O(Nn) state-space solve for W and T = Y0 + G W.  The workspace overlays yext / jd / hy0 / [A|B]: everything read
+        // from there goes through registers first.
+        double bv[3], dv = 0.0;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int idx = tid + u * nt;
+            bv[u] = 0.0;
+            if (idx < 3 * Nn) {
+                const int i = idx / 3;
+                bv[u] = sm.px[idx] - sm.p1[i] * sm.y0[idx] + (have_priors ? p.alpha * (sm.yext[idx] - sm.y0[idx]) : 0.0);
+            }
+        }
+        if (tid < Nn) dv = sm.p1[tid] + (have_priors ? p.alpha * sm.jd[tid] : 0.0);
+        double4 ph4 = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (smode == 0 && tid + 1 < Nn) ph4 = ldcg4(reinterpret_cast<const double4*>(scr + sc.PHI) + tid);
+        __syncthreads();
+        double* kdd = sm.yext;              // [Nn]
+        double* kbt = kdd + Nn;             // [3][Nn]
+        if (smode == 2) {
+            // with LLE: B's third term -sigma2 gamma H Y0 enters as the observations yb = -sqrt(eps) E Y0 of the filter
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int idx = tid + u * nt;
+                if (idx < 3 * Nn) { const int i = idx / 3, d = idx - 3 * i; kbt[d * Nn + i] = bv[u]; }
+            }
+            if (tid < Nn) kdd[tid] = dv;
+            for (int i = tid + nt; i < Nn; i += nt) kdd[i] = sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0);
+            __syncthreads();
+            TQ_TICK(6)
+            double* kub = kbt + 3 * Nn;         // [3][Nn]
+            double* keb = kub + 3 * Nn;         // [Nn][7]
+            double* key = keb + 7 * Nn;         // [Nn][3]
+            double* kst = key + 3 * Nn;         // [KL_STAGE]
+            sing = mct_kalman_lle_solve(Nn, p.lambda * sigma2, sigma2 * p.gamma, p.beta, kdd, kbt, sm.y0, scr + sc.KTR, scr + sc.AB, scr + sc.HY0,
+                                        sm.wsol, sm.tnew, kub, keb, key, kst, scr + sc.KLW);
+            if (sing) status |= ST_SINGULAR;
+            TQ_TICK(7)
+        } else {
+        double* kphi = kbt + 3 * Nn;        // [Nn][4]
+        double* krf = kphi + 4 * Nn;        // [Nn]
+        double* kkk = krf + Nn;             // [2 Nn]
+        double* kpp = kkk + 2 * Nn;         // [2 Nn]
+        double* kam = kpp + 2 * Nn;         // [6 Nn]
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int idx = tid + u * nt;
+            if (idx < 3 * Nn) { const int i = idx / 3, d = idx - 3 * i; kbt[d * Nn + i] = bv[u]; }
+        }
+        if (tid < Nn) { kdd[tid] = dv; *reinterpret_cast<double4*>(kphi + 4 * tid) = ph4; }
+        for (int i = tid + nt; i < Nn; i += nt) {            // (Nn > nt: not reachable with Nn <= 256)
+            kdd[i] = sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0);
+            *reinterpret_cast<double4*>(kphi + 4 * i) = ldcg4(reinterpret_cast<const double4*>(scr + sc.PHI) + i);
+        }
+        __syncthreads();
+        TQ_TICK(6)
+        sing = mct_kalman_solve(Nn, p.lambda * sigma2, p.beta, kdd, kbt, kphi, sm.y0, sm.wsol, sm.tnew, krf, kkk, kpp, kam);
+        if (sing) status |= ST_SINGULAR;
+        TQ_TICK(7)
+        }
+    } else {
 
     // ---- assemble [A | B] (trackdlo.cpp:392-413).  Without LLE, A = D'G + cI (D' = diag(P1 + alpha J), c = lambda sigma2)
     // is similar to the SPD matrix D'^1/2 G D'^1/2 + cI: solve that for Z = D'^-1/2 W (rows with D' = 0 have B = 0)
@@ -1015,7 +1129,6 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
     }
     __syncthreads();
     TQ_TICK(6)
-    int sing;
     if (small) {
         double sdreg[3];
         if (spd) for (int t = 0, i = tid; t < 3 && i < 3 * Nn; t++, i += nt) sdreg[t] = sm.tnew[i / 3];
@@ -1059,6 +1172,7 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
             if (lane == 0) { sm.tnew[3 * i] = sm.y0[3 * i] + ax; sm.tnew[3 * i + 1] = sm.y0[3 * i + 1] + ay; sm.tnew[3 * i + 2] = sm.y0[3 * i + 2] + az; }
         }
     }
+    }       // dense path
     __syncthreads();
     // ---- sigma2 update and convergence test (trackdlo.cpp:418-431)
     if (warp == 0) {
