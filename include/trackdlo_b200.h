@@ -179,6 +179,36 @@ int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);
  * front of tdlo_tracking_step_batched_device. */
 int tdlo_visibility_batched_device(tdlo_ctx* ctx, const tdlo_vis_batch* batch, void* stream);
 
+/* Perception front-end that produces the tracker's input cloud (trackdlo/src/trackdlo_node.cpp:159-242), for a
+ * batch of independent frames: BGR image -> HSV -> colour band(s) (cv::inRange, or the node's four-band color_thresholding)
+ * -> AND with the grey occlusion image -> masked pixels + depth (uint16, millimetres) -> points through the projection
+ * matrix (float32, like pcl::PointXYZRGB) -> pcl::VoxelGrid centroid down-sampling -> double.  Output: the points of all
+ * frames concatenated (ascending voxel index inside a frame, PCL's order) + CSR offsets = the X / x_offsets inputs of
+ * tdlo_visibility_batched(_device) and tdlo_tracking_step_batched(_device).  The OpenCV stages are bit-exact with OpenCV
+ * (pinned against cv2 over all 2^24 colours); voxel membership and order follow PCL 1.10, the centroid is the exact mean
+ * rounded once to float32 (PCL sums in float32 in an unspecified order): see oracle/frontend.py. */
+#define TDLO_FE_EMPTY 1      /* status: no pixel of the frame passed the mask                                     */
+#define TDLO_FE_GRID 2       /* status: the voxel grid over the masked points exceeds INT_MAX cells (PCL's own bail-out)
+                                or the context's grid workspace (TDLO_OPT_VOXEL_CELLS): frame not down-sampled, 0 points */
+#define TDLO_FE_CAPACITY 4   /* status: X is full: this frame and all later ones got 0 points                      */
+typedef struct tdlo_frontend_batch {
+    int32_t n_frames;
+    int32_t rows, cols;              /* image size, the same for the whole batch                                  */
+    int32_t multi_color;             /* 0: one band [hsv_lower, hsv_upper]; 1: color_thresholding (trackdlo_node.cpp:88-119) */
+    const uint8_t* bgr;              /* [n_frames][rows][cols][3]                                                  */
+    const uint16_t* depth;           /* [n_frames][rows][cols] millimetres (trackdlo_node.cpp:216)                  */
+    const uint8_t* occlusion_bgr;    /* optional [n_frames][rows][cols][3] (the /mask_with_occlusion image, :172-180) */
+    const double* proj;              /* [n_frames][12] row-major 3x4 projection matrix (fx, fy, cx, cy are read)    */
+    int32_t hsv_lower[3], hsv_upper[3];   /* launch/trackdlo.launch:8-10 defaults: 90 90 30 / 130 255 255           */
+    double leaf_size;                /* downsample_leaf_size, 0.008                                                */
+    double* X;                       /* out [x_capacity][3]                                                         */
+    int64_t* x_offsets;              /* out [n_frames+1]                                                            */
+    int64_t x_capacity;              /* points X can hold                                                          */
+    int32_t* status;                 /* optional out [n_frames] TDLO_FE_* mask                                      */
+} tdlo_frontend_batch;
+int tdlo_point_cloud_batched(tdlo_ctx* ctx, const tdlo_frontend_batch* batch);                        /* host pointers, synchronous */
+int tdlo_point_cloud_batched_device(tdlo_ctx* ctx, const tdlo_frontend_batch* batch, void* stream);   /* device pointers, stream-ordered */
+
 /* Evaluator frame error (trackdlo/src/evaluator.cpp:233-283, 333-341): for every frame the mean distance of
  * the nodes of Y_track to the nearest segment of the polyline Y_true, symmetrised ((E1 + E2) / 2). */
 typedef struct tdlo_err_batch {
@@ -251,6 +281,8 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         (register-resident Gauss-Jordan for Nn <= 64, blocked Cholesky with FP64 tensor-core MMAs /
  *                         pivoted elimination above); 2 = structured always.  A caller-supplied H and a negative alpha
  *                         always solve densely.
+ *  TDLO_OPT_VOXEL_CELLS   cells of the front-end's voxel-grid workspace, summed over a batch (default: 2^19 per frame of the
+ *                         context, at least 2^22, at most 2^25; 32 B each).  Takes effect at the next front-end call.
  *  TDLO_OPT_WATCHDOG_MS   a CTA of the persistent kernel that waits longer than this for its next task (or for a frame's
  *                         upload) abandons the launch and the call returns TDLO_ERR_CUDA instead of hanging the caller
  *                         (default 20000; 0 = never). */
@@ -260,6 +292,7 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 #define TDLO_OPT_THREADS 5
 #define TDLO_OPT_WATCHDOG_MS 6
 #define TDLO_OPT_SOLVER 7
+#define TDLO_OPT_VOXEL_CELLS 8
 int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value);
 
 #ifdef __cplusplus

@@ -52,7 +52,8 @@ int main(void){
          offsetof(tdlo_cpd_batch, status), offsetof(tdlo_track_batch, state));
   printf("%zu %zu %zu %zu ", sizeof(tdlo_vis_batch), offsetof(tdlo_vis_batch, visible_ext_offsets),
          sizeof(tdlo_seq_batch), offsetof(tdlo_seq_batch, status_traj));
-  printf("%zu %zu\n", sizeof(tdlo_err_batch), offsetof(tdlo_err_batch, error));
+  printf("%zu %zu ", sizeof(tdlo_err_batch), offsetof(tdlo_err_batch, error));
+  printf("%zu %zu %zu %zu\n", sizeof(tdlo_frontend_batch), offsetof(tdlo_frontend_batch, status), offsetof(tdlo_cpd_batch, priors_stride), offsetof(tdlo_track_batch, packed_results));
   return 0; }
 '''
     import tempfile
@@ -68,6 +69,8 @@ int main(void){
     assert vals[8] == C.sizeof(api.VisBatchC) and vals[9] == api.VisBatchC.visible_ext_offsets.offset
     assert vals[10] == C.sizeof(api.SeqBatchC) and vals[11] == api.SeqBatchC.status_traj.offset
     assert vals[12] == C.sizeof(api.ErrBatchC) and vals[13] == api.ErrBatchC.error.offset
+    assert vals[14] == C.sizeof(api.FrontendBatchC) and vals[15] == api.FrontendBatchC.status.offset
+    assert vals[16] == api.CpdBatchC.priors_stride.offset and vals[17] == api.TrackBatchC.packed_results.offset
 
 
 def test_create_fails_loudly_without_gpu():

@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrackdlo_b200.so")
 
+FE_EMPTY, FE_GRID, FE_CAPACITY = 1, 2, 4
 ST_NOT_CONVERGED, ST_SINGULAR, ST_TOO_FEW_NODES, ST_EMPTY_CLOUD, ST_TRAVERSE_UB, ST_PRE_NOT_CONVERGED, ST_INVALID_INPUT = 1, 2, 4, 8, 16, 32, 64
 
 ABI_SYMBOLS = [
@@ -22,6 +23,7 @@ ABI_SYMBOLS = [
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
     "tdlo_last_launch_info", "tdlo_synchronize", "tdlo_profile_phases", "tdlo_set_option",
     "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences", "tdlo_tracking_error_batched", "tdlo_tracking_error_batched_device",
+    "tdlo_point_cloud_batched", "tdlo_point_cloud_batched_device",
 ]
 
 
@@ -65,6 +67,13 @@ class VisBatchC(C.Structure):
 class ErrBatchC(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("n_track", C.c_int32), ("n_true", C.c_int32), ("reserved", C.c_int32),
                 ("Y_track", C.c_void_p), ("Y_true", C.c_void_p), ("error", C.c_void_p)]
+
+
+class FrontendBatchC(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("multi_color", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("bgr", "depth", "occlusion_bgr", "proj")] + \
+               [("hsv_lower", C.c_int32 * 3), ("hsv_upper", C.c_int32 * 3), ("leaf_size", C.c_double)] + \
+               [("X", C.c_void_p), ("x_offsets", C.c_void_p), ("x_capacity", C.c_int64), ("status", C.c_void_p)]
 
 
 class SeqBatchC(C.Structure):
@@ -143,6 +152,8 @@ def load_library():
         lib.tdlo_tracking_error_batched.argtypes = [C.c_void_p, C.POINTER(ErrBatchC)]
         lib.tdlo_tracking_error_batched_device.argtypes = [C.c_void_p, C.POINTER(ErrBatchC), C.c_void_p]
         lib.tdlo_track_sequences.argtypes = [C.c_void_p, C.POINTER(SeqBatchC), C.POINTER(TrackParamsC)]
+        lib.tdlo_point_cloud_batched.argtypes = [C.c_void_p, C.POINTER(FrontendBatchC)]
+        lib.tdlo_point_cloud_batched_device.argtypes = [C.c_void_p, C.POINTER(FrontendBatchC), C.c_void_p]
         lib.tdlo_visibility_batched.argtypes = [C.c_void_p, C.POINTER(VisBatchC)]
         lib.tdlo_visibility_batched_device.argtypes = [C.c_void_p, C.POINTER(VisBatchC), C.c_void_p]
         _lib = lib
@@ -192,7 +203,7 @@ class Context:
         """tdlo_synchronize: waits for the last *_device call; raises if the kernel's watchdog gave up."""
         self._check(self.lib.tdlo_synchronize(self.h), "tdlo_synchronize")
 
-    OPTIONS = {"chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5, "watchdog_ms": 6, "solver": 7}
+    OPTIONS = {"chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5, "watchdog_ms": 6, "solver": 7, "voxel_cells": 8}
 
     def set_option(self, name, value):
         """tdlo_set_option: chunk_points, truncation, inflight, threads, watchdog_ms."""
@@ -273,6 +284,27 @@ class Context:
         b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo))
         self._check(self.lib.tdlo_visibility_batched(self.h, C.byref(b)), "tdlo_visibility_batched")
         return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo)
+
+    # ------------------------------------------------------------------ perception front-end (trackdlo_node.cpp:159-242)
+    def point_cloud_batched(self, bgr, depth, proj, hsv_lower=(90, 90, 30), hsv_upper=(130, 255, 255), multi_color=False,
+                            occlusion_bgr=None, leaf_size=0.008, x_capacity=None):
+        """bgr [F,H,W,3] uint8, depth [F,H,W] uint16 (mm), proj [F,3,4]  ->  dict(X [sum Mp,3], x_offsets [F+1], status [F])."""
+        bgr = _np(bgr, np.uint8); F, H, W = bgr.shape[0], bgr.shape[1], bgr.shape[2]
+        depth = _np(depth, np.uint16, (F, H, W)); proj = _np(proj, np.float64, (F, 12))
+        occ = None if occlusion_bgr is None else _np(occlusion_bgr, np.uint8, (F, H, W, 3))
+        cap = int(x_capacity if x_capacity is not None else F * H * W)
+        X = np.zeros((cap, 3)); xo = np.zeros(F + 1, np.int64); st = np.zeros(F, np.int32)
+        b = FrontendBatchC(F, H, W, int(multi_color), _ptr(bgr), _ptr(depth), _ptr(occ), _ptr(proj), (C.c_int32 * 3)(*hsv_lower),
+                           (C.c_int32 * 3)(*hsv_upper), leaf_size, _ptr(X), _ptr(xo), cap, _ptr(st))
+        self._check(self.lib.tdlo_point_cloud_batched(self.h, C.byref(b)), "tdlo_point_cloud_batched")
+        return dict(X=X[:xo[F]].copy(), x_offsets=xo, status=st)
+
+    def point_cloud_batched_raw(self, batch: "FrontendBatchC", device=True, stream=0):
+        if device:
+            rc = self.lib.tdlo_point_cloud_batched_device(self.h, C.byref(batch), C.c_void_p(stream))
+        else:
+            rc = self.lib.tdlo_point_cloud_batched(self.h, C.byref(batch))
+        self._check(rc, "tdlo_point_cloud_batched")
 
     # ------------------------------------------------------------------ evaluator frame error (evaluator.cpp:233-283, 333-341)
     def tracking_error_batched(self, Y_track, Y_true):

@@ -4,6 +4,7 @@
 #include "../../include/trackdlo_b200.h"
 #include "tdlo_taskq.cuh"
 #include "tdlo_visibility.cuh"
+#include "tdlo_frontend.cuh"
 
 #include <vector>
 
@@ -41,6 +42,11 @@ struct tdlo_ctx {
     // visibility front-end workspace
     unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr; long long* d_vslice = nullptr;
     double* d_vdmin = nullptr; int *d_vvis = nullptr, *d_vext = nullptr;
+    // perception front-end workspace (tdlo_frontend.cuh)
+    long long fe_cells_opt = 0, fe_cells_cap = 0, fe_tiles_cap = 0;
+    int *d_fe_bbox = nullptr, *d_fe_dims = nullptr, *d_fe_tilecnt = nullptr, *d_fe_status = nullptr;
+    long long *d_fe_cellbase = nullptr, *d_fe_tilebase = nullptr, *d_fe_acc = nullptr, *d_fe_tileoff = nullptr;
+    unsigned char *d_fe_bgr = nullptr, *d_fe_occl = nullptr; unsigned short* d_fe_depth = nullptr; double* d_fe_proj = nullptr; long long fe_pix_cap = 0;
     // task-queue engine (tdlo_taskq.cuh)
     int tq_chunk = 0;               // raw points per chunk task (0 = automatic: 1024, or 2048 / 4096 for large batches)
     int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
@@ -88,7 +94,9 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
                     ctx->d_Xc, ctx->d_bkt, ctx->d_exp_tab, ctx->d_prof_buf,
                     ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph,
-                    ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext};
+                    ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext,
+                    ctx->d_fe_bbox, ctx->d_fe_dims, ctx->d_fe_tilecnt, ctx->d_fe_status, ctx->d_fe_cellbase, ctx->d_fe_tilebase, ctx->d_fe_acc,
+                    ctx->d_fe_tileoff, ctx->d_fe_bgr, ctx->d_fe_occl, ctx->d_fe_depth, ctx->d_fe_proj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -625,6 +633,113 @@ extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// perception front-end (tdlo_frontend.cuh)
+// ---------------------------------------------------------------------------------------------
+static int fe_workspace(tdlo_ctx* ctx) {
+    long long want = ctx->fe_cells_opt;
+    if (want <= 0) want = std::min<long long>(1LL << 25, std::max<long long>(1LL << 22, (long long)ctx->max_frames << 19));
+    if (ctx->d_fe_acc && ctx->fe_cells_cap == want) return TDLO_OK;
+    CK(cudaDeviceSynchronize());
+    void* old[] = {ctx->d_fe_bbox, ctx->d_fe_dims, ctx->d_fe_tilecnt, ctx->d_fe_status, ctx->d_fe_cellbase, ctx->d_fe_tilebase, ctx->d_fe_acc, ctx->d_fe_tileoff};
+    for (void* p : old) if (p) cudaFree(p);
+    ctx->d_fe_bbox = ctx->d_fe_dims = ctx->d_fe_tilecnt = ctx->d_fe_status = nullptr;
+    ctx->d_fe_cellbase = ctx->d_fe_tilebase = ctx->d_fe_acc = ctx->d_fe_tileoff = nullptr;
+    const size_t F = ctx->max_frames;
+    ctx->fe_cells_cap = want;
+    ctx->fe_tiles_cap = want / FE_TILE + (long long)F + 1;
+    CK(dalloc(&ctx->d_fe_bbox, F * 6)); CK(dalloc(&ctx->d_fe_dims, F * 4)); CK(dalloc(&ctx->d_fe_status, F));
+    CK(dalloc(&ctx->d_fe_cellbase, F + 1)); CK(dalloc(&ctx->d_fe_tilebase, F + 1));
+    CK(dalloc(&ctx->d_fe_acc, (size_t)want * 4));
+    CK(dalloc(&ctx->d_fe_tilecnt, (size_t)ctx->fe_tiles_cap)); CK(dalloc(&ctx->d_fe_tileoff, (size_t)ctx->fe_tiles_cap));
+    return TDLO_OK;
+}
+
+static int fe_check(tdlo_ctx* ctx, const tdlo_frontend_batch* b) {
+    if (!b) return fail(ctx, TDLO_ERR_INVALID, "null batch");
+    if (b->n_frames < 0 || b->n_frames > ctx->max_frames) return fail(ctx, TDLO_ERR_INVALID, "n_frames %d exceeds capacity %d", b->n_frames, ctx->max_frames);
+    if (b->rows < 1 || b->cols < 1 || (long long)b->rows * b->cols > (1LL << 30)) return fail(ctx, TDLO_ERR_INVALID, "bad image size %d x %d", b->rows, b->cols);
+    if (!b->bgr || !b->depth || !b->proj || !b->X || !b->x_offsets) return fail(ctx, TDLO_ERR_INVALID, "bgr, depth, proj, X, x_offsets are required");
+    if (!(b->leaf_size > 0.0)) return fail(ctx, TDLO_ERR_INVALID, "leaf_size must be > 0 (reference: 0.008)");
+    if (b->x_capacity < 0) return fail(ctx, TDLO_ERR_INVALID, "x_capacity must be >= 0");
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_point_cloud_batched_device(tdlo_ctx* ctx, const tdlo_frontend_batch* b, void* stream_) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = fe_check(ctx, b);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (b->n_frames == 0) return TDLO_OK;
+    rc = fe_workspace(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_frames = b->n_frames; a.rows = b->rows; a.cols = b->cols; a.multi = b->multi_color;
+    a.bgr = b->bgr; a.depth = b->depth; a.occl = b->occlusion_bgr; a.proj = b->proj;
+    for (int i = 0; i < 3; i++) { a.lo[i] = b->hsv_lower[i]; a.hi[i] = b->hsv_upper[i]; }
+    a.inv_leaf = 1.0f / (float)b->leaf_size;                 // PCL: inverse_leaf_size_ = 1 / leaf_size_ in float
+    a.bbox = ctx->d_fe_bbox; a.dims = ctx->d_fe_dims; a.cell_base = ctx->d_fe_cellbase; a.tile_base = ctx->d_fe_tilebase;
+    a.acc = ctx->d_fe_acc; a.cells_cap = ctx->fe_cells_cap; a.tile_cnt = ctx->d_fe_tilecnt; a.tile_off = ctx->d_fe_tileoff; a.tiles_cap = ctx->fe_tiles_cap;
+    a.X = b->X; a.x_off = reinterpret_cast<long long*>(b->x_offsets); a.x_cap = b->x_capacity; a.status = b->status;
+    const long long np = (long long)b->rows * b->cols;
+    const int gx = (int)std::min<long long>((np + 255) / 256, std::max(1, ctx->sm_count * 8 / std::max(1, std::min(b->n_frames, 8))));
+    const dim3 gpix(gx, b->n_frames);
+    const int gcell = ctx->sm_count * 8;
+    fe_init_kernel<<<(b->n_frames * 6 + 255) / 256, 256, 0, stream>>>(a);
+    fe_bbox_kernel<<<gpix, 256, 0, stream>>>(a);
+    fe_layout_kernel<<<1, 32, 0, stream>>>(a);
+    fe_clear_kernel<<<gcell, 256, 0, stream>>>(a);
+    fe_accum_kernel<<<gpix, 256, 0, stream>>>(a);
+    fe_count_kernel<<<gcell, 256, 0, stream>>>(a);
+    fe_scan_kernel<<<1, 256, 0, stream>>>(a);
+    fe_emit_kernel<<<gcell, 256, 0, stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->info[5] = 8;
+    return TDLO_OK;
+}
+
+extern "C" int tdlo_point_cloud_batched(tdlo_ctx* ctx, const tdlo_frontend_batch* b) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    int rc = fe_check(ctx, b);
+    if (rc) return rc;
+    if (b->n_frames == 0) return TDLO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t F = b->n_frames;
+    const long long np = (long long)b->rows * b->cols;
+    if ((long long)F * np > ctx->fe_pix_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_fe_bgr) cudaFree(ctx->d_fe_bgr);
+        if (ctx->d_fe_occl) cudaFree(ctx->d_fe_occl);
+        if (ctx->d_fe_depth) cudaFree(ctx->d_fe_depth);
+        ctx->d_fe_bgr = ctx->d_fe_occl = nullptr; ctx->d_fe_depth = nullptr; ctx->fe_pix_cap = 0;
+        const size_t cap = (size_t)ctx->max_frames * np;
+        CK(dalloc(&ctx->d_fe_bgr, cap * 3)); CK(dalloc(&ctx->d_fe_occl, cap * 3)); CK(dalloc(&ctx->d_fe_depth, cap));
+        ctx->fe_pix_cap = (long long)cap;
+    }
+    if (!ctx->d_fe_proj) CK(dalloc(&ctx->d_fe_proj, (size_t)ctx->max_frames * 12));
+    rc = fe_workspace(ctx);
+    if (rc) return rc;
+    H2D(ctx->d_fe_bgr, b->bgr, F * np * 3);
+    H2D(ctx->d_fe_depth, b->depth, F * np * sizeof(unsigned short));
+    if (b->occlusion_bgr) H2D(ctx->d_fe_occl, b->occlusion_bgr, F * np * 3);
+    H2D(ctx->d_fe_proj, b->proj, F * 12 * sizeof(double));
+    tdlo_frontend_batch d = *b;
+    d.bgr = ctx->d_fe_bgr; d.depth = ctx->d_fe_depth; d.occlusion_bgr = b->occlusion_bgr ? ctx->d_fe_occl : nullptr; d.proj = ctx->d_fe_proj;
+    d.X = ctx->d_X; d.x_offsets = reinterpret_cast<int64_t*>(ctx->d_xoff);
+    d.x_capacity = std::min<long long>(b->x_capacity, ctx->max_points);
+    d.status = ctx->d_fe_status;
+    rc = tdlo_point_cloud_batched_device(ctx, &d, ctx->stream);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    D2H(b->x_offsets, ctx->d_xoff, (F + 1) * sizeof(long long));
+    if (b->status) D2H(b->status, ctx->d_fe_status, F * sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long total = b->x_offsets[F];
+    if (total > 0) CK(cudaMemcpy(b->X, ctx->d_X, (size_t)total * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // evaluator frame error
 // ---------------------------------------------------------------------------------------------
 static int err_check(tdlo_ctx* ctx, const tdlo_err_batch* b) {
@@ -758,6 +873,9 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
         case TDLO_OPT_SOLVER:
             if (value != 0.0 && value != 1.0 && value != 2.0) return fail(ctx, TDLO_ERR_INVALID, "solver must be 0 (automatic), 1 (dense) or 2 (structured)");
             ctx->tq_solver = (int)value; return TDLO_OK;
+        case TDLO_OPT_VOXEL_CELLS:
+            if (value != 0.0 && (value < 4096.0 || value > (double)(1LL << 31))) return fail(ctx, TDLO_ERR_INVALID, "voxel cells must be 0 (automatic) or in [4096, 2^31]");
+            ctx->fe_cells_opt = (long long)value; return TDLO_OK;
         case TDLO_OPT_WATCHDOG_MS:
             if (!(value >= 0.0)) return fail(ctx, TDLO_ERR_INVALID, "watchdog must be >= 0 ms (0 = off)");
             ctx->watchdog_ms = value; return TDLO_OK;

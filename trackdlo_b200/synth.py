@@ -91,3 +91,54 @@ def make_batch(n_frames, first_frame=0, **kw):
         vis=np.concatenate([f["vis"] for f in frames]).astype(np.int32), vis_offsets=voff,
         vis_ext=np.concatenate([f["vis_ext"] for f in frames]).astype(np.int32), vis_ext_offsets=eoff,
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# camera frames for the perception front-end (trackdlo_node.cpp:159-242): a blue DLO on a grey table
+# ---------------------------------------------------------------------------------------------
+def camera_matrix(rows=720, cols=1280, f=915.0):
+    """3x4 projection matrix of a RealSense-like colour camera (launch/realsense_node.launch: 1280x720)."""
+    P = np.zeros((3, 4)); P[0, 0] = f; P[1, 1] = f; P[0, 2] = cols / 2.0 - 0.5; P[1, 2] = rows / 2.0 - 0.5; P[2, 2] = 1.0
+    return P
+
+
+def render_frame(frame_idx, rows=720, cols=1280, width_px=7, occl_windows=None, occlusion_box=None, dlo_bgr=(200, 70, 20), depth_holes=0.01):
+    """Synthetic colour + depth image of the observed curve of frame `frame_idx`: dict(bgr [H,W,3] uint8, depth [H,W] uint16 mm,
+    proj [3,4], occlusion_bgr [H,W,3] or None).  The DLO is drawn as discs of `width_px` pixels around the projections of a dense
+    sampling of observed_curve; `depth_holes` of its pixels get depth 0 (invalid RealSense returns, kept by the reference);
+    occlusion_box = (i0, i1, j0, j1) blacks a rectangle of the occlusion image (utils/simulate_occlusion.py)."""
+    rng = np.random.default_rng(SEED0 + 7919 * frame_idx)
+    P = camera_matrix(rows, cols, f=915.0 * cols / 1280.0)
+    bgr = np.empty((rows, cols, 3), np.uint8)
+    bgr[:] = (118, 120, 123)                                     # table: low saturation
+    bgr = np.clip(bgr.astype(np.int16) + rng.integers(-6, 7, bgr.shape), 0, 255).astype(np.uint8)
+    depth = np.full((rows, cols), 1100, np.uint16)
+    t = np.linspace(0.0, 1.0, 6000)
+    if occl_windows:
+        keep = np.ones(len(t), bool)
+        for (t0, t1) in occl_windows:
+            keep &= ~((t >= t0) & (t <= t1))
+        t = t[keep]
+    pts = observed_curve(t, frame_idx)
+    u = P[0, 0] * pts[:, 0] / pts[:, 2] + P[0, 2]; v = P[1, 1] * pts[:, 1] / pts[:, 2] + P[1, 2]
+    r = width_px // 2
+    zbuf = np.full((rows, cols), np.inf)
+    for di in range(-r, r + 1):
+        for dj in range(-r, r + 1):
+            if di * di + dj * dj > r * r:
+                continue
+            ii = np.rint(v).astype(int) + di; jj = np.rint(u).astype(int) + dj
+            ok = (ii >= 0) & (ii < rows) & (jj >= 0) & (jj < cols)
+            np.minimum.at(zbuf, (ii[ok], jj[ok]), pts[ok, 2])
+    on = np.isfinite(zbuf)
+    col = np.asarray(dlo_bgr, np.int16)
+    bgr[on] = np.clip(col + rng.integers(-12, 13, (int(on.sum()), 3)), 0, 255).astype(np.uint8)
+    depth[on] = np.rint(zbuf[on] * 1000.0 + rng.normal(0.0, 1.0, int(on.sum()))).astype(np.uint16)
+    holes = on & (rng.random((rows, cols)) < depth_holes)
+    depth[holes] = 0
+    occ = None
+    if occlusion_box is not None:
+        occ = np.full((rows, cols, 3), 255, np.uint8)
+        i0, i1, j0, j1 = occlusion_box
+        occ[i0:i1, j0:j1] = 0
+    return dict(bgr=bgr, depth=depth, proj=P, occlusion_bgr=occ)
