@@ -221,6 +221,9 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
         if (est / 4096 >= 2 * slots) chunk = 4096;     // latency is on the frame's critical path
         if (est < 512 * slots) chunk = 512;
         if (est < 256 * slots) chunk = 256;
+        // (a frame that fits ONE chunk -- at most 256 points: one 32-point tile per warp -- is run inline by the CTA that
+        // owns it, without any queue traffic; larger single-CTA chunks lose: a tile is a ~9 k-cycle dependent chain for
+        // its warp, so 2000 points on one CTA take 4x longer than spread over eight -- measured, profiles/r2_production_regime.jsonl)
     }
     // ---- workspace (allocated on first use / when the chunk size changes)
     if (!ctx->d_fscratch || ctx->tq_alloc_chunk != chunk) {

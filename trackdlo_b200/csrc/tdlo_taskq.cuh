@@ -638,7 +638,7 @@ __device__ __forceinline__ double* tq_pri(const TqArgs& a, const TqFrame& fr) {
 // start_call: set-up of one cpd_lle call (trackdlo.cpp:197-260) + publication of its PRUNE wave.
 // Returns the next action for this CTA.
 // ------------------------------------------------------------------------------------------
-static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int stage) {
+static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr, int stage, unsigned long long& local_wd) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const KArgs& k = a.k;
     const CpdP& p = tq_params(a, stage);
@@ -752,8 +752,11 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     }
     __syncthreads();
     for (int j = tid; j < Nn; j += nt) gS[j] = sm.s[j];
-    // the PRUNE wave only needs node4: publish it now, do the rest of the set-up meanwhile
-    tq_push(a, sm, TK_PRUNE, f, n_chunks);
+    // the PRUNE wave only needs node4: publish it now, do the rest of the set-up meanwhile.  A frame of a single chunk (a
+    // live sequence with a few hundred to a few thousand points) never goes through the queue: this CTA runs the chunk
+    // itself right after the set-up (one CTA owns the whole frame, no ticket / publish / pop latency per wave).
+    if (n_chunks == 1) local_wd = tq_word(0, a.qmask, TK_PRUNE, f, 0);
+    else tq_push(a, sm, TK_PRUNE, f, n_chunks);
 
     // ---- G, priors, LLE products (trackdlo.cpp:225-260).  The dense kernel matrix is only built when a dense solve
     // will use it (LLE regulariser, negative alpha, or the dense solver selected); the structured solve needs the
@@ -889,7 +892,7 @@ static __device__ int tq_after_prune(const TqArgs& a, TqSm& sm, const TqFrame& f
 // ------------------------------------------------------------------------------------------
 // begin_iter: per-iteration header (scaled arc lengths, outlier constant) and the next wave
 // ------------------------------------------------------------------------------------------
-static __device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+static __device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr, unsigned long long& local_wd) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const int use_vis = __ldcg(fr.ctl + FC_USEVIS);
@@ -907,12 +910,13 @@ static __device__ int tq_begin_iter(const TqArgs& a, TqSm& sm, const TqFrame& fr
         fr.ctl[FC_PHASE] = use_vis ? TK_DMIN : TK_ESTEP;
         fr.ctl[FC_PENDING] = n_chunks;
     }
-    tq_push(a, sm, use_vis ? TK_DMIN : TK_ESTEP, fr.f, n_chunks);
+    if (n_chunks == 1) { __syncthreads(); local_wd = tq_word(0, a.qmask, use_vis ? TK_DMIN : TK_ESTEP, fr.f, 0); }
+    else tq_push(a, sm, use_vis ? TK_DMIN : TK_ESTEP, fr.f, n_chunks);
     return A_NONE;
 }
 
 // after_dmin: visibility weights (trackdlo.cpp:291-293, 358-375), then the E-step wave
-static __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr) {
+static __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr, unsigned long long& local_wd) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int stage = __ldcg(fr.ctl + FC_STAGE), Nn = __ldcg(fr.ctl + FC_NN), n_chunks = __ldcg(fr.ctl + FC_NCHUNK);
     const CpdP& p = tq_params(a, stage);
@@ -931,7 +935,8 @@ static __device__ int tq_after_dmin(const TqArgs& a, TqSm& sm, const TqFrame& fr
     double* gVW = fr.scr + fr.sc.VW;
     for (int j = tid; j < Nn; j += nt) gVW[j] = sm.vw[j] / tot;      // trackdlo.cpp:372
     if (tid == 0) { fr.ctl[FC_PHASE] = TK_ESTEP; fr.ctl[FC_PENDING] = n_chunks; }
-    tq_push(a, sm, TK_ESTEP, fr.f, n_chunks);
+    if (n_chunks == 1) { __syncthreads(); local_wd = tq_word(0, a.qmask, TK_ESTEP, fr.f, 0); }
+    else tq_push(a, sm, TK_ESTEP, fr.f, n_chunks);
     return A_NONE;
 }
 
@@ -1377,6 +1382,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
     unsigned long long* prof = a.k.prof;
     long long tprev = prof ? clock64() : 0;
     int action = A_NONE, af = 0, astage = 0;
+    unsigned long long local_wd = 0;       // a task this CTA hands to itself (single-chunk frames)
     // The first `inflight` CTAs to get here each CLAIM a frame from the shared counter (not "frame = blockIdx.x"): a CTA
     // that becomes resident late (MPS, a debugger, a shared GPU) can then never restart a frame somebody else already ran.
     if (tid == 0) {
@@ -1393,10 +1399,10 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
         while (action != A_NONE) {
             const TqFrame fr = tq_frame(a, af);
             switch (action) {
-                case A_START_CALL: action = tq_start_call(a, sm, fr, astage); TQ_TICK(4) break;
+                case A_START_CALL: action = tq_start_call(a, sm, fr, astage, local_wd); TQ_TICK(4) break;
                 case A_AFTER_PRUNE: action = tq_after_prune(a, sm, fr); TQ_TICK(5) break;
-                case A_BEGIN_ITER: action = tq_begin_iter(a, sm, fr); TQ_TICK(5) break;
-                case A_AFTER_DMIN: action = tq_after_dmin(a, sm, fr); TQ_TICK(5) break;
+                case A_BEGIN_ITER: action = tq_begin_iter(a, sm, fr, local_wd); TQ_TICK(5) break;
+                case A_AFTER_DMIN: action = tq_after_dmin(a, sm, fr, local_wd); TQ_TICK(5) break;
                 case A_MSTEP: action = tq_mstep(a, sm, fr, tprev); break;
                 case A_FINISH_CALL: action = tq_finish_call(a, sm, fr, astage); TQ_TICK(9) break;
                 case A_FRAME_DONE: {
@@ -1421,7 +1427,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
             }
         }
         // ---- next task
-        const unsigned long long wd = tq_pop(a, sm);
+        const unsigned long long wd = local_wd ? local_wd : tq_pop(a, sm);
+        local_wd = 0;
         TQ_TICK(0)
         const int type = (int)((wd >> 37) & 7), f = (int)((wd >> 20) & 0x1ffff), c = (int)(wd & 0xfffff);
         if (type == TK_EXIT) break;
