@@ -9,6 +9,8 @@ import sys
 
 rep = sys.argv[1]
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 45
+BY_SAMPLES = len(sys.argv) > 3 and sys.argv[3] == "samples"      # sort by stall samples instead of executed instructions
+FILTER = sys.argv[4] if len(sys.argv) > 4 else ""                # only lines of files whose name contains this
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 fname = "?"
@@ -51,6 +53,7 @@ print("opcode mix: " + "  ".join(f"{o}:{100*c/tot_i:.1f}%" for o, c in ops_tot.m
 f64 = sum(c for o, c in ops_tot.items() if o in ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX"))
 print(f"FP64-pipe instructions (DFMA/DADD/DMUL/DSETP/DMNMX): {f64:.4g} = {100*f64/tot_i:.1f}%")
 print(f"{'file:line':>24s} {'inst%':>6s} {'smpl%':>6s}  top ops | source")
-for (f, l, s), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:N]:
+rows_ = [kv for kv in agg.items() if FILTER in kv[0][0]]
+for (f, l, s), a in sorted(rows_, key=lambda kv: -kv[1][1 if BY_SAMPLES else 0])[:N]:
     ops = " ".join(f"{o}:{100*c/max(a[0],1):.0f}" for o, c in a[2].most_common(4))
     print(f"{f[-18:]+':'+l:>24s} {100*a[0]/max(tot_i,1):6.2f} {100*a[1]/max(tot_s,1):6.2f}  {ops:36s} | {s}")

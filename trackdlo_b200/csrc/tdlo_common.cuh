@@ -758,6 +758,7 @@ static __device__ int mct_kalman_solve(int n, double c, double beta, double* __r
             d = dn; y = yn; p00 = q00; p01 = q01; p10 = q10; p11 = q11;
         }
         // backward: r <- Phi_t^T r ;  u_t = v_t / F_t - k_t . r ;  r <- r + h u ;  smoothed f_t = a_t[0] + P_t[0,:] . r
+        __syncwarp(0x7u);                                 // lanes 1, 2 read what lane 0 stored (rF, kk, pp)
         double r0 = 0.0, r1 = 0.0;
         int t = n - 1;
         double vt = v[t], rf = rF[t], kt0 = kk[2 * t], kt1 = kk[2 * t + 1], pt0 = pp[2 * t], pt1 = pp[2 * t + 1], at = a0s[t], dt = dd[t];
@@ -794,44 +795,17 @@ static __device__ int mct_kalman_solve(int n, double c, double beta, double* __r
 // (scripts/kalman_solver_check.py, profiles/r2_kalman_solver_accuracy.txt): ~10x more accurate than LAPACK's dense solve.
 // It replaces, at Nn = 200, a 200 x 200 pivoted elimination per EM iteration (and the H G, H Y0 products per call).
 //
-// Lanes 0..2 of warp 0 run the filter, one right-hand-side column each, the 8 x 8 covariance (upper triangle, 36
-// registers) redundantly.  Forward results go to a global workspace (gws, 43 n doubles); the backward pass stages them
-// back through shared memory in blocks of KL_BLK nodes (all threads copy, three lanes compute).
+// Forward filter: one warp, lane i < 8 owns row i of the 8 x 8 covariance, lanes 8..10 the mean vectors of the three
+// right-hand sides (an observation costs one 8-value shuffle gather and ~30 FP64 instructions per lane).  Its results go
+// to a global workspace (gws, 43 n doubles); the backward (adjoint) pass stages them back through shared memory in
+// blocks of KL_BLK nodes (all threads copy, three lanes compute, one right-hand side each).
 //   in (shared): sd[n] = D_t (overwritten with d_t), ya[3][n] (overwritten: the smoothing errors uA end up there), y0[n][3]
 //   in (global): tr[n][8] = {Phi00, Phi01, Phi10, Phi11, Q00, Q01, Q11, -} of the gap t -> t+1, Eg[n][n] = E, ey0[n][3] = E Y0
-//   out (shared): wsol[n][3], tnew[n][3];  ws (shared): ub[3][n], eb[n][7] (band of E), ey[n][3], stage[KL_STAGE]
+//   out (shared): wsol[n][3], tnew[n][3];  ws (shared): ub[3][n], eb[n][7] (band of E), ey[n][3], stage[KL_STAGE] (16-byte aligned);
+//   gws (global): 43 n + 64 doubles
 // ------------------------------------------------------------------------------------------
 constexpr int KL_BLK = 32;
-constexpr int KL_STAGE = KL_BLK * 17 + (KL_BLK + 4) * 17 + KL_BLK * 6 + (KL_BLK + 4) * 3;
-#define KL_P(i, j) P[(i) * 8 - ((i) * ((i) - 1)) / 2 + ((j) - (i))]      /* upper triangle, i <= j, compile-time indices */
-
-struct KlObs { double r, v; };
-// one scalar observation h . x = y (+ noise c): updates (P, m), returns 1/F and the innovation, leaves the gain in k[]
-__device__ __forceinline__ KlObs kl_observe(double (&P)[36], double (&m)[8], const double (&h)[8], double y, double c, double (&k)[8], int& bad) {
-    double g[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc = fma(i <= j ? KL_P(i, j) : KL_P(j, i), h[j], acc);
-        g[i] = acc;
-    }
-    double F = c, hm = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { F = fma(h[i], g[i], F); hm = fma(h[i], m[i], hm); }
-    const double r = rcp_fast(F);
-    bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
-    const double v = y - hm;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { k[i] = g[i] * r; m[i] = fma(k[i], v, m[i]); }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = i; j < 8; j++) KL_P(i, j) = fma(-k[i], g[j], KL_P(i, j));
-    KlObs o; o.r = r; o.v = v;
-    return o;
-}
-
+constexpr int KL_STAGE = KL_BLK * 17 + (KL_BLK + 4) * 17 + KL_BLK * 6 + (KL_BLK + 4) * 3;      // >= 64 + 256 doubles (forward exchange buffers)
 static __device__ int mct_kalman_lle_solve(int n, double c, double eps, double beta, double* __restrict__ sd, double* __restrict__ ya,
                                            const double* __restrict__ y0, const double* __restrict__ tr, const double* __restrict__ Eg,
                                            const double* __restrict__ ey0, double* __restrict__ wsol, double* __restrict__ tnew,
@@ -856,97 +830,131 @@ static __device__ int mct_kalman_lle_solve(int n, double c, double eps, double b
     double* gB = gws + 17 * n;             // [n][17]: 1/F, k[8], h[8]      (indexed by LLE row)
     double* gC = gws + 34 * n;             // per column: vA[3][n], m0[3][n], vB[3][n]
     int bad = 0;
-    if (tid < 3) {
-        const int col = tid;
+    if (tid < 32) {
+        // ---- forward filter, ONE WARP: lane i < 8 owns row i of the 8 x 8 covariance, lane 8 + c the mean vector of
+        // right-hand side c.  Both kinds of lane run the same instructions on their 8 registers `row[]`:
+        //   observation h:  dot = row . h   (= (P h)_i on a covariance lane, = h . m on a mean lane)
+        //                   g[j] = (P h)_j of lanes 0..7,  F = h . g + c,  r = 1 / F
+        //                   row[j] += g[j] * beta,   beta = -dot r (covariance: P -= k g^T)  or  (y - dot) r (mean: m += k v)
+        //   transition:     row <- T row on every lane (columns of P, entries of m), then the covariance lanes exchange
+        //                   rows (P <- T P) and add Q.
+        // Lanes exchange through shared memory + __syncwarp, not shuffles: this code sits under thread-dependent control
+        // flow, where ptxas wraps every shuffle into a WARPSYNC.COLLECTIVE call (measured: 4240 cycles per node with ~80
+        // shuffles per node, 2400 this way; profiles/r2_kalman_lle_tuning.txt).  Roles act through selects, idle lanes
+        // store to a dummy slot.  What is left is ~350 mostly dependent instructions per node on a single in-order warp.
+        const int lane = tid;
+        const bool cov = lane < 8, mean = lane >= 8 && lane < 11;
+        const int col = mean ? lane - 8 : 0;
         const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
-        double P[36], m[8], k[8];
+        double* xg = stage;                 // [2][32] (P h) of the covariance lanes, double-buffered
+        double* xr = stage + 64;            // [32][8] rows of P T^T during a transition (lanes >= 8: scratch)
+        double* dummy = gws + 43 * n + lane;
+        double row[8];
 #pragma unroll
-        for (int i = 0; i < 36; i++) P[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) m[i] = 0.0;
-        KL_P(0, 0) = s2f; KL_P(1, 1) = a * a * s2f;
+        for (int jj = 0; jj < 8; jj++) row[jj] = 0.0;
+        row[0] = lane == 0 ? s2f : 0.0;
+        row[1] = lane == 1 ? a * a * s2f : 0.0;
+        int xb = 0;
+        const int src = (lane >= 3 && lane < 8) ? lane - 1 : 0;
         double4 phn = ldcg4(reinterpret_cast<const double4*>(tr)), qqn = ldcg4(reinterpret_cast<const double4*>(tr + 4));
         for (int t = 0; t < n; t++) {
             const double4 ph = phn, qq = qqn;             // transition t-1 -> t (loaded one node ahead)
-            if (t + 1 < n) { phn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * t)); qqn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * t + 4)); }
-            if (t > 0) {
-                // ---- transition t-1 -> t: lags shift down, (f, f') <- Phi (f, f') + w
-#pragma unroll
-                for (int i = 7; i >= 3; i--)
-#pragma unroll
-                    for (int j = 7; j >= i; j--) KL_P(i, j) = KL_P(i - 1, j - 1);
-#pragma unroll
-                for (int j = 7; j >= 3; j--) KL_P(2, j) = KL_P(0, j - 1);
-                KL_P(2, 2) = KL_P(0, 0);
-#pragma unroll
-                for (int j = 7; j >= 3; j--) KL_P(1, j) = KL_P(1, j - 1);
-                KL_P(1, 2) = KL_P(0, 1);
-#pragma unroll
-                for (int j = 7; j >= 3; j--) KL_P(0, j) = KL_P(0, j - 1);
-                KL_P(0, 2) = KL_P(0, 0);
-#pragma unroll
-                for (int j = 2; j < 8; j++) {
-                    const double t0 = KL_P(0, j), t1 = KL_P(1, j);
-                    KL_P(0, j) = fma(ph.x, t0, ph.y * t1); KL_P(1, j) = fma(ph.z, t0, ph.w * t1);
-                }
+            {
+                const int tn = t + 1 < n ? t : (t > 0 ? t - 1 : 0);
+                phn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * tn)); qqn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * tn + 4));
+            }
+            if (t > 0) {                                   // (uniform)
+                // columns / entries: x'_0 = Phi00 x_0 + Phi01 x_1, x'_1 = Phi10 x_0 + Phi11 x_1, x'_2 = x_0, x'_k = x_{k-1}
                 {
-                    const double p00 = KL_P(0, 0), p01 = KL_P(0, 1), p11 = KL_P(1, 1);
-                    const double M00 = fma(ph.x, p00, ph.y * p01), M01 = fma(ph.x, p01, ph.y * p11);
-                    const double M10 = fma(ph.z, p00, ph.w * p01), M11 = fma(ph.z, p01, ph.w * p11);
-                    KL_P(0, 0) = fma(M00, ph.x, fma(M01, ph.y, qq.x));
-                    KL_P(0, 1) = fma(M00, ph.z, fma(M01, ph.w, qq.y));
-                    KL_P(1, 1) = fma(M10, ph.z, fma(M11, ph.w, qq.z));
-                }
+                    const double t0 = row[0], t1 = row[1];
 #pragma unroll
-                for (int i = 7; i >= 3; i--) m[i] = m[i - 1];
-                m[2] = m[0];
-                { const double t0 = m[0], t1 = m[1]; m[0] = fma(ph.x, t0, ph.y * t1); m[1] = fma(ph.z, t0, ph.w * t1); }
+                    for (int jj = 7; jj >= 3; jj--) row[jj] = row[jj - 1];
+                    row[2] = t0;
+                    row[0] = fma(ph.x, t0, ph.y * t1); row[1] = fma(ph.z, t0, ph.w * t1);
+                }
+                // rows of the covariance: row'_0 = Phi00 R_0 + Phi01 R_1, row'_1 = Phi10 R_0 + Phi11 R_1, row'_2 = R_0, row'_k = R_{k-1}
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) *reinterpret_cast<double2*>(xr + 8 * lane + jj) = make_double2(row[jj], row[jj + 1]);
+                __syncwarp();
+                const double c0 = lane == 0 ? ph.x : (lane == 1 ? ph.z : 1.0);       // weight of R_0 (lane 2: row'_2 = R_0)
+                const double c1 = lane == 0 ? ph.y : (lane == 1 ? ph.w : 0.0);       // weight of R_1
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(xr + jj), v1 = *reinterpret_cast<const double2*>(xr + 8 + jj);
+                    const double2 vs = *reinterpret_cast<const double2*>(xr + 8 * src + jj);
+                    const double nx = lane >= 3 ? vs.x : fma(c0, v0.x, c1 * v1.x), ny = lane >= 3 ? vs.y : fma(c0, v0.y, c1 * v1.y);
+                    row[jj] = cov ? nx : row[jj]; row[jj + 1] = cov ? ny : row[jj + 1];
+                }
+                row[0] += lane == 0 ? qq.x : (lane == 1 ? qq.y : 0.0);
+                row[1] += lane == 0 ? qq.y : (lane == 1 ? qq.z : 0.0);
+                __syncwarp();
             }
             // ---- observation A(t): d_t f_t = ya_t
             {
                 const double d = sd[t];
-                if (col == 0) {
-                    double* o = gA + 17 * t + 9;
+                const double p0i = row[0];                                    // P(i,0) = P(0,i) before the observation / m_0
+                const double dot = row[0] * d;                                // h = d e_0
+                xg[32 * xb + lane] = dot;
+                __syncwarp();
+                double g[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) o[j] = KL_P(0, j);
-                }
-                gC[(3 + col) * n + t] = m[0];
-                double h[8];
+                for (int jj = 0; jj < 8; jj += 2) { const double2 v = *reinterpret_cast<const double2*>(xg + 32 * xb + jj); g[jj] = v.x; g[jj + 1] = v.y; }
+                xb ^= 1;
+                const double F = fma(d, g[0], c);
+                const double r = rcp_fast(F);
+                bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
+                const double inn = ya[col * n + t] - dot;
+                const double bta = cov ? -dot * r : inn * r;
 #pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = 0.0;
-                h[0] = d;
-                const KlObs ob = kl_observe(P, m, h, ya[col * n + t], c, k, bad);
-                if (col == 0) {
-                    double* o = gA + 17 * t;
-                    o[0] = ob.r;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) o[1 + j] = k[j];
-                }
-                gC[col * n + t] = ob.v;
+                for (int jj = 0; jj < 8; jj++) row[jj] = fma(g[jj], bta, row[jj]);
+                // stores (one instruction each, every lane): gains + 1/F + innovations, then P(0,:) / m_0 before the observation
+                double* p1 = cov ? gA + 17 * t + 1 + lane : (mean ? gC + col * n + t : (lane == 11 ? gA + 17 * t : dummy));
+                double* p2 = cov ? gA + 17 * t + 9 + lane : (mean ? gC + (3 + col) * n + t : dummy);
+                *p1 = cov ? dot * r : (mean ? inn : r);
+                *p2 = p0i;
             }
             // ---- LLE rows complete at t: r = t-3 (t >= 3), and at the last node every remaining row
             const int rlo = t + 1 < n ? t - 3 : (t - 3 > 0 ? t - 3 : 0), rhi = t + 1 < n ? t - 3 : n - 1;
-            for (int r = rlo < 0 ? n : rlo; r <= rhi; r++) {
+            for (int rw = rlo < 0 ? n : rlo; rw <= rhi; rw++) {
                 double h[8];
-                const double* er = eb + 7 * r;
+                const double* er = eb + 7 * rw;
 #pragma unroll
                 for (int lag = 0; lag < 7; lag++) {
-                    const int b = t - lag - (r - 3);                            // position of node t-lag in the row's band r-3..r+3
-                    const double e = (b >= 0 && b < 7) ? er[b] : 0.0;
-                    h[lag == 0 ? 0 : lag + 1] = se * e;
+                    const int b = t - lag - (rw - 3);                           // position of node t-lag in the row's band rw-3..rw+3
+                    const double e = er[b < 0 ? 0 : (b > 6 ? 6 : b)];
+                    h[lag == 0 ? 0 : lag + 1] = (b >= 0 && b < 7) ? se * e : 0.0;
                 }
                 h[1] = 0.0;
-                const double yb = -se * ey[3 * r + col];
-                const KlObs ob = kl_observe(P, m, h, yb, c, k, bad);
-                if (col == 0) {
-                    double* o = gB + 17 * r;
-                    o[0] = ob.r;
+                double dot = 0.0, dot2 = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { o[1 + j] = k[j]; o[9 + j] = h[j]; }
-                }
-                gC[(6 + col) * n + r] = ob.v;
+                for (int jj = 0; jj < 8; jj += 2) { dot = fma(row[jj], h[jj], dot); dot2 = fma(row[jj + 1], h[jj + 1], dot2); }
+                dot += dot2;
+                xg[32 * xb + lane] = dot;
+                __syncwarp();
+                double g[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) { const double2 v = *reinterpret_cast<const double2*>(xg + 32 * xb + jj); g[jj] = v.x; g[jj + 1] = v.y; }
+                xb ^= 1;
+                double F = c, F2 = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) { F = fma(h[jj], g[jj], F); F2 = fma(h[jj + 1], g[jj + 1], F2); }
+                F += F2;
+                const double r = rcp_fast(F);
+                bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
+                const double inn = -se * ey[3 * rw + col] - dot;
+                const double bta = cov ? -dot * r : inn * r;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) row[jj] = fma(g[jj], bta, row[jj]);
+                double hl = h[0];
+#pragma unroll
+                for (int jj = 1; jj < 8; jj++) hl = lane == jj ? h[jj] : hl;
+                double* p1 = cov ? gB + 17 * rw + 1 + lane : (mean ? gC + (6 + col) * n + rw : (lane == 11 ? gB + 17 * rw : dummy));
+                double* p2 = cov ? gB + 17 * rw + 9 + lane : dummy;
+                *p1 = cov ? dot * r : (mean ? inn : r);
+                *p2 = hl;
             }
         }
+        bad = __any_sync(0xffffffffu, bad);
     }
     __threadfence_block();
     __syncthreads();
@@ -1018,7 +1026,6 @@ static __device__ int mct_kalman_lle_solve(int n, double c, double eps, double b
     }
     return __syncthreads_or(bad);
 }
-#undef KL_P
 
 // ------------------------------------------------------------------------------------------
 // LLE weights, one node per thread (trackdlo.cpp:92-159).  Mirrors the operation order of

@@ -56,7 +56,7 @@ __host__ __device__ inline TqScr tq_scr_layout(int N) {
     s.GUIDE = o; o += 3 * N;
     s.PHI = o; o += 4 * N;
     s.KTR = o; o += 8 * N;                   // structured LLE solve: transitions {Phi, Q} of every gap
-    s.KLW = o; o += 43LL * N + 16;            // ... and its forward-pass workspace
+    s.KLW = o; o += 43LL * N + 64;            // ... and its forward-pass workspace
     s.CTL = o; o += FC_WORDS / 2;
     s.total = (o + 15) & ~15LL;
     return s;
@@ -105,7 +105,7 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     l.chol_doubles = (e_end - l.yext) / 8;
     // the structured LLE solve (mct_kalman_lle_solve) needs 17 N + KL_STAGE doubles from yext on: more than the E-step
     // view at N = 256
-    const int k_end = l.yext + (17 * N + KL_STAGE + 8) * 8;
+    const int k_end = l.yext + (17 * N + KL_STAGE + 10) * 8;
     l.total = e_end > k_end ? e_end : k_end;
     return l;
 }
@@ -1072,6 +1072,7 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
             double* keb = kub + 3 * Nn;         // [Nn][7]
             double* key = keb + 7 * Nn;         // [Nn][3]
             double* kst = key + 3 * Nn;         // [KL_STAGE]
+            kst += (reinterpret_cast<uintptr_t>(kst) >> 3) & 1;      // 16-byte aligned (vector loads of the exchange buffers)
             sing = mct_kalman_lle_solve(Nn, p.lambda * sigma2, sigma2 * p.gamma, p.beta, kdd, kbt, sm.y0, scr + sc.KTR, scr + sc.AB, scr + sc.HY0,
                                         sm.wsol, sm.tnew, kub, keb, key, kst, scr + sc.KLW);
             if (sing) status |= ST_SINGULAR;
