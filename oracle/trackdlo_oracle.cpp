@@ -10,14 +10,17 @@
 // cpu_baseline / --impl reference legs of bench.py and by nothing else: the product
 // (trackdlo_b200/) never links, imports or calls it.
 //
-// PARITY UNPINNED: the reference ships no golden vectors / known-answer tests and cannot be
-// built here (needs Eigen + ROS + PCL + OpenCV; none installed, no network).  The third-party
-// arithmetic that lives outside /root/reference is Eigen 3.3.7 (docs/RUN.md:10):
-//   * completeOrthogonalDecomposition().solve (trackdlo.cpp:415)  -> restated here as a
-//     column-pivoted Householder QR solve (same algorithm class; identical for full-rank A)
-//   * .inverse()/.determinant() on the LLE Gram matrices (trackdlo.cpp:136-143) -> restated as
-//     partial-pivot LU.  Those Gram matrices are rank-3 6x6, so their inverse is rounding noise
-//     (SURVEY.md §8 a3); no restatement can reproduce Eigen's bits there.
+// PINNING: the reference ships no golden vectors / known-answer tests.  This restatement is pinned against the
+// reference's own statements instead: oracle/Makefile target `_ref` compiles the UNMODIFIED trackdlo.cpp + utils.cpp
+// behind ref_harness.cpp, and tests/test_ref_pin.py compares the two on every golden input, random option sweeps, all
+// five tracking_step states and all traversal alignments (agreement 1e-12..1e-14; integer outputs identical).
+// What that build cannot pin is the third-party arithmetic outside /root/reference -- Eigen 3.3.7 (docs/RUN.md:10),
+// absent from this image -- which both this file and the _ref build's stand-in (ref_shim/eigen) restate:
+//   * completeOrthogonalDecomposition().solve (trackdlo.cpp:415)  -> column-pivoted Householder QR solve
+//     (same algorithm class; identical for full-rank A; checked against LAPACK in test_ref_pin.py)
+//   * .inverse()/.determinant() on the LLE Gram matrices (trackdlo.cpp:136-143) -> partial-pivot LU.  Those Gram
+//     matrices are rank-3 6x6, so their inverse is rounding noise; no restatement can reproduce
+//     Eigen's bits there.  With a real Eigen: make -C oracle -B _ref EIGEN_INCLUDE=/usr/include/eigen3.
 // The oracle is cross-checked against an independent NumPy/LAPACK twin (oracle/numpy_twin.py).
 //
 // Matrices at the C boundary are row-major [rows][3] doubles (NumPy default).
