@@ -269,6 +269,9 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *  TDLO_OPT_TRUNCATION    z_cut: affinity entries exp(-z) with z > z_cut are skipped.  745.2 skips only entries
  *                         that are exactly 0 in the reference (double underflow); the default 100 skips entries
  *                         below 3.8e-44 of the column maximum, i.e. far below one ulp of every sum they enter.
+ *  TDLO_OPT_TRUNCATION_REL  z_rel: additionally, entries more than exp(-z_rel) below the LARGEST entry of their column (the point's
+ *                         nearest node) are skipped.  Default 45: what is dropped is below 3e-20 of the column sum it would
+ *                         enter (half an ulp is 1.1e-16), so every sum is unchanged to the last bit or two; 745.2 = off.
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
  *  TDLO_OPT_THREADS       kernel variant for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
  *                         224 (3 CTAs/SM, 80 registers; measured equal or slower).  Nn > 64 always uses 256.
@@ -293,6 +296,7 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
 #define TDLO_OPT_WATCHDOG_MS 6
 #define TDLO_OPT_SOLVER 7
 #define TDLO_OPT_VOXEL_CELLS 8
+#define TDLO_OPT_TRUNCATION_REL 9
 int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value);
 
 #ifdef __cplusplus

@@ -1,6 +1,6 @@
 // Development aid: does instruction-level parallelism inside ONE warp pay on the FP64 pipe?  K interleaved exp(-z)
 // chains per trip, 1 warp and 8 warps per CTA, one CTA per SM.
-#include "../../trackdlo_b200/csrc/tdlo_kernels.cuh"
+#include "../../trackdlo_b200/csrc/tdlo_common.cuh"
 #include <cstdio>
 using namespace tdlo;
 template <int K>

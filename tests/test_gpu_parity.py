@@ -42,7 +42,7 @@ ENGINE_CFGS = {
     "dense_solver": dict(solver=1),                         # M-step: dense Gauss-Jordan / blocked Cholesky instead of the O(Nn) state-space solve
     "structured_all": dict(solver=2),                       # ... and the state-space solve also for the LLE registrations below 65 nodes
     "tq_224thr": dict(chunk_points=1024, truncation=100.0, threads=224),
-    "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, threads=224),
+    "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, truncation_rel=745.2, threads=224),
     "tq_256thr": dict(chunk_points=2048, truncation=100.0, threads=256),
 }
 
@@ -398,7 +398,7 @@ def test_evaluator_error_metric_matches_oracle(ctx):
 
 
 def test_engine_options_are_validated(ctx):
-    for name, bad in (("watchdog_ms", -1.0), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0),
+    for name, bad in (("watchdog_ms", -1.0), ("chunk_points", 100), ("chunk_points", 1000), ("truncation", 10.0), ("truncation", 800.0), ("truncation_rel", 10.0), ("truncation_rel", 800.0),
                       ("threads", 128), ("inflight", -1)):
         with pytest.raises(api.TdloError):
             ctx.set_option(name, bad)

@@ -236,6 +236,7 @@ def test_fuzz_slice_single_frames(ctx):
         f = synth.make_frame(int(rng.integers(0, 10000)), n_nodes=Nn, n_points=Mp, occlusion=occ, occl_start=start)
         ctx.set_option("chunk_points", int(rng.choice([0, 256, 512, 1024, 4096])))
         ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
+        ctx.set_option("truncation_rel", float(rng.choice([45.0, 745.2])))
         ctx.set_option("threads", int(rng.choice([224, 256])))
         mi = int(rng.integers(1, 25)); tol = float(rng.choice([0.0, 2e-4]))
         try:
@@ -257,7 +258,7 @@ def test_fuzz_slice_single_frames(ctx):
             assert rel(r["Y"][0], o["Y"]) < 1e-6, (case, Nn, Mp, occ, start)
             n += 1
         finally:
-            ctx.set_option("chunk_points", 0); ctx.set_option("truncation", 100.0); ctx.set_option("threads", 256)
+            ctx.set_option("chunk_points", 0); ctx.set_option("truncation", 100.0); ctx.set_option("truncation_rel", 45.0); ctx.set_option("threads", 256)
     assert n >= 50
 
 

@@ -203,7 +203,7 @@ class Context:
         """tdlo_synchronize: waits for the last *_device call; raises if the kernel's watchdog gave up."""
         self._check(self.lib.tdlo_synchronize(self.h), "tdlo_synchronize")
 
-    OPTIONS = {"chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5, "watchdog_ms": 6, "solver": 7, "voxel_cells": 8}
+    OPTIONS = {"chunk_points": 2, "truncation": 3, "inflight": 4, "threads": 5, "watchdog_ms": 6, "solver": 7, "voxel_cells": 8, "truncation_rel": 9}
 
     def set_option(self, name, value):
         """tdlo_set_option: chunk_points, truncation, inflight, threads, watchdog_ms."""

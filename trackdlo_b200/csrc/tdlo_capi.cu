@@ -52,6 +52,7 @@ struct tdlo_ctx {
     int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
+    double tq_zrel = 45.0;          // relative truncation exponent (745.2 = off)
     int tq_solver = 0;              // M-step solve: 0 = automatic, 1 = dense always, 2 = structured always (TDLO_OPT_SOLVER)
     double watchdog_ms = 20000.0;   // a CTA waiting longer than this for a task aborts the launch (0 = off)
     cudaStream_t last_stream = nullptr; bool launched = false;
@@ -256,8 +257,12 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     const int npass = kv.npass, threads_eff = kv.threads;
     const TqSmemL L = tq_smem_layout(32 * npass, threads_eff / 32);
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
+    // development aid (scripts/occupancy_probe.py): TDLO_DEV_SMEM_PAD=<bytes> pads the dynamic shared memory to lower the
+    // number of resident CTAs per SM
+    static const int dev_pad = getenv("TDLO_DEV_SMEM_PAD") ? atoi(getenv("TDLO_DEV_SMEM_PAD")) : 0;
+    const int smem_launch = std::min(L.total + dev_pad, 227 * 1024);
     int occ = 0;
-    CK(kv.prepare(L.total, &occ));
+    CK(kv.prepare(smem_launch, &occ));
     if (occ < 1) return fail(ctx, TDLO_ERR_CUDA, "task-queue kernel does not fit (smem %d B, %d threads)", L.total, threads_eff);
     const int grid = ctx->sm_count * occ;
     TqArgs t;
@@ -269,6 +274,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.inflight = ctx->tq_inflight > 0 ? ctx->tq_inflight : std::max(grid / 2, 64);
     t.inflight = std::min(std::min(t.inflight, grid), a.n_frames);
     t.zcut = ctx->tq_zcut;
+    t.zrel = ctx->tq_zrel;
     t.solver = ctx->tq_solver;
     t.qctl = ctx->d_q; t.qslots = ctx->d_q + 8; t.qmask = ctx->qcap - 1;
     t.fscratch = ctx->d_fscratch; t.fstride = ctx->fstride;
@@ -279,7 +285,7 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
     t.watchdog_ns = (unsigned long long)(ctx->watchdog_ms * 1e6);
     CK(cudaMemsetAsync(ctx->d_q, 0, ((size_t)ctx->qcap + 8) * sizeof(unsigned long long), stream));
     ctx->last_stream = stream; ctx->launched = true;
-    CK(kv.launch(grid, L.total, stream, t));
+    CK(kv.launch(grid, smem_launch, stream, t));
     ctx->info[0] = 1; ctx->info[1] = grid; ctx->info[2] = threads_eff; ctx->info[3] = L.total; ctx->info[4] = chunk;
     ctx->info[5] = 1; ctx->info[6] = occ; ctx->info[7] = ctx->sm_count;
     return TDLO_OK;
@@ -865,6 +871,9 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
         case TDLO_OPT_TRUNCATION:
             if (!(value >= 40.0 && value <= 745.2)) return fail(ctx, TDLO_ERR_INVALID, "truncation exponent must be in [40, 745.2]");
             ctx->tq_zcut = value; return TDLO_OK;
+        case TDLO_OPT_TRUNCATION_REL:
+            if (!(value >= 38.0 && value <= 745.2)) return fail(ctx, TDLO_ERR_INVALID, "relative truncation exponent must be in [38, 745.2]");
+            ctx->tq_zrel = value; return TDLO_OK;
         case TDLO_OPT_INFLIGHT:
             if (value < 0) return fail(ctx, TDLO_ERR_INVALID, "inflight must be >= 0");
             ctx->tq_inflight = (int)value; return TDLO_OK;

@@ -65,7 +65,7 @@ __host__ __device__ inline TqScr tq_scr_layout(int N) {
 // ---- shared memory layout (bytes).  One fixed head (exp table, node data) + a region that is the E-step's
 // P tiles during chunk tasks and the M-step's [A|B] + vectors during continuations.
 struct TqSmemL {
-    int tab, node4, nsoa, vw, bcast, wbuf, ptile, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, chol_doubles, total;
+    int tab, node4, nsoa, vw, bcast, wbuf, ptile, wacc, y0, s, yext, jd, hy0, p1, px, wsol, tnew, red, gjbuf, prow, used, ab, ab_doubles, chol_doubles, total;
 };
 __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     TqSmemL l{};
@@ -81,6 +81,9 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     // E-step view
     l.wbuf = o; o += nw * 32 * 32;
     l.ptile = o; o += nw * TQ_ROWS * TQ_RS * 8;
+    // per-warp P1 / PX accumulators [nw][N][4] for N <= 64 (wider node ranges keep them in registers: the P tiles are then
+    // reused for the cross-warp reduction)
+    l.wacc = o; if (N <= 64) o += nw * N * 32;
     const int e_end = o;
     // M-step view (aliases the E-step view)
     o = u;
@@ -115,6 +118,7 @@ struct TqArgs {
     int chunk;                       // raw points per chunk task
     int inflight;                    // frames started at launch; one more starts whenever a frame completes
     double zcut;                     // Gaussian truncation: entries exp(-z), z > zcut, are skipped (745.2 = exact zeros only)
+    double zrel;                     // ... and entries more than exp(-zrel) below the point's largest entry (745.2 = off)
     int solver;                      // M-step solve: 0 = automatic (structured O(Nn) state-space solve without LLE, and with LLE above 64 nodes),
                                      // 1 = dense always, 2 = structured always
     unsigned long long* qctl;        // [0] head ticket, [1] tail, [2] ints {next frame, start tickets}, [3] ints {frames done, abort flag}
@@ -130,7 +134,7 @@ struct TqArgs {
 
 struct TqSm {
     double* tab; double4* node4; double* nsoa; double* vw; int* bcast; double* red;
-    double4* wbuf; double* ptile;
+    double4* wbuf; double* ptile; double* wacc;
     double *y0, *s, *yext, *jd, *hy0, *p1, *px, *wsol, *tnew, *gjbuf; int *prow, *used; double* ab;
 };
 
@@ -284,7 +288,7 @@ __device__ __forceinline__ double sqrt_ub(double x) {
 // ------------------------------------------------------------------------------------------
 template <int NPASS, bool VIS, int NW>
 static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__ Xc, const double4* __restrict__ sph, int n_local, int Nn,
-                               double sigma2, double c_norm, double rscale, double zcut, double* part_out,
+                               double sigma2, double c_norm, double rscale, double zcut, double zrel, double k_vis, double* part_out,
                                unsigned long long* prof) {
     constexpr int RS = TQ_RS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -300,9 +304,18 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
     const double* __restrict__ nsy = sm.nsoa + Nn;
     const double* __restrict__ nsz = sm.nsoa + 2 * Nn;
     const double* __restrict__ nss = sm.nsoa + 3 * Nn;
-    double acc[NPASS][4];
+    // P1 / PX accumulators of this warp: shared memory [Nn][4] for Nn <= 64 (frees 32 registers in the tile loop and the
+    // hand-over to owner lanes), registers (lane l owns nodes l, l+32, ...) above
+    constexpr bool SACC = NPASS <= 2;
+    double4* __restrict__ wacc = reinterpret_cast<double4*>(sm.wacc) + warp * (32 * NPASS);
+    double acc[SACC ? 1 : NPASS][4];
+    if (SACC) {
+        for (int m = lane; m < Nn; m += 32) wacc[m] = make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncwarp();
+    } else {
 #pragma unroll
-    for (int ps = 0; ps < NPASS; ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
+        for (int ps = 0; ps < (SACC ? 1 : NPASS); ps++) { acc[ps][0] = acc[ps][1] = acc[ps][2] = acc[ps][3] = 0.0; }
+    }
     double sxx = 0.0;
     const double uflow = 1490.2 * sigma2;
     const double T = sqrt(zcut);
@@ -393,11 +406,17 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
         const double alo = nd[lo].w + dlo * rscale;      // t_j = alo - s'_j  for j <= lo
         const double ahi = dhi * rscale - nd[hi].w;      // t_j = ahi + s'_j  for j >= hi
 
-        // ---- node window [jlo, jhi] of this warp: P entries outside are below exp(-zcut) for all 32 points
+        // ---- node window [jlo, jhi] of this warp: P entries outside are, for each of the 32 points, below exp(-zcut) or more
+        // than exp(-zrel) below the point's largest entry (>= exp(-zn) vw_a, a = its nearest node) -- with the default
+        // zrel = 45 that is 3e-20 of the column sum they would enter, three orders below half an ulp.  With visibility
+        // weights: vw_j / vw_a <= exp(k_vis dm_a) <= exp(k_vis da) (node a is at most da away from a point), added to the margin.
         int jlo, jhi;
         {
-            const double thr_lo = warp_min_pos_lb(alo) - T;                        // keep j <= lo while s'_j > thr_lo
-            const double thr_hi = T - (warp_min_pos_lb(ahi + s_last) - s_last);    // keep j >= hi while s'_j < thr_hi
+            double zn = fma(best, rscale * rscale, zrel);
+            if (VIS) zn = fma(fabs(k_vis), da, zn);
+            const double tl = fmin(sqrt_ub(zn), T);                                 // this point keeps |t| <= tl
+            const double thr_lo = warp_min_pos_lb(alo + (T - tl)) - T;                        // keep j <= lo while s'_j > thr_lo
+            const double thr_hi = (T + s_last) - warp_min_pos_lb((ahi + s_last) + (T - tl));  // keep j >= hi while s'_j < thr_hi
             const int lomin = __reduce_min_sync(0xffffffffu, lo);
             const int himax = __reduce_max_sync(0xffffffffu, hi);
             jlo = Nn; jhi = -1;
@@ -496,15 +515,24 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                 b0 += __shfl_xor_sync(0xffffffffu, b0, off); b1 += __shfl_xor_sync(0xffffffffu, b1, off);
                 b2 += __shfl_xor_sync(0xffffffffu, b2, off); b3 += __shfl_xor_sync(0xffffffffu, b3, off);
             }
-            // owner lane l holds nodes l, l+32, ...; at most one of them lies in [j0, j1]
-            const int src = (lane - j0) & 31;             // row index of the owned node inside this block, if any
-            const double o0 = __shfl_sync(0xffffffffu, b0, src), o1 = __shfl_sync(0xffffffffu, b1, src);
-            const double o2 = __shfl_sync(0xffffffffu, b2, src), o3 = __shfl_sync(0xffffffffu, b3, src);
-            const int m = j0 + src;                       // the owned node (m % 32 == lane)
-            if (src < Wb) {
+            if (SACC) {
+                // lanes 0 .. Wb-1 (row r = lane, group 0) hold the block's row sums
+                if (lane < Wb) {
+                    double4 v = wacc[j0 + lane];
+                    v.x += b0; v.y += b1; v.z += b2; v.w += b3;
+                    wacc[j0 + lane] = v;
+                }
+            } else {
+                // owner lane l holds nodes l, l+32, ...; at most one of them lies in [j0, j1]
+                const int src = (lane - j0) & 31;             // row index of the owned node inside this block, if any
+                const double o0 = __shfl_sync(0xffffffffu, b0, src), o1 = __shfl_sync(0xffffffffu, b1, src);
+                const double o2 = __shfl_sync(0xffffffffu, b2, src), o3 = __shfl_sync(0xffffffffu, b3, src);
+                const int m = j0 + src;                       // the owned node (m % 32 == lane)
+                if (src < Wb) {
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ps++)
-                    if ((m >> 5) == ps) { acc[ps][0] += o0; acc[ps][1] += o1; acc[ps][2] += o2; acc[ps][3] += o3; }
+                    for (int ps = 0; ps < (SACC ? 1 : NPASS); ps++)
+                        if ((m >> 5) == ps) { acc[ps][0] += o0; acc[ps][1] += o1; acc[ps][2] += o2; acc[ps][3] += o3; }
+                }
             }
             __syncwarp();
         }
@@ -514,20 +542,30 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
     const long long t_red0 = prof ? clock64() : 0;
     // ---- cross-warp reduction in a fixed order (deterministic)
     __syncthreads();
-    double* __restrict__ racc = sm.ptile;                 // [nw][Nn][4]; the P tiles are dead now
+    if (SACC) {
+        const double* __restrict__ racc = sm.wacc;        // [nw][32 NPASS][4]
+        for (int i = tid; i < 4 * Nn; i += nt) {
+            double v = 0.0;
 #pragma unroll
-    for (int ps = 0; ps < NPASS; ps++) {
-        const int m = lane + 32 * ps;
-        if (m < Nn) {
-            double* dst = racc + ((long long)warp * Nn + m) * 4;
-            dst[0] = acc[ps][0]; dst[1] = acc[ps][1]; dst[2] = acc[ps][2]; dst[3] = acc[ps][3];
+            for (int ww = 0; ww < nw; ww++) v += racc[ww * (128 * NPASS) + i];
+            __stcg(part_out + i, v);
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < 4 * Nn; i += nt) {
-        double v = 0.0;
-        for (int ww = 0; ww < nw; ww++) v += racc[ww * 4 * Nn + i];
-        __stcg(part_out + i, v);
+    } else {
+        double* __restrict__ racc = sm.ptile;             // [nw][Nn][4]; the P tiles are dead now
+#pragma unroll
+        for (int ps = 0; ps < (SACC ? 1 : NPASS); ps++) {
+            const int m = lane + 32 * ps;
+            if (m < Nn) {
+                double* dst = racc + ((long long)warp * Nn + m) * 4;
+                dst[0] = acc[ps][0]; dst[1] = acc[ps][1]; dst[2] = acc[ps][2]; dst[3] = acc[ps][3];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 4 * Nn; i += nt) {
+            double v = 0.0;
+            for (int ww = 0; ww < nw; ww++) v += racc[ww * 4 * Nn + i];
+            __stcg(part_out + i, v);
+        }
     }
     const double sx = block_sum(sxx, sm.red);
     if (tid == 0) __stcg(part_out + 4 * Nn, sx);
@@ -1363,6 +1401,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
     sm.red = reinterpret_cast<double*>(smem_raw + L.red);
     sm.wbuf = reinterpret_cast<double4*>(smem_raw + L.wbuf);
     sm.ptile = reinterpret_cast<double*>(smem_raw + L.ptile);
+    sm.wacc = reinterpret_cast<double*>(smem_raw + L.wacc);
     sm.y0 = reinterpret_cast<double*>(smem_raw + L.y0);
     sm.s = reinterpret_cast<double*>(smem_raw + L.s);
     sm.yext = reinterpret_cast<double*>(smem_raw + L.yext);
@@ -1464,8 +1503,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
         } else {
             double* part = a.part + (long long)g * a.part_stride;
             if (prof && tid == 0) atomicAdd(prof + 10, 1ull);
-            if (use_vis) tq_estep_chunk<NPASS, true, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
-            else tq_estep_chunk<NPASS, false, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, part, prof);
+            if (use_vis) tq_estep_chunk<NPASS, true, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, a.zrel, tq_params(a, stage).k_vis, part, prof);
+            else tq_estep_chunk<NPASS, false, THREADS / 32>(sm, fr.Xc + r0 * 3, a.tsph + (long long)g * (a.chunk >> 5), n_kept, Nn, sigma2, c_norm, rscale, a.zcut, a.zrel, tq_params(a, stage).k_vis, part, prof);
         }
         TQ_TICK(type)
         if (tq_arrive(sm, fr.ctl)) {
