@@ -27,11 +27,15 @@ def run(name, frames, nodes, points, tp, steps=5, distinct=None, occlusion=0.0):
     iters = int(db.iters.sum()); c = ph["cycles"]; tot = sum(c.values()); n = ph["counts"]
     print(f"{name:6s} {os.environ.get('TDLO_DEV_SMEM_PAD', '')} {opts} launch={ctx.launch_info()} median {t[len(t)//2]:8.3f} ms min {t[0]:8.3f}  iters {iters}  cyc/tile {n['warp_tile_loop_cycles']/max(n['tiles'],1):7.0f} | " +
           " ".join(f"{k}={v/tot:.3f}" for k, v in c.items() if v / tot > 0.02), flush=True)
+    if frames == 1:
+        print("        thread-0 cycles per EM iteration: " + " ".join(f"{k}={v/iters:.0f}" for k, v in c.items() if k != "queue_wait"), flush=True)
     ctx.close()
 for s in shapes:
     if s == "C2": run("C2", 64, 50, 20000, api.TrackParams(max_iter=50, tol=0.0))
     if s == "C2x8": run("C2x8", 512, 50, 20000, api.TrackParams(max_iter=50, tol=0.0), distinct=64, steps=3)
     if s == "C4": run("C4", 512, 50, 20000, api.TrackParams(), distinct=64, steps=3)
+    if s == "C2x1": run("C2x1", 1, 50, 20000, api.TrackParams(max_iter=50, tol=0.0))
+    if s == "C2x16": run("C2x16", 16, 50, 20000, api.TrackParams(max_iter=50, tol=0.0))
     if s == "C1": run("C1", 1, 30, 2000, api.TrackParams(max_iter=20, tol=0.0))
     if s == "C3": run("C3", 1, 50, 50000, api.TrackParams(max_iter=50, tol=0.0), occlusion=0.4)
     if s == "C5": run("C5", 8, 200, 100000, api.TrackParams(max_iter=50, tol=0.0), distinct=2, steps=2)

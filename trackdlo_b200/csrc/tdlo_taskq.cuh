@@ -274,6 +274,32 @@ __device__ __forceinline__ double sqrt_ub(double x) {
     return x * r * (1.0 + 1e-5);
 }
 
+// Phase B of the E-step for one block of Wb <= WP node rows (WP = 8, 16, 32): lane = (row r, point group g), every lane
+// accumulates P1 / PX of its row over the WP points of its group; the 32 / WP groups are then combined by shuffles, so
+// that every lane ends up with the sums of row r over all 32 points.
+template <int WP>
+__device__ __forceinline__ void tq_phase_b(const double* __restrict__ pt, const double2* __restrict__ wlo, const double2* __restrict__ whi,
+                                           int lane, int Wb, double& b0, double& b1, double& b2, double& b3) {
+    const int r = lane & (WP - 1);
+    const double* __restrict__ prow = pt + r * TQ_RS + (lane - r);       // points [g*WP, (g+1)*WP)
+    const double2* __restrict__ wgl = wlo + (lane - r);
+    const double2* __restrict__ wgh = whi + (lane - r);
+    b0 = 0.0; b1 = 0.0; b2 = 0.0; b3 = 0.0;
+    if (r < Wb) {
+#pragma unroll
+        for (int u = 0; u < WP; u++) {
+            const double p = prow[u];
+            const double2 wa = wgl[u], wc = wgh[u];
+            b0 = fma(p, wa.x, b0); b1 = fma(p, wa.y, b1); b2 = fma(p, wc.x, b2); b3 = fma(p, wc.y, b3);
+        }
+    }
+#pragma unroll
+    for (int off = WP; off < 32; off <<= 1) {
+        b0 += __shfl_xor_sync(0xffffffffu, b0, off); b1 += __shfl_xor_sync(0xffffffffu, b1, off);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, off); b3 += __shfl_xor_sync(0xffffffffu, b3, off);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused E-step over one chunk (trackdlo.cpp:278-389): distances -> arg-max node -> geodesic distances -> P ->
 // (visibility weights) -> normalisation -> P1, PX, sum Pt1*|x|^2.  Every WARP is autonomous: it takes 32 sorted
@@ -325,23 +351,22 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
     // software prefetch: the next tile's point and sphere are requested before the current tile is processed
     double xn = 0.0, yn = 0.0, zn = 0.0;
     double4 sn = make_double4(0.0, 0.0, 0.0, 0.0);
+    const double* __restrict__ xp = Xc + (warp * 32 + lane) * 3;         // this lane's point of the warp's next tile
+    const double4* __restrict__ sp = sph + warp;
     if (warp * 32 < n_local) {
-        const int b0 = warp * 32;
-        const int n = b0 + lane < n_local ? b0 + lane : b0;
-        xn = __ldcg(Xc + (long long)n * 3); yn = __ldcg(Xc + (long long)n * 3 + 1); zn = __ldcg(Xc + (long long)n * 3 + 2);
-        sn = ldcg4(sph + (b0 >> 5));
+        const double* q = warp * 32 + lane < n_local ? xp : xp - lane * 3;
+        xn = __ldcg(q); yn = __ldcg(q + 1); zn = __ldcg(q + 2);
+        sn = ldcg4(sp);
     }
     for (int base = warp * 32; base < n_local; base += nw * 32) {
         const bool valid = base + lane < n_local;            // idle lanes shadow the tile's first point (weight 0)
         const double x = xn, y = yn, z = zn;
         const double cx = sn.x, cy = sn.y, cz = sn.z, rho = sn.w;
-        {
-            const int nb = base + nw * 32;
-            if (nb < n_local) {
-                const int n = nb + lane < n_local ? nb + lane : nb;
-                xn = __ldcg(Xc + (long long)n * 3); yn = __ldcg(Xc + (long long)n * 3 + 1); zn = __ldcg(Xc + (long long)n * 3 + 2);
-                sn = ldcg4(sph + (nb >> 5));
-            }
+        xp += nw * 96; sp += nw;
+        if (base + nw * 32 < n_local) {
+            const double* q = base + nw * 32 + lane < n_local ? xp : xp - lane * 3;
+            xn = __ldcg(q); yn = __ldcg(q + 1); zn = __ldcg(q + 2);
+            sn = ldcg4(sp);
         }
 
         // ---- nearest node: exact bounding-sphere pruning of the scan range: a node farther from the tile's sphere
@@ -417,21 +442,27 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
             const double tl = fmin(sqrt_ub(zn), T);                                 // this point keeps |t| <= tl
             const double thr_lo = warp_min_pos_lb(alo + (T - tl)) - T;                        // keep j <= lo while s'_j > thr_lo
             const double thr_hi = (T + s_last) - warp_min_pos_lb((ahi + s_last) + (T - tl));  // keep j >= hi while s'_j < thr_hi
-            const int lomin = __reduce_min_sync(0xffffffffu, lo);
-            const int himax = __reduce_max_sync(0xffffffffu, hi);
-            jlo = Nn; jhi = -1;
-#pragma unroll
-            for (int ps = 0; ps < NPASS; ps++) {
-                const int j = lane + 32 * ps;
-                const double sj = j < Nn ? nss[j] : 0.0;
-                const unsigned m1 = __ballot_sync(0xffffffffu, j < Nn && sj > thr_lo);
-                const unsigned m2 = __ballot_sync(0xffffffffu, j < Nn && sj < thr_hi);
-                if (m1 && jlo == Nn) jlo = 32 * ps + __ffs(m1) - 1;
-                if (m2) jhi = 32 * ps + 31 - __clz(m2);
+            // s' is non-decreasing in j: the window ends are found by looking 32 rows at a time below the smallest lo /
+            // above the largest hi of the tile (one ballot each in all but the first, wide iterations)
+            jlo = __reduce_min_sync(0xffffffffu, lo);
+            jhi = __reduce_max_sync(0xffffffffu, hi);
+            for (;;) {
+                const int j = jlo - 1 - lane;
+                const unsigned m = __ballot_sync(0xffffffffu, j >= 0 && nss[max(j, 0)] > thr_lo);
+                const int k = __ffs(~m) - 1;                 // leading lanes that keep their row (-1: all 32)
+                if (k >= 0) { jlo -= k; break; }
+                jlo -= 32;
             }
-            jlo = min(jlo, lomin); jhi = max(jhi, himax);
+            for (;;) {
+                const int j = jhi + 1 + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, j < Nn && nss[min(j, Nn - 1)] < thr_hi);
+                const int k = __ffs(~m) - 1;
+                if (k >= 0) { jhi += k; break; }
+                jhi += 32;
+            }
         }
         if (prof && lane == 0) { atomicAdd(prof + 11, 1ull); atomicAdd(prof + 12, (unsigned long long)(jhi - jlo + 1)); atomicAdd(prof + 13, (unsigned long long)((jhi - jlo) / TQ_ROWS + 1)); }
+        const double nahi = -ahi;
         const bool quirk = (hi - lo == 2);               // the row strictly between lo and hi keeps geodesic 0 -> P = 1 (x vw)
         const int jq = lo + 1;
 
@@ -449,10 +480,11 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                     const double s0 = nd[j].w, s1 = nd[j + 1].w, s2 = nd[j + 2].w, s3 = nd[j + 3].w;
                     double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
                     if (VIS) { v0 = vw[j]; v1 = vw[j + 1]; v2 = vw[j + 2]; v3 = vw[j + 3]; }
-                    const double t0 = (j <= lo) ? (alo - s0) : (ahi + s0);
-                    const double t1 = (j + 1 <= lo) ? (alo - s1) : (ahi + s1);
-                    const double t2 = (j + 2 <= lo) ? (alo - s2) : (ahi + s2);
-                    const double t3 = (j + 3 <= lo) ? (alo - s3) : (ahi + s3);
+                    // t_j = alo - s'_j (j <= lo) or ahi + s'_j (j > lo); only t^2 is used: select the centre, not the result
+                    const double t0 = ((j <= lo) ? alo : nahi) - s0;
+                    const double t1 = ((j + 1 <= lo) ? alo : nahi) - s1;
+                    const double t2 = ((j + 2 <= lo) ? alo : nahi) - s2;
+                    const double t3 = ((j + 3 <= lo) ? alo : nahi) - s3;
                     double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
                     if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
                     colsum += (p0 + p1) + (p2 + p3);
@@ -466,7 +498,7 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                 }
                 for (; j <= jend; j++) {
                     const double sj = nd[j].w;
-                    const double t = (j <= lo) ? (alo - sj) : (ahi + sj);
+                    const double t = ((j <= lo) ? alo : nahi) - sj;
                     double p = exp_neg(t * t, tab);
                     if (VIS) p *= vw[j];
                     colsum += p;
@@ -495,26 +527,10 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
             // ---- phase B (trackdlo.cpp:387-389): lane = (row r, point group g); P1 / PX of the block's rows over
             // the warp's 32 points; groups are combined by shuffles and handed to the lanes that own the nodes.
             const int Wb = j1 - j0 + 1;
-            const int Wp = Wb <= 8 ? 8 : (Wb <= 16 ? 16 : 32);
-            const int r = lane & (Wp - 1);
-            const double* __restrict__ prow = pt + r * RS + (lane - r);       // points [g*Wp, (g+1)*Wp)
-            const double2* __restrict__ wgl = wlo + (lane - r);
-            const double2* __restrict__ wgh = whi + (lane - r);
-            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            if (r < Wb) {
-                for (int i0 = 0; i0 < Wp; i0 += 8) {                           // Wp is 8, 16 or 32
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const double p = prow[i0 + u];
-                        const double2 wa = wgl[i0 + u], wc = wgh[i0 + u];
-                        b0 = fma(p, wa.x, b0); b1 = fma(p, wa.y, b1); b2 = fma(p, wc.x, b2); b3 = fma(p, wc.y, b3);
-                    }
-                }
-            }
-            for (int off = Wp; off < 32; off <<= 1) {
-                b0 += __shfl_xor_sync(0xffffffffu, b0, off); b1 += __shfl_xor_sync(0xffffffffu, b1, off);
-                b2 += __shfl_xor_sync(0xffffffffu, b2, off); b3 += __shfl_xor_sync(0xffffffffu, b3, off);
-            }
+            double b0, b1, b2, b3;
+            if (Wb <= 8) tq_phase_b<8>(pt, wlo, whi, lane, Wb, b0, b1, b2, b3);
+            else if (Wb <= 16) tq_phase_b<16>(pt, wlo, whi, lane, Wb, b0, b1, b2, b3);
+            else tq_phase_b<32>(pt, wlo, whi, lane, Wb, b0, b1, b2, b3);
             if (SACC) {
                 // lanes 0 .. Wb-1 (row r = lane, group 0) hold the block's row sums
                 if (lane < Wb) {
