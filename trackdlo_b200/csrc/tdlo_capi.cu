@@ -36,7 +36,7 @@ struct tdlo_ctx {
     // workspace
     double* d_Xc = nullptr;
     unsigned short* d_bkt = nullptr;
-    double* d_exp_tab = nullptr;    // 2^(j/64), j = 0..63
+    double* d_exp_tab = nullptr;    // 2^(j/2048), j = 0..2047
     unsigned long long* d_prof = nullptr;   // phase cycle counters (enabled by tdlo_profile_phases)
     unsigned long long* d_prof_buf = nullptr;
     // visibility front-end workspace
@@ -176,11 +176,11 @@ extern "C" int tdlo_create(tdlo_ctx** out, int device, int32_t max_frames, int32
     CKC(dalloc(&ctx->d_npri_out, F));
     CKC(dalloc(&ctx->d_state, F));
     CKC(dalloc(&ctx->d_prof_buf, 16));
-    // exp table 2^(j/64)
-    double tab[64];
-    for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
-    CKC(dalloc(&ctx->d_exp_tab, 64));
-    CKC(cudaMemcpy(ctx->d_exp_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    // exp table 2^(j/2048) (correctly rounded from long double)
+    std::vector<double> tab(EXP_TAB);
+    for (int j = 0; j < EXP_TAB; j++) tab[j] = (double)exp2l((long double)j / (long double)EXP_TAB);
+    CKC(dalloc(&ctx->d_exp_tab, EXP_TAB));
+    CKC(cudaMemcpy(ctx->d_exp_tab, tab.data(), sizeof(double) * EXP_TAB, cudaMemcpyHostToDevice));
 #undef CKC
     *out = ctx;
     return TDLO_OK;

@@ -51,7 +51,7 @@ struct KArgs {
     unsigned short* bkt; // nearest-node bucket per raw point (sort key), same indexing as X
     int scr_nodes;       // node capacity the scratch layout was sized for
     unsigned long long* prof;   // optional [16] phase cycle counters
-    const double* exp_tab;      // [64] 2^(j/64), filled by the host at context creation
+    const double* exp_tab;      // [EXP_TAB] 2^(j/EXP_TAB), filled by the host at context creation
 };
 
 // the shared-memory arrays prune_sort_slice works in
@@ -102,6 +102,27 @@ __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ t
     const double p = fma(q, r2, r);
     const double e = fma(tj, p, tj);
     return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
+}
+
+// The E-step's exp(-z): 2048-entry table 2^(j/2048) (16 KB of shared memory) + degree-3 polynomial -- two FP64
+// instructions fewer than exp_neg; |r| <= ln2/4096 = 1.7e-4, truncation r^4/24 <= 3.4e-17 relative, same error bound and
+// clamp as exp_neg.
+constexpr int EXP_TAB_BITS = 11, EXP_TAB = 1 << EXP_TAB_BITS;
+__device__ __forceinline__ double exp_neg_t(double z, const double* __restrict__ tab) {
+    const double L = 2954.639443740597;           // 2048 / ln 2
+    const double C_HI = 3.384507717577858e-4;     // ln 2 / 2048
+    const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52
+    z = __hiloint2double(min(__double2hiint(z), 0x40861000), __double2loint(z));   // NaN also lands here
+    const double t = fma(z, -L, MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    const double r = fma(nf, -C_HI, -z);
+    const double tj = tab[n & (EXP_TAB - 1)];
+    const double r2 = r * r;
+    const double q = fma(r, 1.6666666666666666e-1, 0.5);
+    const double p = fma(q, r2, r);
+    const double e = fma(tj, p, tj);
+    return __hiloint2double(__double2hiint(e) + ((n >> EXP_TAB_BITS) << 20), __double2loint(e));
 }
 
 // 32-byte L2 load (data written by other CTAs during this launch must not come from L1)

@@ -70,7 +70,7 @@ struct TqSmemL {
 __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     TqSmemL l{};
     int o = 0;
-    l.tab = o; o += 64 * 8;
+    l.tab = o; o += (N <= 64 ? EXP_TAB : 64) * 8;      // 2048-entry exp table up to 64 nodes, the 64-entry one above (shared memory)
     l.node4 = o; o += N * 32;
     l.nsoa = o; o += 4 * N * 8;          // node x[], y[], z[], s'[] (lane = node loads without bank conflicts)
     l.vw = o; o += N * 8;
@@ -274,6 +274,10 @@ __device__ __forceinline__ double sqrt_ub(double x) {
     return x * r * (1.0 + 1e-5);
 }
 
+// exp(-z) of the E-step: the 2048-entry table variant where the shared-memory budget allows it (node ranges up to 64)
+template <int NPASS>
+__device__ __forceinline__ double tq_exp(double z, const double* __restrict__ tab) { return NPASS <= 2 ? exp_neg_t(z, tab) : exp_neg(z, tab); }
+
 // Phase B of the E-step for one block of Wb <= WP node rows (WP = 8, 16, 32): lane = (row r, point group g), every lane
 // accumulates P1 / PX of its row over the WP points of its group; the 32 / WP groups are then combined by shuffles, so
 // that every lane ends up with the sums of row r over all 32 points.
@@ -317,7 +321,11 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                                double sigma2, double c_norm, double rscale, double zcut, double zrel, double k_vis, double* part_out,
                                unsigned long long* prof) {
     constexpr int RS = TQ_RS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    int lane = tid & 31, warp = tid >> 5;
+    // opaque to the compiler: otherwise every use inside the tile loop re-derives them from %tid (S2R + LOP3 + IMAD chains,
+    // ~60 instructions per tile in the ncu source view) instead of keeping two registers
+    asm volatile("" : "+r"(lane), "+r"(warp));
     constexpr int nw = NW, nt = NW * 32;
     double* __restrict__ pt = sm.ptile + warp * (TQ_ROWS * RS);
     double2* __restrict__ wlo = reinterpret_cast<double2*>(sm.wbuf + warp * 32);     // (w, w x) per point
@@ -485,7 +493,7 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                     const double t1 = ((j + 1 <= lo) ? alo : nahi) - s1;
                     const double t2 = ((j + 2 <= lo) ? alo : nahi) - s2;
                     const double t3 = ((j + 3 <= lo) ? alo : nahi) - s3;
-                    double p0 = exp_neg(t0 * t0, tab), p1 = exp_neg(t1 * t1, tab), p2 = exp_neg(t2 * t2, tab), p3 = exp_neg(t3 * t3, tab);
+                    double p0 = tq_exp<NPASS>(t0 * t0, tab), p1 = tq_exp<NPASS>(t1 * t1, tab), p2 = tq_exp<NPASS>(t2 * t2, tab), p3 = tq_exp<NPASS>(t3 * t3, tab);
                     if (VIS) { p0 *= v0; p1 *= v1; p2 *= v2; p3 *= v3; }
                     colsum += (p0 + p1) + (p2 + p3);
                     if (j + 3 <= j1) { pc[0] = p0; pc[RS] = p1; pc[2 * RS] = p2; pc[3 * RS] = p3; }
@@ -499,7 +507,7 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                 for (; j <= jend; j++) {
                     const double sj = nd[j].w;
                     const double t = ((j <= lo) ? alo : nahi) - sj;
-                    double p = exp_neg(t * t, tab);
+                    double p = tq_exp<NPASS>(t * t, tab);
                     if (VIS) p *= vw[j];
                     colsum += p;
                     if (j <= j1) *pc = p;
@@ -510,7 +518,7 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
                 const double pn = VIS ? vw[jq] : 1.0;
                 if (j0 == jlo) {
                     const double tq = ahi + nd[jq].w;    // what the loop computed for row jq (jq > lo)
-                    double pq = exp_neg(tq * tq, tab);
+                    double pq = tq_exp<NPASS>(tq * tq, tab);
                     if (VIS) pq *= vw[jq];
                     colsum += pn - pq;
                 }
@@ -1167,6 +1175,24 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
         for (int i = tid; i < Nn; i += nt) sm.tnew[i] = sqrt(sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0));
         __syncthreads();
     }
+    if (g_in_smem && !spd) {
+        // Nn <= 64, pivoted path (LLE): all H G entries of this thread are requested from L2 before the first is used
+        double hv[20];                                            // Nn^2 <= 4096 <= 20 * 224
+#pragma unroll
+        for (int u = 0; u < 20; u++) { const int idx = tid + u * nt; hv[u] = (p.include_lle && idx < Nn * Nn) ? __ldcg(gHG + idx) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 20; u++) {
+            const int idx = tid + u * nt;
+            if (idx < Nn * Nn) {
+                const int i = idx / Nn, j = idx - i * Nn;
+                const double g = sG[idx];
+                double v = sm.p1[i] * g + (i == j ? ls : 0.0);
+                if (p.include_lle) v += sg * hv[u];
+                if (have_priors) v += p.alpha * sm.jd[i] * g;
+                AB[(long long)i * ld + j] = v;
+            }
+        }
+    } else
     for (int idx = tid; idx < Nn * Nn; idx += nt) {
         const int i = idx / Nn, j = idx - i * Nn;
         const double g = g_in_smem ? sG[idx] : __ldcg(gG + idx);
@@ -1431,7 +1457,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
     sm.prow = reinterpret_cast<int*>(smem_raw + L.prow);
     sm.used = reinterpret_cast<int*>(smem_raw + L.used);
     sm.ab = reinterpret_cast<double*>(smem_raw + L.ab);
-    for (int i = tid; i < 64; i += nt) sm.tab[i] = a.k.exp_tab[i];          // 2^(i/64)
+    if (NPASS <= 2) { for (int i = tid; i < EXP_TAB; i += nt) sm.tab[i] = a.k.exp_tab[i]; }            // 2^(i/2048)
+    else { for (int i = tid; i < 64; i += nt) sm.tab[i] = a.k.exp_tab[i * (EXP_TAB / 64)]; }           // 2^(i/64)
     __syncthreads();
 
     int* qi = reinterpret_cast<int*>(a.qctl + 2);          // [0] next frame, [1] start tickets, [2] frames done, [3] abort flag
