@@ -172,6 +172,15 @@ typedef struct tdlo_vis_batch {
     int64_t* visible_offsets;     /* out [n_frames+1]                                           */
     int32_t* visible_ext;         /* out, capacity n_frames*n_nodes                             */
     int64_t* visible_ext_offsets; /* out [n_frames+1]                                           */
+    /* Optional self-occlusion test (trackdlo_node.cpp:280-343): with proj != NULL a node is only visible if, in addition,
+     * its pixel is not covered by the thick lines (cv::line, thickness dlo_pixel_width) of the edges nearer to the camera that
+     * the reference has drawn before it visits the node.  Evaluated without a raster, bit-exact with OpenCV 4.x's cv::line
+     * (oracle/raster.py, pinned against cv2).  A zero-initialised tail keeps the old behaviour (every node not self-occluded). */
+    const double* proj;           /* [n_frames][12] row-major 3x4 projection matrices (camera_info P), or NULL = off */
+    int32_t rows, cols;           /* image size of the camera (mask.rows, mask.cols)                                  */
+    int32_t pixel_width;          /* dlo_pixel_width (launch default 40); 2..512                                     */
+    int32_t reserved;
+    int32_t* not_self_occluded;   /* optional out [n_frames][n_nodes]: 1 = the reference's not_self_occluded_nodes      */
 } tdlo_vis_batch;
 /* Host pointers; synchronous. */
 int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* batch);

@@ -49,3 +49,11 @@ fr = synth.render_frame(0, rows=90, cols=160, width_px=3)
 pc = c5.point_cloud_batched(fr["bgr"][None], fr["depth"][None], fr["proj"][None])
 print("front-end points", int(pc["x_offsets"][1]), "status", pc["status"].tolist())
 c5.close()
+# visibility lists with the self-occlusion test (thick-line coverage of projected edges)
+import glob, os
+gs = np.load(sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "selfocc_coil.npz")))[0])
+c6 = api.Context(max_frames=1, max_nodes=len(gs["Y"]), max_points_total=len(gs["X"]))
+rv = c6.visibility_batched(gs["X"], o1(len(gs["X"])), gs["Y"][None], gs["node_coord"][None], proj=gs["proj"][None], rows=int(gs["rows"]), cols=int(gs["cols"]),
+                           pixel_width=int(gs["pixel_width"]))
+print("self-occluded nodes", int((rv["not_self_occluded"] == 0).sum()), "visible", len(rv["visible"]))
+c6.close()

@@ -61,7 +61,9 @@ class VisBatchC(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("n_nodes", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "node_coord")] + \
                [("visibility_threshold", C.c_double), ("d_vis", C.c_double)] + \
-               [(n, C.c_void_p) for n in ("dmin", "visible", "visible_offsets", "visible_ext", "visible_ext_offsets")]
+               [(n, C.c_void_p) for n in ("dmin", "visible", "visible_offsets", "visible_ext", "visible_ext_offsets")] + \
+               [("proj", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("pixel_width", C.c_int32), ("reserved", C.c_int32),
+                ("not_self_occluded", C.c_void_p)]
 
 
 class ErrBatchC(C.Structure):
@@ -275,15 +277,21 @@ class Context:
         return dict(Y=Y, sigma2=s2, guide=guide, priors=pri, n_priors=npri, iters=iters, status=status, state=state, packed=packed)
 
     # ------------------------------------------------------------------ visibility front-end (trackdlo_node.cpp:254-277, 346-360)
-    def visibility_batched(self, X, x_offsets, Y, node_coord, visibility_threshold=0.008, d_vis=0.06):
+    def visibility_batched(self, X, x_offsets, Y, node_coord, visibility_threshold=0.008, d_vis=0.06, proj=None, rows=0, cols=0,
+                           pixel_width=40):
+        """proj [F,3,4] (with rows, cols, pixel_width) switches the self-occlusion test of trackdlo_node.cpp:280-343 on."""
         X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
         Y = _np(Y, np.float64); F, N = Y.shape[0], Y.shape[1]
         nc = _np(node_coord, np.float64, (F, N))
         dmin = np.zeros((F, N)); vis = np.zeros(F * N, np.int32); ext = np.zeros(F * N, np.int32)
         vo = np.zeros(F + 1, np.int64); eo = np.zeros(F + 1, np.int64)
-        b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo))
+        pr = None if proj is None else _np(proj, np.float64, (F, 12))
+        free = np.ones((F, N), np.int32)
+        b = VisBatchC(F, N, _ptr(X), _ptr(xo), _ptr(Y), _ptr(nc), visibility_threshold, d_vis, _ptr(dmin), _ptr(vis), _ptr(vo), _ptr(ext), _ptr(eo),
+                      _ptr(pr), int(rows), int(cols), int(pixel_width), 0, _ptr(free) if pr is not None else None)
         self._check(self.lib.tdlo_visibility_batched(self.h, C.byref(b)), "tdlo_visibility_batched")
-        return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo)
+        return dict(dmin=dmin, visible=vis[:vo[F]].copy(), visible_offsets=vo, visible_ext=ext[:eo[F]].copy(), visible_ext_offsets=eo,
+                    not_self_occluded=free)
 
     # ------------------------------------------------------------------ perception front-end (trackdlo_node.cpp:159-242)
     def point_cloud_batched(self, bgr, depth, proj, hsv_lower=(90, 90, 30), hsv_upper=(130, 255, 255), multi_color=False,

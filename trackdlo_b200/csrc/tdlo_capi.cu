@@ -41,6 +41,7 @@ struct tdlo_ctx {
     unsigned long long* d_prof_buf = nullptr;
     // visibility front-end workspace
     unsigned long long* d_vbits = nullptr; int *d_vtmp = nullptr, *d_vcnt = nullptr; long long* d_vslice = nullptr;
+    int* d_vfree = nullptr; double* d_vproj = nullptr;      // self-occlusion test: flags [F][N], projection matrices [F][12]
     double* d_vdmin = nullptr; int *d_vvis = nullptr, *d_vext = nullptr;
     // perception front-end workspace (tdlo_frontend.cuh)
     long long fe_cells_opt = 0, fe_cells_cap = 0, fe_tiles_cap = 0;
@@ -95,7 +96,7 @@ extern "C" void tdlo_destroy(tdlo_ctx* ctx) {
                     ctx->d_nvis, ctx->d_iters, ctx->d_status, ctx->d_vis, ctx->d_ext, ctx->d_npri_out, ctx->d_state,
                     ctx->d_Xc, ctx->d_bkt, ctx->d_exp_tab, ctx->d_prof_buf,
                     ctx->d_fscratch, ctx->d_part, ctx->d_dminp, ctx->d_gath, ctx->d_nkept, ctx->d_q, ctx->d_tsph,
-                    ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext,
+                    ctx->d_vbits, ctx->d_vtmp, ctx->d_vcnt, ctx->d_vslice, ctx->d_vfree, ctx->d_vproj, ctx->d_vdmin, ctx->d_vvis, ctx->d_vext,
                     ctx->d_fe_bbox, ctx->d_fe_dims, ctx->d_fe_tilecnt, ctx->d_fe_status, ctx->d_fe_cellbase, ctx->d_fe_tilebase, ctx->d_fe_acc,
                     ctx->d_fe_tileoff, ctx->d_fe_bgr, ctx->d_fe_occl, ctx->d_fe_depth, ctx->d_fe_proj};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -560,6 +561,8 @@ static int vis_workspace(tdlo_ctx* ctx) {
     CK(dalloc(&ctx->d_vtmp, 2 * F * N));
     CK(dalloc(&ctx->d_vcnt, 2 * F));
     CK(dalloc(&ctx->d_vslice, F + 1));
+    CK(dalloc(&ctx->d_vfree, F * N));
+    CK(dalloc(&ctx->d_vproj, F * 12));
     return TDLO_OK;
 }
 
@@ -577,11 +580,14 @@ static int vis_launch(tdlo_ctx* ctx, const tdlo_vis_batch* b, cudaStream_t strea
     a.slice_start = ctx->d_vslice; a.max_points = ctx->max_points;
     a.vis = b->visible; a.vis_off = reinterpret_cast<long long*>(b->visible_offsets);
     a.ext = b->visible_ext; a.ext_off = reinterpret_cast<long long*>(b->visible_ext_offsets);
+    a.proj = b->proj; a.rows = b->rows; a.cols = b->cols; a.pixel_width = b->pixel_width;
+    a.free_flag = b->proj ? (b->not_self_occluded ? b->not_self_occluded : ctx->d_vfree) : nullptr;
     CK(cudaMemsetAsync(ctx->d_vbits, 0x7f, (size_t)F * N * sizeof(unsigned long long), stream));   // 0x7f7f... = 1.4e306
     const long long max_slices = ctx->max_points / VIS_SLICE + F;
     const int grid = (int)std::max<long long>(1, std::min<long long>(max_slices, (long long)ctx->sm_count * 8));
     tdlo_vis_slices_kernel<<<1, 256, 0, stream>>>(a);
     tdlo_vis_dmin_kernel<<<grid, 256, 0, stream>>>(a);
+    if (a.proj) tdlo_vis_selfocc_kernel<<<F, 256, 0, stream>>>(a);
     tdlo_vis_lists_kernel<<<(F + 63) / 64, 64, 0, stream>>>(a);
     tdlo_vis_compact_kernel<<<1, 256, 0, stream>>>(a);
     CK(cudaGetLastError());
@@ -595,6 +601,10 @@ static int vis_check(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
     if (b->n_nodes < 1 || b->n_nodes > ctx->max_nodes) return fail(ctx, TDLO_ERR_INVALID, "n_nodes %d outside [1,%d]", b->n_nodes, ctx->max_nodes);
     if (!b->X || !b->x_offsets || !b->Y || !b->node_coord || !b->visible || !b->visible_offsets || !b->visible_ext || !b->visible_ext_offsets)
         return fail(ctx, TDLO_ERR_INVALID, "X, x_offsets, Y, node_coord and the four output arrays are required");
+    if (b->proj) {
+        if (b->rows < 1 || b->cols < 1 || b->rows > (1 << 20) || b->cols > (1 << 20)) return fail(ctx, TDLO_ERR_INVALID, "self-occlusion test: bad image size %d x %d", b->rows, b->cols);
+        if (b->pixel_width < 2 || b->pixel_width > 2 * SO_MAX_RADIUS) return fail(ctx, TDLO_ERR_INVALID, "self-occlusion test: pixel_width %d outside [2, %d]", b->pixel_width, 2 * SO_MAX_RADIUS);
+    }
     return TDLO_OK;
 }
 
@@ -626,13 +636,18 @@ extern "C" int tdlo_visibility_batched(tdlo_ctx* ctx, const tdlo_vis_batch* b) {
     H2D(ctx->d_xoff, b->x_offsets, (F + 1) * sizeof(long long));
     H2D(ctx->d_Y, b->Y, F * N * 3 * sizeof(double));
     H2D(ctx->d_rest, b->node_coord, F * N * sizeof(double));
+    rc = vis_workspace(ctx);
+    if (rc) return rc;
+    if (b->proj) H2D(ctx->d_vproj, b->proj, F * 12 * sizeof(double));
     tdlo_vis_batch d = *b;
+    if (b->proj) { d.proj = ctx->d_vproj; d.not_self_occluded = ctx->d_vfree; }
     d.X = ctx->d_X; d.x_offsets = reinterpret_cast<const int64_t*>(ctx->d_xoff); d.Y = ctx->d_Y; d.node_coord = ctx->d_rest;
     d.dmin = ctx->d_vdmin; d.visible = ctx->d_vvis; d.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
     d.visible_ext = ctx->d_vext; d.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
     rc = vis_launch(ctx, &d, ctx->stream);
     if (rc) return rc;
     if (b->dmin) D2H(b->dmin, ctx->d_vdmin, F * N * sizeof(double));
+    if (b->proj && b->not_self_occluded) D2H(b->not_self_occluded, ctx->d_vfree, F * N * sizeof(int));
     D2H(b->visible_offsets, ctx->d_visoff, (F + 1) * sizeof(long long));
     D2H(b->visible_ext_offsets, ctx->d_extoff, (F + 1) * sizeof(long long));
     D2H(b->visible, ctx->d_vvis, F * N * sizeof(int));

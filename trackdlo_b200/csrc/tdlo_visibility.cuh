@@ -1,8 +1,8 @@
 // Visibility front-end feeding tracking_step, batched over independent frames:
 //   shortest node-to-point distances           trackdlo/src/trackdlo_node.cpp:254-277
 //   visible_nodes (sorted) / visible_nodes_extended (d_vis rule)   trackdlo_node.cpp:346-360
-// The self-occlusion raster (:280-343) is out of scope: every node counts as not self-occluded.
-// Four small kernels, no host round trip (the device-pointer entry point is fully stream-ordered):
+//   self-occlusion test (optional)               trackdlo_node.cpp:280-343  (tdlo_vis_selfocc_kernel below)
+// Small kernels, no host round trip (the device-pointer entry point is fully stream-ordered):
 // (0) one CTA: slice table = exclusive scan of ceil(Mp_f / VIS_SLICE) over the frames; (1) per-node min squared
 // distance, a fixed grid of CTAs striding over the (frame, slice) pairs, combined with atomicMin on the bit pattern
 // (non-negative doubles order like their bits); (2) per frame: sqrt, threshold, the two lists at a fixed stride +
@@ -26,6 +26,10 @@ struct VisArgs {
     long long* slice_start;           // [F+1] workspace: first global slice of every frame
     long long max_points;             // capacity: frames whose offsets exceed it contribute no slices
     int* vis; long long* vis_off; int* ext; long long* ext_off;
+    // self-occlusion test (proj == nullptr: off, every node counts as not self-occluded)
+    const double* proj;               // [F][12] row-major 3x4 projection matrices
+    int rows, cols, pixel_width;      // image size, dlo_pixel_width (cv::line thickness, >= 2)
+    int* free_flag;                   // [F][N] workspace / optional output: 1 = not self-occluded
 };
 
 constexpr int VIS_SLICE = 4096;       // points per CTA of kernel 1
@@ -106,7 +110,7 @@ __global__ void tdlo_vis_lists_kernel(const VisArgs a) {
         double d = sqrt(d2);
         if (!(d < 100000.0)) d = 100000.0;                        // the reference's initial shortest_dist
         if (a.dmin_out) a.dmin_out[(long long)f * N + m] = d;
-        if (d <= a.tau) vis[nv++] = m;
+        if (d <= a.tau && (!a.proj || a.free_flag[(long long)f * N + m])) vis[nv++] = m;
     }
     int ne = 0;
     if (nv > 0) {
@@ -145,6 +149,251 @@ __global__ void __launch_bounds__(256) tdlo_vis_compact_kernel(const VisArgs a) 
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Self-occlusion test (trackdlo_node.cpp:280-343): the edges (i, i+1) are visited nearest-to-camera first; a node whose
+// pixel is not yet covered by the thick lines (cv::line, thickness dlo_pixel_width) of the edges visited before is "not
+// self-occluded".  No raster here: a node is tested once, at its first visit, against every earlier edge with an exact
+// per-pixel restatement of what cv::line draws (OpenCV 4.x drawing.cpp: the segment clipped to the image grown by
+// `thickness`, ThickLine = FillConvexPoly of the four corners p +- dp + its Line2 outline + a filled Circle at both ends) --
+// oracle/raster.py is the readable version, pinned against cv2.line.  One CTA per frame.
+// ------------------------------------------------------------------------------------------
+constexpr int SO_SHIFT = 16;
+constexpr long long SO_ONE = 1LL << SO_SHIFT, SO_HALF = SO_ONE >> 1;
+constexpr int SO_MAX_RADIUS = 256;
+
+struct SoEdge { long long qx[4], qy[4]; int cx[2], cy[2]; int has_quad, drawn; int bx0, bx1, by0, by1; };
+
+__device__ __forceinline__ long long so_trunc(double v) { return (long long)v; }      // (int64)(double): toward zero
+
+// cv::clipLine(Size2l(w, h), pt1, pt2)
+__device__ inline bool so_clip_line(long long w, long long h, long long& x1, long long& y1, long long& x2, long long& y2) {
+    const long long right = w - 1, bottom = h - 1;
+    if (w <= 0 || h <= 0) return false;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += so_trunc(__ddiv_rn(__dmul_rn((double)(a - y1), (double)(x2 - x1)), (double)(y2 - y1)));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += so_trunc(__ddiv_rn(__dmul_rn((double)(a - y2), (double)(x2 - x1)), (double)(y2 - y1)));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += so_trunc(__ddiv_rn(__dmul_rn((double)(a - x1), (double)(y2 - y1)), (double)(x2 - x1)));
+                x1 = a; c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += so_trunc(__ddiv_rn(__dmul_rn((double)(a - x2), (double)(y2 - y1)), (double)(x2 - x1)));
+                x2 = a; c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// Line2 (16.16 DDA between two fixed-point points, clipped to the image in fixed point): does it set pixel (px, py)?
+__device__ inline bool so_line2_hits(int W, int H, long long x1, long long y1, long long x2, long long y2, int px, int py) {
+    if (!so_clip_line((long long)W << SO_SHIFT, (long long)H << SO_SHIFT, x1, y1, x2, y2)) return false;
+    long long dx = x2 - x1, dy = y2 - y1;
+    const long long j = dx < 0 ? -1 : 0, ax = (dx ^ j) - j;
+    const long long i = dy < 0 ? -1 : 0, ay = (dy ^ i) - i;
+    if (ax > ay) {
+        dy = (dy ^ j) - j;
+        if (j) { long long t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+        if (px == (int)((x2 + SO_HALF) >> SO_SHIFT) && py == (int)((y2 + SO_HALF) >> SO_SHIFT)) return true;     // the far end point is put first
+        const long long y_step = (dy * SO_ONE) / (ax | 1);
+        const long long ecount = (x2 - x1) >> SO_SHIFT;
+        x1 += SO_HALF; y1 += SO_HALF;
+        const long long k = (long long)px - (x1 >> SO_SHIFT);
+        return k >= 0 && k <= ecount && (int)((y1 + k * y_step) >> SO_SHIFT) == py;
+    }
+    dx = (dx ^ i) - i;
+    if (i) { long long t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    if (px == (int)((x2 + SO_HALF) >> SO_SHIFT) && py == (int)((y2 + SO_HALF) >> SO_SHIFT)) return true;
+    const long long x_step = (dx * SO_ONE) / (ay | 1);
+    const long long ecount = (y2 - y1) >> SO_SHIFT;
+    x1 += SO_HALF; y1 += SO_HALF;
+    const long long k = (long long)py - (y1 >> SO_SHIFT);
+    return k >= 0 && k <= ecount && (int)((x1 + k * x_step) >> SO_SHIFT) == px;
+}
+
+// FillConvexPoly's scan conversion of a quadrilateral: is (px, py) inside the span of row py?
+__device__ inline bool so_fill_hits(int W, int H, const long long* vx, const long long* vy, int px, int py) {
+    constexpr int npts = 4;
+    long long ymin = vy[0], ymax = vy[0], xmin = vx[0], xmax = vx[0];
+    int imin = 0;
+    for (int i = 0; i < npts; i++) {
+        if (vy[i] < ymin) { ymin = vy[i]; imin = i; }
+        ymax = vy[i] > ymax ? vy[i] : ymax; xmax = vx[i] > xmax ? vx[i] : xmax; xmin = vx[i] < xmin ? vx[i] : xmin;
+    }
+    xmin = (xmin + SO_HALF) >> SO_SHIFT; xmax = (xmax + SO_HALF) >> SO_SHIFT;
+    ymin = (ymin + SO_HALF) >> SO_SHIFT; ymax = (ymax + SO_HALF) >> SO_SHIFT;
+    if (xmax < 0 || ymax < 0 || xmin >= W || ymin >= H) return false;
+    if (ymax > H - 1) ymax = H - 1;
+    if (py < ymin || py > ymax) return false;
+    int e_idx[2] = {imin, imin}, e_di[2] = {1, npts - 1};
+    long long e_x[2] = {-SO_ONE, -SO_ONE}, e_dx[2] = {0, 0}, e_ye[2] = {ymin, ymin};
+    long long y = ymin;
+    int edges = npts;
+    for (;;) {
+        for (int i = 0; i < 2; i++) {
+            if (y >= e_ye[i]) {
+                int idx0 = e_idx[i];
+                const int di = e_di[i];
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                for (;;) {
+                    if (--edges < 0) break;
+                    const long long ty = (vy[idx] + SO_HALF) >> SO_SHIFT;
+                    if (ty > y) {
+                        const long long xs = vx[idx0], xe = vx[idx];
+                        e_ye[i] = ty; e_dx[i] = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y)); e_x[i] = xs; e_idx[i] = idx;
+                        break;
+                    }
+                    idx0 = idx; idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) return false;
+        if (y == py) {
+            const int l = e_x[0] <= e_x[1] ? 0 : 1, r = l ^ 1;
+            const long long xx1 = (e_x[l] + SO_HALF) >> SO_SHIFT, xx2 = (e_x[r] + SO_HALF) >> SO_SHIFT;
+            return px >= xx1 && px <= xx2;          // (xx2 >= 0 && xx1 < W holds for an in-image px inside the span)
+        }
+        e_x[0] += e_dx[0]; e_x[1] += e_dx[1];
+        if (++y > ymax) return false;
+    }
+}
+
+__global__ void __launch_bounds__(256) tdlo_vis_selfocc_kernel(const VisArgs a) {
+    __shared__ SoEdge ed[kMaxNodes];
+    __shared__ int pcol[kMaxNodes], prow[kMaxNodes], rank[kMaxNodes], first[kMaxNodes], freef[kMaxNodes];
+    __shared__ double dist[kMaxNodes];
+    __shared__ int hw[SO_MAX_RADIUS + 1];
+    const int f = blockIdx.x, tid = threadIdx.x, N = a.n_nodes, W = a.cols, H = a.rows, th = a.pixel_width;
+    const double* Y = a.Y + (long long)f * N * 3;
+    const double* P = a.proj + (long long)f * 12;
+    const int radius = (int)((((long long)th << (SO_SHIFT - 1)) + SO_HALF) >> SO_SHIFT);
+    // filled cv::Circle (midpoint algorithm): half-width of the span at row offset k
+    for (int k = tid; k <= radius; k += blockDim.x) hw[k] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+        while (dx >= dy) {
+            hw[dy] = max(hw[dy], dx); hw[dx] = max(hw[dx], dy);
+            dy++; err += plus; plus += 2;
+            const int mask = (err <= 0) - 1;
+            err -= minus & mask; dx += mask; minus -= mask & 2;
+        }
+    }
+    // node pixels (:298-313; the Eigen product restated as a sum in index order) and edge midpoints (:283-286)
+    for (int m = tid; m < N; m += blockDim.x) {
+        const double h[4] = {Y[3 * m], Y[3 * m + 1], Y[3 * m + 2], 1.0};
+        double ic[3];
+        for (int r = 0; r < 3; r++) {
+            double s = 0.0;
+            for (int k = 0; k < 4; k++) s = __dadd_rn(s, __dmul_rn(P[4 * r + k], h[k]));
+            ic[r] = s;
+        }
+        const double qx = __ddiv_rn(ic[0], ic[2]), qy = __ddiv_rn(ic[1], ic[2]);
+        // static_cast<int>: truncation toward zero; a non-finite or huge quotient (undefined in the reference) lands outside every image
+        pcol[m] = (fabs(qx) < 1e9) ? (int)qx : -(1 << 30);
+        prow[m] = (fabs(qy) < 1e9) ? (int)qy : -(1 << 30);
+        freef[m] = 1; first[m] = 1 << 30;
+        if (m + 1 < N) {
+            const double mx = __ddiv_rn(__dadd_rn(Y[3 * m], Y[3 * m + 3]), 2.0), my = __ddiv_rn(__dadd_rn(Y[3 * m + 1], Y[3 * m + 4]), 2.0),
+                         mz = __ddiv_rn(__dadd_rn(Y[3 * m + 2], Y[3 * m + 5]), 2.0);
+            dist[m] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(mx, mx), __dmul_rn(my, my)), __dmul_rn(mz, mz)));
+        }
+    }
+    __syncthreads();
+    // visiting order (std::sort by the midpoint norm; ties, unspecified there, by index) and the edges' geometry
+    for (int e = tid; e < N - 1; e += blockDim.x) {
+        int rk = 0;
+        const double de = dist[e];
+        for (int j = 0; j < N - 1; j++) rk += (dist[j] < de) || (dist[j] == de && j < e);
+        rank[e] = rk;
+        SoEdge& g = ed[e];
+        g.drawn = 0; g.has_quad = 0;
+        const long long m = th;
+        long long x1 = (long long)pcol[e] + m, y1 = (long long)prow[e] + m, x2 = (long long)pcol[e + 1] + m, y2 = (long long)prow[e + 1] + m;
+        if (so_clip_line((long long)W + 2 * m, (long long)H + 2 * m, x1, y1, x2, y2)) {       // cv::line: clipped to the image grown by `thickness`
+            g.drawn = 1;
+            const long long p0x = (x1 - m) << SO_SHIFT, p0y = (y1 - m) << SO_SHIFT, p1x = (x2 - m) << SO_SHIFT, p1y = (y2 - m) << SO_SHIFT;
+            const double inv = 1.0 / 65536.0;
+            const double dx = __dmul_rn((double)(p0x - p1x), inv), dy = __dmul_rn((double)(p1y - p0y), inv);
+            double r = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            const long long thf = (long long)th << (SO_SHIFT - 1);
+            long long bx0 = 1LL << 40, bx1 = -(1LL << 40), by0 = 1LL << 40, by1 = -(1LL << 40);
+            if (fabs(r) > 2.220446049250313e-16) {
+                r = __ddiv_rn(__dadd_rn((double)thf, __dmul_rn((double)((th & 1) * SO_ONE), 0.5)), sqrt(r));
+                const long long dpx = __double2ll_rn(__dmul_rn(dy, r)), dpy = __double2ll_rn(__dmul_rn(dx, r));
+                g.qx[0] = p0x + dpx; g.qy[0] = p0y + dpy; g.qx[1] = p0x - dpx; g.qy[1] = p0y - dpy;
+                g.qx[2] = p1x - dpx; g.qy[2] = p1y - dpy; g.qx[3] = p1x + dpx; g.qy[3] = p1y + dpy;
+                g.has_quad = 1;
+                for (int i = 0; i < 4; i++) {
+                    bx0 = min(bx0, g.qx[i]); bx1 = max(bx1, g.qx[i]); by0 = min(by0, g.qy[i]); by1 = max(by1, g.qy[i]);
+                }
+            }
+            g.cx[0] = (int)((p0x + SO_HALF) >> SO_SHIFT); g.cy[0] = (int)((p0y + SO_HALF) >> SO_SHIFT);
+            g.cx[1] = (int)((p1x + SO_HALF) >> SO_SHIFT); g.cy[1] = (int)((p1y + SO_HALF) >> SO_SHIFT);
+            // conservative pixel bounding box of everything the line draws (quad corners +- 2 px, circles)
+            long long qx0 = (bx0 >> SO_SHIFT) - 2, qx1 = (bx1 >> SO_SHIFT) + 3, qy0 = (by0 >> SO_SHIFT) - 2, qy1 = (by1 >> SO_SHIFT) + 3;
+            if (!g.has_quad) { qx0 = qy0 = 1LL << 30; qx1 = qy1 = -(1LL << 30); }
+            for (int i = 0; i < 2; i++) {
+                qx0 = min(qx0, (long long)g.cx[i] - radius); qx1 = max(qx1, (long long)g.cx[i] + radius);
+                qy0 = min(qy0, (long long)g.cy[i] - radius); qy1 = max(qy1, (long long)g.cy[i] + radius);
+            }
+            g.bx0 = (int)max(qx0, -(1LL << 30)); g.bx1 = (int)min(qx1, 1LL << 30); g.by0 = (int)max(qy0, -(1LL << 30)); g.by1 = (int)min(qy1, 1LL << 30);
+        }
+    }
+    __syncthreads();
+    // first visit of every node = the earlier of its two edges
+    for (int m = tid; m < N; m += blockDim.x) {
+        int fr = 1 << 30;
+        if (m > 0) fr = min(fr, rank[m - 1]);
+        if (m + 1 < N) fr = min(fr, rank[m]);
+        first[m] = fr;
+    }
+    __syncthreads();
+    // (node, earlier edge) pairs
+    const int pairs = N * (N - 1);
+    for (int idx = tid; idx < pairs; idx += blockDim.x) {
+        const int m = idx / (N - 1), e = idx - m * (N - 1);
+        if (rank[e] >= first[m]) continue;
+        const SoEdge& g = ed[e];
+        const int px = pcol[m], py = prow[m];
+        if (!g.drawn || px < 0 || px >= W || py < 0 || py >= H) continue;      // pixels outside the image read as 0
+        if (px < g.bx0 || px > g.bx1 || py < g.by0 || py > g.by1) continue;
+        bool hit = false;
+        for (int i = 0; i < 2 && !hit; i++) {
+            const int k = abs(py - g.cy[i]);
+            hit = k <= radius && hw[k] >= 0 && abs(px - g.cx[i]) <= hw[k];
+        }
+        if (!hit && g.has_quad) {
+            hit = so_fill_hits(W, H, g.qx, g.qy, px, py);
+            for (int i = 0; i < 4 && !hit; i++) {
+                const int i0 = (i + 3) & 3;
+                hit = so_line2_hits(W, H, g.qx[i0], g.qy[i0], g.qx[i], g.qy[i], px, py);
+            }
+        }
+        if (hit) atomicAnd(&freef[m], 0);
+    }
+    __syncthreads();
+    for (int m = tid; m < N; m += blockDim.x) a.free_flag[(long long)f * N + m] = freef[m];
 }
 
 // ------------------------------------------------------------------------------------------
