@@ -5,6 +5,8 @@ sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 import numpy as np, torch
 import bench
 from trackdlo_b200 import api
+if os.environ.get("TDLO_AB_LIB"):          # development A/B: time another build of the library in the same gpurun call
+    api.LIB_PATH = os.path.abspath(os.environ["TDLO_AB_LIB"])
 dev = torch.device("cuda:0")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)

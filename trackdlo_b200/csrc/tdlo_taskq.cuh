@@ -72,7 +72,7 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     int o = 0;
     l.tab = o; o += (N <= 64 ? EXP_TAB : 64) * 8;      // 2048-entry exp table up to 64 nodes, the 64-entry one above (shared memory)
     l.node4 = o; o += N * 32;
-    l.nsoa = o; o += 4 * N * 8;          // node x[], y[], z[], s'[] (lane = node loads without bank conflicts)
+    l.nsoa = o; o += N * 8 + 4 * N * 4;  // node s'[] (doubles), then x[], y[], z[] as floats (conservative sphere pruning; lane = node loads)
     l.vw = o; o += N * 8;
     l.bcast = o; o += 64;
     l.red = o; o += 64 * 8;
@@ -334,10 +334,10 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
     const double* __restrict__ tab = sm.tab;
     const double4* __restrict__ nd = sm.node4;
     const double* __restrict__ vw = sm.vw;
-    const double* __restrict__ nsx = sm.nsoa;
-    const double* __restrict__ nsy = sm.nsoa + Nn;
-    const double* __restrict__ nsz = sm.nsoa + 2 * Nn;
-    const double* __restrict__ nss = sm.nsoa + 3 * Nn;
+    const double* __restrict__ nss = sm.nsoa;
+    const float* __restrict__ nfx = reinterpret_cast<const float*>(sm.nsoa + 32 * NPASS);
+    const float* __restrict__ nfy = nfx + 32 * NPASS;
+    const float* __restrict__ nfz = nfy + 32 * NPASS;
     // P1 / PX accumulators of this warp: shared memory [Nn][4] for Nn <= 64 (frees 32 registers in the tile loop and the
     // hand-over to owner lanes), registers (lane l owns nodes l, l+32, ...) above
     constexpr bool SACC = NPASS <= 2;
@@ -377,26 +377,30 @@ static __device__ void tq_estep_chunk(const TqSm& sm, const double* __restrict__
             sn = ldcg4(sp);
         }
 
-        // ---- nearest node: exact bounding-sphere pruning of the scan range: a node farther from the tile's sphere
-        // {centre c, radius rho} (from the prune pass) than the nearest centre distance + 2 rho cannot be nearest to any
-        // of the 32 points
+        // ---- nearest node: bounding-sphere pruning of the scan range: a node farther from the tile's sphere {centre c,
+        // radius rho} (from the prune pass) than the nearest centre distance + 2 rho cannot be nearest to any of the 32
+        // points.  The range only has to be CONSERVATIVE (the scan below is exact fp64), so this runs in fp32 with the
+        // rounding of the inputs (<= 3e-7 |c|_1 absolute) and of the arithmetic (<= 1e-5 relative) added to the limit.
         int ja, jb;
         {
-            double dc[NPASS];
-            double dloc = 1e300;
+            const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
+            const float slack = 3e-7f * (fabsf(cxf) + fabsf(cyf) + fabsf(czf));
+            float dc[NPASS];
+            float dloc = 3.0e38f;
 #pragma unroll
             for (int ps = 0; ps < NPASS; ps++) {
                 const int m = lane + 32 * ps;
-                dc[ps] = 1e300;
-                if (m < Nn) dc[ps] = dist2(nsx[m], nsy[m], nsz[m], cx, cy, cz);
-                dloc = fmin(dloc, dc[ps]);
+                dc[ps] = 3.0e38f;
+                if (m < Nn) { const float ex = nfx[m] - cxf, ey = nfy[m] - cyf, ez = nfz[m] - czf; dc[ps] = ex * ex + ey * ey + ez * ez; }
+                dloc = fminf(dloc, dc[ps]);
             }
-            double lim = (sqrt_ub(warp_min_pos_ub(dloc + 1e-300)) + 2.0 * rho) * (1.0 + 1e-9);
-            lim = lim * lim;
+            const float dnear = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dloc)));     // non-negative floats order like their bits
+            float lim = (sqrtf(dnear) * (1.0f + 1e-5f) + 2.0f * ((float)rho * (1.0f + 1e-6f)) + 3.0f * slack) * (1.0f + 1e-5f);
+            lim = lim * lim * (1.0f + 1e-6f);
             ja = Nn; jb = -1;
 #pragma unroll
             for (int ps = 0; ps < NPASS; ps++) {
-                const unsigned mk = __ballot_sync(0xffffffffu, dc[ps] <= lim);
+                const unsigned mk = __ballot_sync(0xffffffffu, lane + 32 * ps < Nn && dc[ps] <= lim);
                 if (mk) { if (ja == Nn) ja = 32 * ps + __ffs(mk) - 1; jb = 32 * ps + 31 - __clz(mk); }
             }
         }
@@ -1528,7 +1532,9 @@ __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) 
             const double v = __ldcg(fr.scr + fr.sc.VW + j);
             if (j < Nn) {
                 sm.node4[j] = q; sm.vw[j] = v;
-                sm.nsoa[j] = q.x; sm.nsoa[Nn + j] = q.y; sm.nsoa[2 * Nn + j] = q.z; sm.nsoa[3 * Nn + j] = q.w;
+                sm.nsoa[j] = q.w;
+                float* nf = reinterpret_cast<float*>(sm.nsoa + 32 * NPASS);
+                nf[j] = (float)q.x; nf[32 * NPASS + j] = (float)q.y; nf[64 * NPASS + j] = (float)q.z;
             }
         }
         __syncthreads();
