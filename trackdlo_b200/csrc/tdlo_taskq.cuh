@@ -169,9 +169,10 @@ __device__ __forceinline__ unsigned long long tq_word(unsigned long long ticket,
 // Publishes n tasks (type, frame, chunk 0..n-1).  Called by all threads of the CTA after the data the tasks
 // read has been written; contains the fences and a barrier.
 static __device__ void tq_push(const TqArgs& a, TqSm& sm, int type, int frame, int n) {
-    __threadfence();
+    // release: the CTA barrier orders every thread's writes before thread 0's gpu-scope fence, which is cumulative (the
+    // pattern of a cooperative-groups grid barrier) -- one fence instead of one per thread
     __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = atomicAdd(a.qctl + 1, (unsigned long long)n);
+    if (threadIdx.x == 0) { __threadfence(); *reinterpret_cast<unsigned long long*>(sm.bcast + 4) = atomicAdd(a.qctl + 1, (unsigned long long)n); }
     __syncthreads();
     const unsigned long long base = *reinterpret_cast<unsigned long long*>(sm.bcast + 4);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -222,9 +223,9 @@ static __device__ unsigned long long tq_pop(const TqArgs& a, TqSm& sm) {
 // A chunk task (or the set-up) of frame f is complete.  Returns true (uniform) for the LAST arriver of the
 // wave, which then owns the frame until it publishes the next wave.
 static __device__ bool tq_arrive(TqSm& sm, int* ctl) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();                                      // release (cumulative over the CTA's writes, see tq_push)
         const int old = atomicSub(ctl + FC_PENDING, 1);
         sm.bcast[0] = (old == 1);
         if (old == 1) __threadfence();
