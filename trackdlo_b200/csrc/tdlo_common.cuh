@@ -803,6 +803,189 @@ static __device__ int mct_kalman_solve(int n, double c, double beta, double* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Banded information-form M-step solve WITH the LLE regulariser (pre-processing registration, trackdlo.cpp:396-417), O(Nn).
+//
+// Let z = (f_0, f'_0, f_1, f'_1, ...) be the joint values of the Matern-3/2 process (whose covariance at the nodes is G) and of
+// its derivative, K their precision -- block tridiagonal, because (f, f') is Markov along the arc length -- and P the selection
+// of the f components.  With S = diag(D) + eps H  (D = P1 + alpha J, H = E^T E the LLE matrix, eps = sigma2 gamma), c = lambda sigma2:
+//     (S G + c I) W = B,   V = G W        <=>        (c K + P^T S P) z = P^T B,    V = P z,    W = P K z.
+// The system on the right is symmetric positive definite of size 2 Nn with half-bandwidth 12 (H reaches six nodes): LDL^T
+// without pivoting, right-looking on the band with the three right-hand sides carried along, then a back substitution.
+// It never forms G, A = S G + cI (condition 1e7..1e10) or a dense factor; measured against a 50-digit dense solve it is
+// accurate to 1e-13..1e-16 on W and G W where LAPACK's dense solve of A reaches 1e-9..1e-11
+// (scripts/banded_solver_check.py is the NumPy twin of this function, profiles/r2_banded_solver_accuracy.txt).
+// Replaces the 50 x 53 pivoted elimination (39 k cycles + the O(Nn^2) assembly) and, above 64 nodes, the 8-state filter.
+//
+// Per registration (tq_start_call): kh16[2 Nn][16] = lambda K + gamma P^T H P in band storage (slot k of row i = column
+// i - 12 + k, the diagonal at k = 12; slots 13..15 zero), kf[Nn][6] = K[2t][2t-2 .. 2t+3].  Per M-step the band is
+// sigma2 * kh16 + D on the even diagonal, the right-hand sides sit in slots 13..15 of the even rows.
+//   A (shared, 16-byte aligned): [2 Nn][16] + 4 doubles workspace;  dv: D_t of node t = threadIdx.x;  bv[u]: B entry threadIdx.x + u blockDim.x
+//   out (shared): wsol[n][3] = W, tnew[n][3] = Y0 + G W.   Returns non-zero if a pivot was not positive and finite.
+// ------------------------------------------------------------------------------------------
+constexpr int BL_BW = 12, BL_LD = 16;
+
+// exact-to-rounding 1 - exp(-2x)(1 + 2x + 2x^2) (= Q00 / sigma_f^2 of the gap): the closed form cancels to O(x^3)
+__device__ inline double bl_q00_factor(double x) {
+    if (x >= 0.25) return 1.0 - exp(-2.0 * x) * (1.0 + 2.0 * x + 2.0 * x * x);
+    const double y = 2.0 * x;
+    double term = y * y * y / 6.0, sum = term;
+    for (int k = 4; k < 16; k++) { term *= y / k; sum += term; }
+    return exp(-y) * sum;
+}
+
+// transition over a gap h: c = Q^-1 Phi (row-major 2x2), ptc = Phi^T Q^-1 Phi (00, 01, 11), qi = Q^-1 (00, 01, 11)
+__device__ inline void bl_gap(double h, double a, double s2f, double* c, double* ptc, double* qi) {
+    const double x = a * h, e = exp(-x), e2 = e * e;
+    const double p00 = e * (1.0 + x), p01 = e * h, p10 = -e * a * x, p11 = e * (1.0 - x);
+    const double q00 = s2f * bl_q00_factor(x), q01 = s2f * 2.0 * a * x * x * e2, q11 = s2f * a * a * (1.0 - e2 * (1.0 - 2.0 * x + 2.0 * x * x));
+    const double det = q00 * q11 - q01 * q01;
+    qi[0] = q11 / det; qi[1] = -q01 / det; qi[2] = q00 / det;
+    c[0] = qi[0] * p00 + qi[1] * p10; c[1] = qi[0] * p01 + qi[1] * p11;
+    c[2] = qi[1] * p00 + qi[2] * p10; c[3] = qi[1] * p01 + qi[2] * p11;
+    ptc[0] = p00 * c[0] + p10 * c[2]; ptc[1] = p00 * c[1] + p10 * c[3]; ptc[2] = p01 * c[1] + p11 * c[3];
+}
+
+// Per registration: kh16 and kf (global scratch) from the arc lengths s (shared), H (global, dense [n][n], band |r - c| <= 6).
+static __device__ void mct_banded_lle_setup(int n, double beta, double lambda, double gamma, const double* __restrict__ s,
+                                            const double* __restrict__ H, double* __restrict__ kh16, double* __restrict__ kf) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
+    for (int t = tid; t < n; t += nt) {
+        double* r0 = kh16 + (long long)(2 * t) * BL_LD;
+        double* r1 = r0 + BL_LD;
+        for (int k = 0; k < 2 * BL_LD; k++) r0[k] = 0.0;
+        double cp[4] = {0, 0, 0, 0}, qp[3] = {1.0 / s2f, 0.0, 1.0 / (a * a * s2f)}, tp[3];      // t = 0: the prior P_inf^-1
+        double cn[4] = {0, 0, 0, 0}, qn[3], tn[3] = {0, 0, 0};
+        if (t > 0) bl_gap(fabs(s[t] - s[t - 1]), a, s2f, cp, tp, qp);
+        if (t + 1 < n) bl_gap(fabs(s[t + 1] - s[t]), a, s2f, cn, tn, qn);
+        const double k00 = qp[0] + tn[0], k01 = qp[1] + tn[1], k11 = qp[2] + tn[2];          // K_tt
+        r0[10] = lambda * -cp[0]; r0[11] = lambda * -cp[1]; r0[12] = lambda * k00;
+        r1[9] = lambda * -cp[2]; r1[10] = lambda * -cp[3]; r1[11] = lambda * k01; r1[12] = lambda * k11;
+        for (int u = t - 6 > 0 ? t - 6 : 0; u <= t; u++) r0[BL_BW - 2 * (t - u)] += gamma * H[(long long)t * n + u];
+        double* f = kf + (long long)t * 6;
+        f[0] = -cp[0]; f[1] = -cp[1]; f[2] = k00; f[3] = k01; f[4] = -cn[0]; f[5] = -cn[2];
+    }
+}
+
+static __device__ int mct_banded_lle_solve(int n, double sigma2, double dv, const double* bv, const double* __restrict__ kh16,
+                                           const double* __restrict__ kf, const double* __restrict__ y0, double* __restrict__ A,
+                                           double* __restrict__ wsol, double* __restrict__ tnew) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int m = 2 * n;
+    // ---- band: sigma2 * kh16 (all loads in flight before the first store)
+    {
+        constexpr int U = 20;                                  // 16 m / 2 double2 <= 4096 <= 20 * 224
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(kh16);
+        double2* dst = reinterpret_cast<double2*>(A);
+        const int cnt = m * (BL_LD / 2);
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int i = tid + u * nt; v[u] = i < cnt ? __ldcg(src + i) : make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int i = tid + u * nt; if (i < cnt) dst[i] = make_double2(sigma2 * v[u].x, sigma2 * v[u].y); }
+        for (int i = tid + U * nt; i < cnt; i += nt) { const double2 w = __ldcg(src + i); dst[i] = make_double2(sigma2 * w.x, sigma2 * w.y); }
+    }
+    __syncthreads();
+    if (tid < n) A[(2 * tid) * BL_LD + BL_BW] += dv;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int idx = tid + u * nt;
+        if (idx < 3 * n) { const int i = idx / 3, d = idx - 3 * i; A[(2 * i) * BL_LD + 13 + d] = bv[u]; }
+    }
+    __syncthreads();
+    int bad = 0;
+    // ---- right-looking LDL^T on the band, right-hand sides carried along: warps 0..3, ONE item per thread.  The work of a step
+    // is fixed relative to the pivot row k: 78 pairs (i >= j) of the 12 rows below it + 36 right-hand-side entries = 114 items
+    // (decoded once); per step a thread reads the pivot, its two column-k entries and its own entry, and writes its own entry.
+    // One named barrier per step: the multipliers l_i = u_i / d_k and 1 / d_k overwrite column k one step LATE, when nobody
+    // reads that column any more.  (A single warp is not an option: an in-order warp issues a dependent instruction every ~7
+    // cycles, the first version of this loop -- four items per lane -- took 3100 cycles per step.)
+    if (warp < 4) {
+        const int it = tid;
+        int di = 0, dj = 0, slot = BL_BW, srcj = BL_BW;
+        if (it < 78) {                                         // pair number `it` of the lower triangle: rows di = 1..12, dj = 1..di
+            int r = 1, base = 0;
+            while (base + r <= it) { base += r; r++; }
+            di = r; dj = it - base + 1;
+            slot = BL_BW - di + dj; srcj = dj * BL_LD + BL_BW - dj;
+        } else if (it < 114) {
+            const int w = it - 78;
+            di = w / 3 + 1; const int cc = w - 3 * (di - 1);
+            slot = 13 + cc; srcj = 13 + cc;                    // second factor: the pivot row's right-hand side
+        }
+        const bool item = di > 0;
+        const bool lmul = item && it < 78 && dj == 1;          // these 12 threads also own the multiplier of row k + di
+        // invalid threads / rows beyond the end read the pivot (harmless) and never write
+        const int ocur = item ? di * BL_LD + slot : BL_BW, oui = item ? di * BL_LD + BL_BW - di : BL_BW, ouj = item ? srcj : BL_BW;
+        double* Ak = A;
+        double lprev = 0.0, invprev = 0.0;
+        double* lprev_at = nullptr;
+        for (int k = 0; k < m; k++) {
+            const bool live = item && k + di < m;
+            const double dk = Ak[BL_BW];
+            const double ui = Ak[live ? oui : BL_BW], uj = Ak[live ? ouj : BL_BW], cur = Ak[live ? ocur : BL_BW];
+            const double inv = rcp_fast(dk);
+            bad |= !(dk > 0.0) || !(fabs(inv) <= 1.79e308);
+            const double l = ui * inv;
+            if (live) Ak[ocur] = fma(-l, uj, cur);
+            if (lprev_at) *lprev_at = lprev;                   // column k-1: the multipliers of the previous step
+            if (it == 127 && k > 0) Ak[BL_BW - BL_LD] = invprev;                  // ... and 1 / d_{k-1} on its diagonal slot
+            lprev_at = (lmul && live) ? Ak + oui : nullptr; lprev = l; invprev = inv;
+            Ak += BL_LD;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (lprev_at) *lprev_at = lprev;                       // (none: the last step has no rows below)
+        if (it == 127) Ak[BL_BW - BL_LD] = invprev;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- back substitution z = L^-T D^-1 y, column oriented: warp 0, lane r < 12 owns the pending sums of the rows j = r (mod 12),
+        // for the three right-hand sides; the owner of row k finishes z_k, publishes it, the others add l_{k,j} z_k to their row
+        if (warp == 0) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            double* zs = A + m * BL_LD;                        // 4 doubles behind the band
+            int own = (m - 1) % BL_BW;                         // owner lane of row k
+            for (int k = m - 1; k >= 0; k--) {
+                const double* __restrict__ Ar = A + k * BL_LD;
+                if (lane == own) {
+                    const double inv = Ar[BL_BW];
+                    const double z0 = fma(Ar[13], inv, -a0), z1 = fma(Ar[14], inv, -a1), z2 = fma(Ar[15], inv, -a2);
+                    A[k * BL_LD + 13] = z0; A[k * BL_LD + 14] = z1; A[k * BL_LD + 15] = z2;
+                    zs[0] = z0; zs[1] = z1; zs[2] = z2;
+                    a0 = 0.0; a1 = 0.0; a2 = 0.0;                 // this lane's next row is k - 12
+                }
+                __syncwarp();
+                if (lane < BL_BW && lane != own) {
+                    int d = own - lane; if (d < 0) d += BL_BW;     // this lane's pending row is j = k - d (d = 1..11; d = 12 belongs to the owner's next round)
+                    if (k - d >= 0) {
+                        const double l = Ar[BL_BW - d];
+                        a0 = fma(l, zs[0], a0); a1 = fma(l, zs[1], a1); a2 = fma(l, zs[2], a2);
+                    }
+                } else if (lane == own && k - BL_BW >= 0) {
+                    const double l = Ar[0];                        // d = 12: the owner's next row k - 12
+                    a0 = fma(l, zs[0], a0); a1 = fma(l, zs[1], a1); a2 = fma(l, zs[2], a2);
+                }
+                __syncwarp();
+                own = own == 0 ? BL_BW - 1 : own - 1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- V = P z, W = P K z
+    for (int i = tid; i < 3 * n; i += nt) {
+        const int t = i / 3, c = i - 3 * t;
+        const double* __restrict__ f = kf + (long long)t * 6;
+        double w = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const int j = 2 * t - 2 + q;
+            if (j >= 0 && j < m) w = fma(__ldcg(f + q), A[j * BL_LD + 13 + c], w);
+        }
+        wsol[i] = w;
+        tnew[i] = y0[i] + A[(2 * t) * BL_LD + 13 + c];
+    }
+    return __syncthreads_or(bad);
+}
+
+// ------------------------------------------------------------------------------------------
 // Structured M-step solve WITH the LLE regulariser (pre-processing registration, trackdlo.cpp:396-403), O(Nn):
 //     ((diag(D) + eps E^T E) G + c I) W = B,   E = I - L (LLE weights, rows reach 3 nodes either side), eps = sigma2 gamma,
 //     B = D^1/2 ya + sqrt(eps) E^T yb  with  ya = (PX - P1 Y0 [+ alpha (Yext - Y0)]) / d,  yb = -sqrt(eps) E Y0.

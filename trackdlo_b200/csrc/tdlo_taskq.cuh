@@ -109,7 +109,11 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     // the structured LLE solve (mct_kalman_lle_solve) needs 17 N + KL_STAGE doubles from yext on: more than the E-step
     // view at N = 256
     const int k_end = l.yext + (17 * N + KL_STAGE + 10) * 8;
+    // the banded LLE solve (mct_banded_lle_solve) takes [2N][16] doubles from gjbuf on (gjbuf / prow / used / yext / jd / hy0 /
+    // [A|B] are dead by then)
+    const int b_end = l.gjbuf + (2 * N * BL_LD + 8) * 8;
     l.total = e_end > k_end ? e_end : k_end;
+    l.total = l.total > b_end ? l.total : b_end;
     return l;
 }
 
@@ -291,12 +295,17 @@ __device__ __forceinline__ void tq_phase_b(const double* __restrict__ pt, const 
     const double2* __restrict__ wgh = whi + (lane - r);
     b0 = 0.0; b1 = 0.0; b2 = 0.0; b3 = 0.0;
     if (r < Wb) {
+        // two interleaved partial sums per accumulator (even / odd points): eight independent DFMA chains -- four do not cover
+        // the FP64 latency (this line carried 9 % of the kernel's stall samples)
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
-        for (int u = 0; u < WP; u++) {
-            const double p = prow[u];
-            const double2 wa = wgl[u], wc = wgh[u];
+        for (int u = 0; u < WP; u += 2) {
+            const double p = prow[u], q = prow[u + 1];
+            const double2 wa = wgl[u], wc = wgh[u], xa = wgl[u + 1], xc = wgh[u + 1];
             b0 = fma(p, wa.x, b0); b1 = fma(p, wa.y, b1); b2 = fma(p, wc.x, b2); b3 = fma(p, wc.y, b3);
+            c0 = fma(q, xa.x, c0); c1 = fma(q, xa.y, c1); c2 = fma(q, xc.x, c2); c3 = fma(q, xc.y, c3);
         }
+        b0 += c0; b1 += c1; b2 += c2; b3 += c3;
     }
 #pragma unroll
     for (int off = WP; off < 32; off <<= 1) {
@@ -834,14 +843,23 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     const double beta = p.beta;
     // 0 = structured without LLE, 2 = structured with LLE (needs the weights E themselves: not with a caller-supplied H),
     // 1 = dense (also for a negative alpha, which the state-space form -- a square root of P1 + alpha J -- cannot take)
+    // 3 = banded information-form solve with LLE (the default with LLE; needs distinct arc lengths: a zero gap has no
+    // precision matrix -- such a chain falls back to the dense path)
     int smode = 1;
     if (a.solver != 1 && !(n_priors > 0 && p.alpha < 0.0)) {
         if (!p.include_lle) smode = 0;
-        else if (!Hext && (a.solver == 2 || Nn > 64)) smode = 2;
+        else if (!Hext && (a.solver == 2 || a.solver == 3 || Nn > 64)) smode = a.solver == 2 ? 2 : 3;   // (<= 64 nodes: the register-resident elimination is faster)
     }
-    const bool dense = smode == 1;
+    if (smode == 3) {
+        int zero_gap = 0;
+        for (int t = tid; t + 1 < Nn; t += nt) zero_gap |= !(sm.s[t + 1] - sm.s[t] > 1e-12 * beta);
+        if (__syncthreads_or(zero_gap)) smode = 1;
+    }
+    const bool dense = smode == 1 || smode == 3;          // the dense kernel matrix is only built for smode 1 (below)
     if (tid == 0) fr.ctl[FC_DENSE] = smode;
-    if (dense) {
+    if (smode == 3) {
+        // nothing here: K comes from the arc lengths after H is known (below)
+    } else if (dense) {
         for (int idx = tid; idx < Nn * Nn; idx += nt) {
             const int i = idx / Nn, j = idx - i * Nn;
             const double dd = fabs(sm.s[i] - sm.s[j]);
@@ -914,6 +932,8 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
             }
         }
         __syncthreads();
+        if (smode == 3) mct_banded_lle_setup(Nn, beta, p.lambda, p.gamma, sm.s, gH, scr + sc.KLW, scr + sc.KTR);
+        else
         for (int idx = tid; idx < Nn * Nn; idx += nt) {            // HG = H G
             const int i = idx / Nn, j = idx - i * Nn;
             double s = 0.0;
@@ -1025,7 +1045,7 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
     const double* gHG = scr + sc.HG;
     const int ld = Nn + 3;
     const int smode = __ldcg(fr.ctl + FC_DENSE);
-    const bool dense = smode == 1;
+    const bool dense = smode == 1;                          // 0 / 2 / 3: structured solves (no dense matrix)
     // [A|B] in shared memory only for the register-resident solvers (Nn <= 64); the blocked Cholesky keeps it in global
     // scratch (its shared workspace reuses the whole tail of the region)
     const bool ab_in_smem = Nn <= 64 && (long long)Nn * ld <= (long long)a.L.ab_doubles;
@@ -1116,6 +1136,7 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
             if (idx < 3 * Nn) {
                 const int i = idx / 3;
                 bv[u] = sm.px[idx] - sm.p1[i] * sm.y0[idx] + (have_priors ? p.alpha * (sm.yext[idx] - sm.y0[idx]) : 0.0);
+                if (smode == 3) bv[u] -= sigma2 * p.gamma * sm.hy0[idx];          // - sigma2 gamma H Y0 (trackdlo.cpp:400)
             }
         }
         if (tid < Nn) dv = sm.p1[tid] + (have_priors ? p.alpha * sm.jd[tid] : 0.0);
@@ -1124,7 +1145,14 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
         __syncthreads();
         double* kdd = sm.yext;              // [Nn]
         double* kbt = kdd + Nn;             // [3][Nn]
-        if (smode == 2) {
+        if (smode == 3) {
+            TQ_TICK(6)
+            double* bw = sm.gjbuf;
+            bw += (reinterpret_cast<uintptr_t>(bw) >> 3) & 1;          // 16-byte aligned
+            sing = mct_banded_lle_solve(Nn, sigma2, dv, bv, scr + sc.KLW, scr + sc.KTR, sm.y0, bw, sm.wsol, sm.tnew);
+            if (sing) status |= ST_SINGULAR;
+            TQ_TICK(7)
+        } else if (smode == 2) {
             // with LLE: B's third term -sigma2 gamma H Y0 enters as the observations yb = -sqrt(eps) E Y0 of the filter
 #pragma unroll
             for (int u = 0; u < 3; u++) {
