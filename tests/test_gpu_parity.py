@@ -40,8 +40,7 @@ def ctx():
 ENGINE_CFGS = {
     "tq": dict(chunk_points=0, truncation=100.0, threads=256, solver=0),
     "dense_solver": dict(solver=1),                         # M-step: dense Gauss-Jordan / blocked Cholesky instead of the O(Nn) state-space solve
-    "structured_all": dict(solver=2),                       # ... and the state-space solve also for the LLE registrations below 65 nodes
-    "banded_all": dict(solver=3),                           # ... the banded information-form solve for every LLE registration
+    "structured_all": dict(solver=2),                       # ... and the banded information-form solve also for the LLE registrations below 65 nodes
     "tq_224thr": dict(chunk_points=1024, truncation=100.0, threads=224),
     "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, truncation_rel=745.2, threads=224),
     "tq_256thr": dict(chunk_points=2048, truncation=100.0, threads=256),
@@ -93,7 +92,7 @@ def test_cpd_against_golden(ctx, golden_dir, name, cfg):
 
 
 @pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
-@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr", "dense_solver", "structured_all", "banded_all"])
+@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr", "dense_solver", "structured_all"])
 def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]
@@ -117,7 +116,7 @@ def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     assert abs(r["sigma2"][0] - float(g["sigma2"])) / float(g["sigma2"]) < 1e-5
 
 
-@pytest.fixture(params=["tq", "tq_exact_small_chunks", "dense_solver", "structured_all", "banded_all"])
+@pytest.fixture(params=["tq", "tq_exact_small_chunks", "dense_solver", "structured_all"])
 def ectx(ctx, request):
     _configure(ctx, request.param)
     ctx.engine_name = request.param
@@ -420,7 +419,7 @@ def test_bad_arguments_are_rejected(ctx):
         ctx.cpd_lle_batched(f["X"], np.zeros(201, np.int64), big, np.zeros(200), api.CpdParams())
 
 
-@pytest.mark.parametrize("solver", [0, 1, 2, 3])
+@pytest.mark.parametrize("solver", [0, 1, 2])
 def test_larger_node_counts(solver):
     """Nn = 100 and 200 take the other kernel variants (more node passes per lane); solver 1 = blocked Cholesky."""
     c = api.Context(max_frames=2, max_nodes=200, max_points_total=20000)

@@ -898,7 +898,7 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             ctx->tq_threads = t; return TDLO_OK;
         }
         case TDLO_OPT_SOLVER:
-            if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0) return fail(ctx, TDLO_ERR_INVALID, "solver must be 0 (automatic), 1 (dense), 2 (state-space filters) or 3 (state-space filter / banded information form)");
+            if (value != 0.0 && value != 1.0 && value != 2.0) return fail(ctx, TDLO_ERR_INVALID, "solver must be 0 (automatic), 1 (dense) or 2 (structured)");
             ctx->tq_solver = (int)value; return TDLO_OK;
         case TDLO_OPT_VOXEL_CELLS:
             if (value != 0.0 && (value < 4096.0 || value > (double)(1LL << 31))) return fail(ctx, TDLO_ERR_INVALID, "voxel cells must be 0 (automatic) or in [4096, 2^31]");

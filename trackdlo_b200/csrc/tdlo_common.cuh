@@ -846,7 +846,7 @@ __device__ inline void bl_gap(double h, double a, double s2f, double* c, double*
 }
 
 // Per registration: kh16 and kf (global scratch) from the arc lengths s (shared), H (global, dense [n][n], band |r - c| <= 6).
-static __device__ void mct_banded_lle_setup(int n, double beta, double lambda, double gamma, const double* __restrict__ s,
+static __device__ __noinline__ void mct_banded_lle_setup(int n, double beta, double lambda, double gamma, const double* __restrict__ s,
                                             const double* __restrict__ H, double* __restrict__ kh16, double* __restrict__ kf) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
@@ -867,7 +867,7 @@ static __device__ void mct_banded_lle_setup(int n, double beta, double lambda, d
     }
 }
 
-static __device__ int mct_banded_lle_solve(int n, double sigma2, double dv, const double* bv, const double* __restrict__ kh16,
+static __device__ __noinline__ int mct_banded_lle_solve(int n, double sigma2, double dv, const double* bv, const double* __restrict__ kh16,
                                            const double* __restrict__ kf, const double* __restrict__ y0, double* __restrict__ A,
                                            double* __restrict__ wsol, double* __restrict__ tnew) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -915,55 +915,66 @@ static __device__ int mct_banded_lle_solve(int n, double sigma2, double dv, cons
         }
         const bool item = di > 0;
         const bool lmul = item && it < 78 && dj == 1;          // these 12 threads also own the multiplier of row k + di
-        // invalid threads / rows beyond the end read the pivot (harmless) and never write
-        const int ocur = item ? di * BL_LD + slot : BL_BW, oui = item ? di * BL_LD + BL_BW - di : BL_BW, ouj = item ? srcj : BL_BW;
-        double* Ak = A;
+        // invalid threads read the pivot (harmless) and never write; per-thread pointers step one row per pivot
+        const double* pi = A + (item ? di * BL_LD + BL_BW - di : BL_BW);
+        const double* pj = A + (item ? srcj : BL_BW);
+        double* pc = A + (item ? di * BL_LD + slot : BL_BW);
+        double* pd = A + BL_BW;                                 // the pivot's diagonal slot
         double lprev = 0.0, invprev = 0.0;
-        double* lprev_at = nullptr;
-        for (int k = 0; k < m; k++) {
-            const bool live = item && k + di < m;
-            const double dk = Ak[BL_BW];
-            const double ui = Ak[live ? oui : BL_BW], uj = Ak[live ? ouj : BL_BW], cur = Ak[live ? ocur : BL_BW];
+        int k = 0;
+        // main part: every row of the step's window exists (k + 12 < m)
+#pragma unroll 4
+        for (; k + BL_BW < m; k++) {
+            const double dk = *pd, ui = *pi, uj = *pj, cur = *pc;
+            const double t = ui * uj;                           // (independent of the reciprocal: off the dependent chain)
             const double inv = rcp_fast(dk);
-            bad |= !(dk > 0.0) || !(fabs(inv) <= 1.79e308);
-            const double l = ui * inv;
-            if (live) Ak[ocur] = fma(-l, uj, cur);
-            if (lprev_at) *lprev_at = lprev;                   // column k-1: the multipliers of the previous step
-            if (it == 127 && k > 0) Ak[BL_BW - BL_LD] = invprev;                  // ... and 1 / d_{k-1} on its diagonal slot
-            lprev_at = (lmul && live) ? Ak + oui : nullptr; lprev = l; invprev = inv;
-            Ak += BL_LD;
+            if (item) *pc = fma(-t, inv, cur);
+            if (k > 0) {                                        // column k-1: the multipliers and 1 / d of the previous step
+                if (lmul) const_cast<double*>(pi)[-BL_LD] = lprev;
+                if (it == 127) pd[-BL_LD] = invprev;
+            }
+            lprev = ui * inv; invprev = inv;
+            pd += BL_LD; pi += BL_LD; pj += BL_LD; pc += BL_LD;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (lprev_at) *lprev_at = lprev;                       // (none: the last step has no rows below)
-        if (it == 127) Ak[BL_BW - BL_LD] = invprev;
+        // tail: the last twelve pivots, rows beyond the end are skipped
+        bool plive = item;
+        for (; k < m; k++) {
+            const bool live = item && k + di < m;
+            const double dk = *pd;
+            const double ui = live ? *pi : 0.0, uj = live ? *pj : 0.0, cur = live ? *pc : 0.0;
+            const double inv = rcp_fast(dk);
+            if (live) *pc = fma(-(ui * uj), inv, cur);
+            if (k > 0) {
+                if (lmul && plive) const_cast<double*>(pi)[-BL_LD] = lprev;
+                if (it == 127) pd[-BL_LD] = invprev;
+            }
+            lprev = ui * inv; invprev = inv; plive = live;
+            pd += BL_LD; pi += BL_LD; pj += BL_LD; pc += BL_LD;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (it == 127) pd[-BL_LD] = invprev;                    // (the last pivot has no rows below: no multipliers)
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        // ---- back substitution z = L^-T D^-1 y, column oriented: warp 0, lane r < 12 owns the pending sums of the rows j = r (mod 12),
-        // for the three right-hand sides; the owner of row k finishes z_k, publishes it, the others add l_{k,j} z_k to their row
+        // every diagonal slot now holds 1 / d_k: the pivots must have been positive and finite
+        for (int r = tid; r < m; r += 128) { const double v = A[r * BL_LD + BL_BW]; bad |= !(v > 0.0) || !(v <= 1.79e308); }
+        // ---- back substitution z = L^-T D^-1 y, column oriented: warp 0, lane r < 12 owns the pending sums of the rows j = r (mod 12)
+        // for the three right-hand sides; the owner of row k finishes z_k and broadcasts it (shuffles), every lane adds
+        // l_{k,j} z_k to its pending row j = k - d
         if (warp == 0) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            double* zs = A + m * BL_LD;                        // 4 doubles behind the band
             int own = (m - 1) % BL_BW;                         // owner lane of row k
-            for (int k = m - 1; k >= 0; k--) {
-                const double* __restrict__ Ar = A + k * BL_LD;
+            for (int k2 = m - 1; k2 >= 0; k2--) {
+                double* __restrict__ Ar = A + k2 * BL_LD;
+                int d = own - lane; if (d <= 0) d += BL_BW;    // pending row of this lane: k - d (the owner: its next row, k - 12)
+                const double l = (lane < BL_BW && k2 - d >= 0) ? Ar[BL_BW - d] : 0.0;
+                const double2 iy = *reinterpret_cast<const double2*>(Ar + BL_BW), yy = *reinterpret_cast<const double2*>(Ar + 14);
+                const double z0 = fma(iy.y, iy.x, -a0), z1 = fma(yy.x, iy.x, -a1), z2 = fma(yy.y, iy.x, -a2);      // (meaningful on the owner)
+                const double s0 = __shfl_sync(0xffffffffu, z0, own), s1 = __shfl_sync(0xffffffffu, z1, own), s2 = __shfl_sync(0xffffffffu, z2, own);
                 if (lane == own) {
-                    const double inv = Ar[BL_BW];
-                    const double z0 = fma(Ar[13], inv, -a0), z1 = fma(Ar[14], inv, -a1), z2 = fma(Ar[15], inv, -a2);
-                    A[k * BL_LD + 13] = z0; A[k * BL_LD + 14] = z1; A[k * BL_LD + 15] = z2;
-                    zs[0] = z0; zs[1] = z1; zs[2] = z2;
+                    Ar[13] = s0; *reinterpret_cast<double2*>(Ar + 14) = make_double2(s1, s2);
                     a0 = 0.0; a1 = 0.0; a2 = 0.0;                 // this lane's next row is k - 12
                 }
-                __syncwarp();
-                if (lane < BL_BW && lane != own) {
-                    int d = own - lane; if (d < 0) d += BL_BW;     // this lane's pending row is j = k - d (d = 1..11; d = 12 belongs to the owner's next round)
-                    if (k - d >= 0) {
-                        const double l = Ar[BL_BW - d];
-                        a0 = fma(l, zs[0], a0); a1 = fma(l, zs[1], a1); a2 = fma(l, zs[2], a2);
-                    }
-                } else if (lane == own && k - BL_BW >= 0) {
-                    const double l = Ar[0];                        // d = 12: the owner's next row k - 12
-                    a0 = fma(l, zs[0], a0); a1 = fma(l, zs[1], a1); a2 = fma(l, zs[2], a2);
-                }
-                __syncwarp();
+                a0 = fma(l, s0, a0); a1 = fma(l, s1, a1); a2 = fma(l, s2, a2);
                 own = own == 0 ? BL_BW - 1 : own - 1;
             }
         }
@@ -981,252 +992,6 @@ static __device__ int mct_banded_lle_solve(int n, double sigma2, double dv, cons
         }
         wsol[i] = w;
         tnew[i] = y0[i] + A[(2 * t) * BL_LD + 13 + c];
-    }
-    return __syncthreads_or(bad);
-}
-
-// ------------------------------------------------------------------------------------------
-// Structured M-step solve WITH the LLE regulariser (pre-processing registration, trackdlo.cpp:396-403), O(Nn):
-//     ((diag(D) + eps E^T E) G + c I) W = B,   E = I - L (LLE weights, rows reach 3 nodes either side), eps = sigma2 gamma,
-//     B = D^1/2 ya + sqrt(eps) E^T yb  with  ya = (PX - P1 Y0 [+ alpha (Yext - Y0)]) / d,  yb = -sqrt(eps) E Y0.
-// With S = Z Z^T, Z = [D^1/2, sqrt(eps) E^T], this is GP regression of the same Matern-3/2 process f under 2 Nn scalar
-// observations with noise variance c:  d_t f(s_t) = ya_t  and  sqrt(eps) (E f)_r = yb_r.  The second kind looks at seven
-// consecutive nodes, so the Markov state carries them:  x_t = [f_t, f'_t, f_{t-1}, ..., f_{t-6}]  (8).  The filter runs
-// over the nodes: transition t-1 -> t, observation A(t), then every LLE row r whose last node has arrived
-// (min(r+3, Nn-1) == t).  Its adjoint pass gives the smoothing errors uA, uB = Cov(obs)^-1 [ya; yb], and
-//     W = d uA + sqrt(eps) E^T uB,     G W = smoothed mean of f.
-// Validated in NumPy against a 50-digit dense solve with LLE weights taken from the reference build
-// (scripts/kalman_solver_check.py, profiles/r2_kalman_solver_accuracy.txt): ~10x more accurate than LAPACK's dense solve.
-// It replaces, at Nn = 200, a 200 x 200 pivoted elimination per EM iteration (and the H G, H Y0 products per call).
-//
-// Forward filter: one warp, lane i < 8 owns row i of the 8 x 8 covariance, lanes 8..10 the mean vectors of the three
-// right-hand sides (an observation costs one 8-value shuffle gather and ~30 FP64 instructions per lane).  Its results go
-// to a global workspace (gws, 43 n doubles); the backward (adjoint) pass stages them back through shared memory in
-// blocks of KL_BLK nodes (all threads copy, three lanes compute, one right-hand side each).
-//   in (shared): sd[n] = D_t (overwritten with d_t), ya[3][n] (overwritten: the smoothing errors uA end up there), y0[n][3]
-//   in (global): tr[n][8] = {Phi00, Phi01, Phi10, Phi11, Q00, Q01, Q11, -} of the gap t -> t+1, Eg[n][n] = E, ey0[n][3] = E Y0
-//   out (shared): wsol[n][3], tnew[n][3];  ws (shared): ub[3][n], eb[n][7] (band of E), ey[n][3], stage[KL_STAGE] (16-byte aligned);
-//   gws (global): 43 n + 64 doubles
-// ------------------------------------------------------------------------------------------
-constexpr int KL_BLK = 32;
-constexpr int KL_STAGE = KL_BLK * 17 + (KL_BLK + 4) * 17 + KL_BLK * 6 + (KL_BLK + 4) * 3;      // >= 64 + 256 doubles (forward exchange buffers)
-static __device__ int mct_kalman_lle_solve(int n, double c, double eps, double beta, double* __restrict__ sd, double* __restrict__ ya,
-                                           const double* __restrict__ y0, const double* __restrict__ tr, const double* __restrict__ Eg,
-                                           const double* __restrict__ ey0, double* __restrict__ wsol, double* __restrict__ tnew,
-                                           double* __restrict__ ub, double* __restrict__ eb, double* __restrict__ ey,
-                                           double* __restrict__ stage, double* __restrict__ gws) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double* __restrict__ ua = ya;
-    for (int i = tid; i < n; i += nt) {
-        const double D = sd[i];
-        const double d = sqrt(D), rd = D > 0.0 ? 1.0 / d : 0.0;
-        sd[i] = d;
-        ya[i] *= rd; ya[n + i] *= rd; ya[2 * n + i] *= rd;
-    }
-    for (int i = tid; i < 7 * n; i += nt) {              // band of E: eb[r][b] = E[r][r-3+b]
-        const int r = i / 7, node = r - 3 + (i - 7 * r);
-        eb[i] = (node >= 0 && node < n) ? __ldcg(Eg + (long long)r * n + node) : 0.0;
-    }
-    for (int i = tid; i < 3 * n; i += nt) ey[i] = __ldcg(ey0 + i);
-    __syncthreads();
-    const double se = sqrt(eps);
-    double* gA = gws;                      // [n][17]: 1/F, k[8], P(0,:) before the observation
-    double* gB = gws + 17 * n;             // [n][17]: 1/F, k[8], h[8]      (indexed by LLE row)
-    double* gC = gws + 34 * n;             // per column: vA[3][n], m0[3][n], vB[3][n]
-    int bad = 0;
-    if (tid < 32) {
-        // ---- forward filter, ONE WARP: lane i < 8 owns row i of the 8 x 8 covariance, lane 8 + c the mean vector of
-        // right-hand side c.  Both kinds of lane run the same instructions on their 8 registers `row[]`:
-        //   observation h:  dot = row . h   (= (P h)_i on a covariance lane, = h . m on a mean lane)
-        //                   g[j] = (P h)_j of lanes 0..7,  F = h . g + c,  r = 1 / F
-        //                   row[j] += g[j] * beta,   beta = -dot r (covariance: P -= k g^T)  or  (y - dot) r (mean: m += k v)
-        //   transition:     row <- T row on every lane (columns of P, entries of m), then the covariance lanes exchange
-        //                   rows (P <- T P) and add Q.
-        // Lanes exchange through shared memory + __syncwarp, not shuffles: this code sits under thread-dependent control
-        // flow, where ptxas wraps every shuffle into a WARPSYNC.COLLECTIVE call (measured: 4240 cycles per node with ~80
-        // shuffles per node, 2400 this way; profiles/r2_kalman_lle_tuning.txt).  Roles act through selects, idle lanes
-        // store to a dummy slot.  What is left is ~350 mostly dependent instructions per node on a single in-order warp.
-        const int lane = tid;
-        const bool cov = lane < 8, mean = lane >= 8 && lane < 11;
-        const int col = mean ? lane - 8 : 0;
-        const double a = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
-        double* xg = stage;                 // [2][32] (P h) of the covariance lanes, double-buffered
-        double* xr = stage + 64;            // [32][8] rows of P T^T during a transition (lanes >= 8: scratch)
-        double* dummy = gws + 43 * n + lane;
-        double row[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) row[jj] = 0.0;
-        row[0] = lane == 0 ? s2f : 0.0;
-        row[1] = lane == 1 ? a * a * s2f : 0.0;
-        int xb = 0;
-        const int src = (lane >= 3 && lane < 8) ? lane - 1 : 0;
-        double4 phn = ldcg4(reinterpret_cast<const double4*>(tr)), qqn = ldcg4(reinterpret_cast<const double4*>(tr + 4));
-        for (int t = 0; t < n; t++) {
-            const double4 ph = phn, qq = qqn;             // transition t-1 -> t (loaded one node ahead)
-            {
-                const int tn = t + 1 < n ? t : (t > 0 ? t - 1 : 0);
-                phn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * tn)); qqn = ldcg4(reinterpret_cast<const double4*>(tr + 8 * tn + 4));
-            }
-            if (t > 0) {                                   // (uniform)
-                // columns / entries: x'_0 = Phi00 x_0 + Phi01 x_1, x'_1 = Phi10 x_0 + Phi11 x_1, x'_2 = x_0, x'_k = x_{k-1}
-                {
-                    const double t0 = row[0], t1 = row[1];
-#pragma unroll
-                    for (int jj = 7; jj >= 3; jj--) row[jj] = row[jj - 1];
-                    row[2] = t0;
-                    row[0] = fma(ph.x, t0, ph.y * t1); row[1] = fma(ph.z, t0, ph.w * t1);
-                }
-                // rows of the covariance: row'_0 = Phi00 R_0 + Phi01 R_1, row'_1 = Phi10 R_0 + Phi11 R_1, row'_2 = R_0, row'_k = R_{k-1}
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) *reinterpret_cast<double2*>(xr + 8 * lane + jj) = make_double2(row[jj], row[jj + 1]);
-                __syncwarp();
-                const double c0 = lane == 0 ? ph.x : (lane == 1 ? ph.z : 1.0);       // weight of R_0 (lane 2: row'_2 = R_0)
-                const double c1 = lane == 0 ? ph.y : (lane == 1 ? ph.w : 0.0);       // weight of R_1
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) {
-                    const double2 v0 = *reinterpret_cast<const double2*>(xr + jj), v1 = *reinterpret_cast<const double2*>(xr + 8 + jj);
-                    const double2 vs = *reinterpret_cast<const double2*>(xr + 8 * src + jj);
-                    const double nx = lane >= 3 ? vs.x : fma(c0, v0.x, c1 * v1.x), ny = lane >= 3 ? vs.y : fma(c0, v0.y, c1 * v1.y);
-                    row[jj] = cov ? nx : row[jj]; row[jj + 1] = cov ? ny : row[jj + 1];
-                }
-                row[0] += lane == 0 ? qq.x : (lane == 1 ? qq.y : 0.0);
-                row[1] += lane == 0 ? qq.y : (lane == 1 ? qq.z : 0.0);
-                __syncwarp();
-            }
-            // ---- observation A(t): d_t f_t = ya_t
-            {
-                const double d = sd[t];
-                const double p0i = row[0];                                    // P(i,0) = P(0,i) before the observation / m_0
-                const double dot = row[0] * d;                                // h = d e_0
-                xg[32 * xb + lane] = dot;
-                __syncwarp();
-                double g[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) { const double2 v = *reinterpret_cast<const double2*>(xg + 32 * xb + jj); g[jj] = v.x; g[jj + 1] = v.y; }
-                xb ^= 1;
-                const double F = fma(d, g[0], c);
-                const double r = rcp_fast(F);
-                bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
-                const double inn = ya[col * n + t] - dot;
-                const double bta = cov ? -dot * r : inn * r;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) row[jj] = fma(g[jj], bta, row[jj]);
-                // stores (one instruction each, every lane): gains + 1/F + innovations, then P(0,:) / m_0 before the observation
-                double* p1 = cov ? gA + 17 * t + 1 + lane : (mean ? gC + col * n + t : (lane == 11 ? gA + 17 * t : dummy));
-                double* p2 = cov ? gA + 17 * t + 9 + lane : (mean ? gC + (3 + col) * n + t : dummy);
-                *p1 = cov ? dot * r : (mean ? inn : r);
-                *p2 = p0i;
-            }
-            // ---- LLE rows complete at t: r = t-3 (t >= 3), and at the last node every remaining row
-            const int rlo = t + 1 < n ? t - 3 : (t - 3 > 0 ? t - 3 : 0), rhi = t + 1 < n ? t - 3 : n - 1;
-            for (int rw = rlo < 0 ? n : rlo; rw <= rhi; rw++) {
-                double h[8];
-                const double* er = eb + 7 * rw;
-#pragma unroll
-                for (int lag = 0; lag < 7; lag++) {
-                    const int b = t - lag - (rw - 3);                           // position of node t-lag in the row's band rw-3..rw+3
-                    const double e = er[b < 0 ? 0 : (b > 6 ? 6 : b)];
-                    h[lag == 0 ? 0 : lag + 1] = (b >= 0 && b < 7) ? se * e : 0.0;
-                }
-                h[1] = 0.0;
-                double dot = 0.0, dot2 = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) { dot = fma(row[jj], h[jj], dot); dot2 = fma(row[jj + 1], h[jj + 1], dot2); }
-                dot += dot2;
-                xg[32 * xb + lane] = dot;
-                __syncwarp();
-                double g[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) { const double2 v = *reinterpret_cast<const double2*>(xg + 32 * xb + jj); g[jj] = v.x; g[jj + 1] = v.y; }
-                xb ^= 1;
-                double F = c, F2 = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj += 2) { F = fma(h[jj], g[jj], F); F2 = fma(h[jj + 1], g[jj + 1], F2); }
-                F += F2;
-                const double r = rcp_fast(F);
-                bad |= !(F > 0.0) || !(fabs(r) <= 1.79e308);
-                const double inn = -se * ey[3 * rw + col] - dot;
-                const double bta = cov ? -dot * r : inn * r;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) row[jj] = fma(g[jj], bta, row[jj]);
-                double hl = h[0];
-#pragma unroll
-                for (int jj = 1; jj < 8; jj++) hl = lane == jj ? h[jj] : hl;
-                double* p1 = cov ? gB + 17 * rw + 1 + lane : (mean ? gC + (6 + col) * n + rw : (lane == 11 ? gB + 17 * rw : dummy));
-                double* p2 = cov ? gB + 17 * rw + 9 + lane : dummy;
-                *p1 = cov ? dot * r : (mean ? inn : r);
-                *p2 = hl;
-            }
-        }
-        bad = __any_sync(0xffffffffu, bad);
-    }
-    __threadfence_block();
-    __syncthreads();
-    // ---- backward pass, blocks of KL_BLK nodes from the end; rows of the block: r = t-3, and all rows >= n-4 with t = n-1
-    double* sA = stage;                                   // [KL_BLK][17]
-    double* sB = sA + KL_BLK * 17;                        // [KL_BLK+4][17]
-    double* sCa = sB + (KL_BLK + 4) * 17;                 // vA, m0: [KL_BLK][6]
-    double* sCb = sCa + KL_BLK * 6;                       // vB: [KL_BLK+4][3]
-    double rr[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) rr[i] = 0.0;
-    for (int t1 = n; t1 > 0; t1 -= KL_BLK) {
-        const int t0 = t1 - KL_BLK > 0 ? t1 - KL_BLK : 0;
-        const int r0 = t0 - 3 > 0 ? t0 - 3 : 0, r1 = t1 == n ? n : (t1 - 3 > 0 ? t1 - 3 : 0);     // rows [r0, r1)
-        __syncthreads();
-        for (int i = tid; i < (t1 - t0) * 17; i += nt) sA[i] = __ldcg(gA + 17 * t0 + i);
-        for (int i = tid; i < (r1 - r0) * 17; i += nt) sB[i] = __ldcg(gB + 17 * r0 + i);
-        for (int i = tid; i < (t1 - t0) * 6; i += nt) { const int tt = i / 6, q = i - 6 * tt; sCa[i] = __ldcg(gC + (long long)q * n + t0 + tt); }
-        for (int i = tid; i < (r1 - r0) * 3; i += nt) { const int rw = i / 3, q = i - 3 * rw; sCb[i] = __ldcg(gC + (long long)(6 + q) * n + r0 + rw); }
-        __syncthreads();
-        if (tid < 3) {
-            const int col = tid;
-            for (int t = t1 - 1; t >= t0; t--) {
-                // LLE rows of node t, in reverse order
-                const int rlo = t + 1 < n ? t - 3 : (t - 3 > 0 ? t - 3 : 0), rhi = t + 1 < n ? t - 3 : n - 1;
-                for (int r = rhi; r >= rlo && r >= 0; r--) {
-                    const double* o = sB + 17 * (r - r0);
-                    double kr = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) kr = fma(o[1 + i], rr[i], kr);
-                    const double u = fma(sCb[3 * (r - r0) + col], o[0], -kr);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) rr[i] = fma(o[9 + i], u, rr[i]);
-                    ub[col * n + r] = u;
-                }
-                {   // observation A(t)
-                    const double* o = sA + 17 * (t - t0);
-                    double kr = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) kr = fma(o[1 + i], rr[i], kr);
-                    const double u = fma(sCa[6 * (t - t0) + col], o[0], -kr);
-                    rr[0] = fma(sd[t], u, rr[0]);
-                    double V = sCa[6 * (t - t0) + 3 + col];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) V = fma(o[9 + i], rr[i], V);
-                    ua[col * n + t] = u;
-                    tnew[3 * t + col] = y0[3 * t + col] + V;
-                }
-                if (t > 0) {   // adjoint of the transition t-1 -> t
-                    const double4 ph = ldcg4(reinterpret_cast<const double4*>(tr + 8 * (t - 1)));
-                    const double n0 = fma(ph.x, rr[0], fma(ph.z, rr[1], rr[2])), n1 = fma(ph.y, rr[0], ph.w * rr[1]);
-                    rr[0] = n0; rr[1] = n1;
-#pragma unroll
-                    for (int i = 2; i < 7; i++) rr[i] = rr[i + 1];
-                    rr[7] = 0.0;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- W = d uA + sqrt(eps) E^T uB   (E^T uB: rows j-3 .. j+3 of column j)
-    for (int idx = tid; idx < 3 * n; idx += nt) {
-        const int j = idx / 3, col = idx - 3 * j;
-        double w = sd[j] * ua[col * n + j];
-        double acc = 0.0;
-        const int ra = j - 3 > 0 ? j - 3 : 0, rb = j + 3 < n - 1 ? j + 3 : n - 1;
-        for (int r = ra; r <= rb; r++) acc = fma(eb[7 * r + (j - r + 3)], ub[col * n + r], acc);
-        wsol[idx] = fma(se, acc, w);
     }
     return __syncthreads_or(bad);
 }

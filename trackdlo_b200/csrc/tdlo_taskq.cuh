@@ -106,14 +106,10 @@ __host__ __device__ constexpr TqSmemL tq_smem_layout(int N, int nw) {
     l.ab = o;
     l.ab_doubles = (e_end - o) / 8;
     l.chol_doubles = (e_end - l.yext) / 8;
-    // the structured LLE solve (mct_kalman_lle_solve) needs 17 N + KL_STAGE doubles from yext on: more than the E-step
-    // view at N = 256
-    const int k_end = l.yext + (17 * N + KL_STAGE + 10) * 8;
     // the banded LLE solve (mct_banded_lle_solve) takes [2N][16] doubles from gjbuf on (gjbuf / prow / used / yext / jd / hy0 /
     // [A|B] are dead by then)
     const int b_end = l.gjbuf + (2 * N * BL_LD + 8) * 8;
-    l.total = e_end > k_end ? e_end : k_end;
-    l.total = l.total > b_end ? l.total : b_end;
+    l.total = e_end > b_end ? e_end : b_end;
     return l;
 }
 
@@ -841,14 +837,14 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     double* gHG = scr + sc.HG;
     double* gH = scr + sc.H;
     const double beta = p.beta;
-    // 0 = structured without LLE, 2 = structured with LLE (needs the weights E themselves: not with a caller-supplied H),
+    // 0 = structured (state-space filter) without LLE,
     // 1 = dense (also for a negative alpha, which the state-space form -- a square root of P1 + alpha J -- cannot take)
     // 3 = banded information-form solve with LLE (the default with LLE; needs distinct arc lengths: a zero gap has no
     // precision matrix -- such a chain falls back to the dense path)
     int smode = 1;
     if (a.solver != 1 && !(n_priors > 0 && p.alpha < 0.0)) {
         if (!p.include_lle) smode = 0;
-        else if (!Hext && (a.solver == 2 || a.solver == 3 || Nn > 64)) smode = a.solver == 2 ? 2 : 3;   // (<= 64 nodes: the register-resident elimination is faster)
+        else if (!Hext && (a.solver >= 2 || Nn > 64)) smode = 3;   // (<= 64 nodes: the register-resident elimination is faster)
     }
     if (smode == 3) {
         int zero_gap = 0;
@@ -868,20 +864,11 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     } else {
         // Phi(h) = e^{-ah} [[1 + ah, h], [-a^2 h, 1 - ah]],  Q(h) = P_inf - Phi P_inf Phi^T,  P_inf = sigma_f^2 diag(1, a^2)
         double* gPhi = scr + sc.PHI;
-        double* gTr = scr + sc.KTR;
-        const double ak = sqrt(2.0) / beta, s2f = sqrt(2.0) / (4.0 * beta);
+        const double ak = sqrt(2.0) / beta;
         for (int t = tid; t + 1 < Nn; t += nt) {
             const double h = fabs(sm.s[t + 1] - sm.s[t]), x = ak * h, e = exp(-x);
             const double p00 = e * (1.0 + x), p01 = e * h, p10 = -e * ak * x, p11 = e * (1.0 - x);
-            if (smode == 0) { gPhi[4 * t] = p00; gPhi[4 * t + 1] = p01; gPhi[4 * t + 2] = p10; gPhi[4 * t + 3] = p11; }
-            else {
-                const double e2 = e * e;
-                gTr[8 * t] = p00; gTr[8 * t + 1] = p01; gTr[8 * t + 2] = p10; gTr[8 * t + 3] = p11;
-                gTr[8 * t + 4] = s2f * (1.0 - e2 * (1.0 + 2.0 * x + 2.0 * x * x));
-                gTr[8 * t + 5] = s2f * 2.0 * ak * x * x * e2;
-                gTr[8 * t + 6] = s2f * ak * ak * (1.0 - e2 * (1.0 - 2.0 * x + 2.0 * x * x));
-                gTr[8 * t + 7] = 0.0;
-            }
+            gPhi[4 * t] = p00; gPhi[4 * t + 1] = p01; gPhi[4 * t + 2] = p10; gPhi[4 * t + 3] = p11;
         }
     }
     double* gJD = scr + sc.JD;
@@ -897,22 +884,7 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
             gYE[idx * 3] = priors[kk * 4 + 1]; gYE[idx * 3 + 1] = priors[kk * 4 + 2]; gYE[idx * 3 + 2] = priors[kk * 4 + 3];
         }
     }
-    if (smode == 2) {
-        // structured LLE solve: the weights themselves (E = I - L, dense rows, zero outside i-3..i+3) and E Y0
-        double* E = scr + sc.AB;
-        for (int idx = tid; idx < Nn * Nn; idx += nt) E[idx] = 0.0;
-        __syncthreads();
-        for (int i = tid; i < Nn; i += nt) lle_row(sm.y0, Nn, i, E + (long long)i * Nn);
-        __syncthreads();
-        double* gEY = scr + sc.HY0;
-        for (int idx = tid; idx < 3 * Nn; idx += nt) {
-            const int i = idx / 3, d = idx - 3 * i;
-            const int ka = i - 3 > 0 ? i - 3 : 0, kb = i + 3 < Nn - 1 ? i + 3 : Nn - 1;
-            double sacc = 0.0;
-            for (int kk = ka; kk <= kb; kk++) sacc = fma(E[(long long)i * Nn + kk], sm.y0[3 * kk + d], sacc);
-            gEY[idx] = sacc;
-        }
-    } else if (p.include_lle) {
+    if (p.include_lle) {
         if (Hext) {
             for (int idx = tid; idx < Nn * Nn; idx += nt) { const int i = idx / Nn, j = idx - i * Nn; gH[idx] = Hext[(long long)i * hstride + j]; }
         } else {
@@ -1150,26 +1122,6 @@ static __device__ int tq_mstep(const TqArgs& a, TqSm& sm, const TqFrame& fr, lon
             double* bw = sm.gjbuf;
             bw += (reinterpret_cast<uintptr_t>(bw) >> 3) & 1;          // 16-byte aligned
             sing = mct_banded_lle_solve(Nn, sigma2, dv, bv, scr + sc.KLW, scr + sc.KTR, sm.y0, bw, sm.wsol, sm.tnew);
-            if (sing) status |= ST_SINGULAR;
-            TQ_TICK(7)
-        } else if (smode == 2) {
-            // with LLE: B's third term -sigma2 gamma H Y0 enters as the observations yb = -sqrt(eps) E Y0 of the filter
-#pragma unroll
-            for (int u = 0; u < 3; u++) {
-                const int idx = tid + u * nt;
-                if (idx < 3 * Nn) { const int i = idx / 3, d = idx - 3 * i; kbt[d * Nn + i] = bv[u]; }
-            }
-            if (tid < Nn) kdd[tid] = dv;
-            for (int i = tid + nt; i < Nn; i += nt) kdd[i] = sm.p1[i] + (have_priors ? p.alpha * sm.jd[i] : 0.0);
-            __syncthreads();
-            TQ_TICK(6)
-            double* kub = kbt + 3 * Nn;         // [3][Nn]
-            double* keb = kub + 3 * Nn;         // [Nn][7]
-            double* key = keb + 7 * Nn;         // [Nn][3]
-            double* kst = key + 3 * Nn;         // [KL_STAGE]
-            kst += (reinterpret_cast<uintptr_t>(kst) >> 3) & 1;      // 16-byte aligned (vector loads of the exchange buffers)
-            sing = mct_kalman_lle_solve(Nn, p.lambda * sigma2, sigma2 * p.gamma, p.beta, kdd, kbt, sm.y0, scr + sc.KTR, scr + sc.AB, scr + sc.HY0,
-                                        sm.wsol, sm.tnew, kub, keb, key, kst, scr + sc.KLW);
             if (sing) status |= ST_SINGULAR;
             TQ_TICK(7)
         } else {
