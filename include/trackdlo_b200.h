@@ -291,10 +291,9 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         (c K + P^T S P) z = P^T B on the joint values (f, f') of the process, K its block-tridiagonal
  *                         precision.  Both are MORE accurate than a dense solve of the ill-conditioned A (1e-13 vs 1e-9
  *                         against a 50-digit solve: profiles/r2_kalman_solver_accuracy.txt, r2_banded_solver_accuracy.txt).
- *                         0 (default) = automatic: structured without LLE, and with LLE above 64 nodes (below, the
- *                         register-resident pivoted elimination is faster); 1 = dense always (register-resident Gauss-Jordan
- *                         for Nn <= 64, blocked Cholesky with FP64 tensor-core MMAs / pivoted elimination above);
- *                         2 = structured always.  A caller-supplied H and a negative alpha always solve densely.
+ *                         0 (default) and 2 = structured; 1 = dense always (register-resident Gauss-Jordan for Nn <= 64,
+ *                         blocked Cholesky with FP64 tensor-core MMAs / pivoted elimination above).  A caller-supplied H and
+ *                         a negative alpha always solve densely.
  *  TDLO_OPT_VOXEL_CELLS   cells of the front-end's voxel-grid workspace, summed over a batch (default: 2^19 per frame of the
  *                         context, at least 2^22, at most 2^25; 32 B each).  Takes effect at the next front-end call.
  *  TDLO_OPT_WATCHDOG_MS   a CTA of the persistent kernel that waits longer than this for its next task (or for a frame's

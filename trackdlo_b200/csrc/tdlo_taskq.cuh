@@ -844,7 +844,7 @@ static __device__ int tq_start_call(const TqArgs& a, TqSm& sm, const TqFrame& fr
     int smode = 1;
     if (a.solver != 1 && !(n_priors > 0 && p.alpha < 0.0)) {
         if (!p.include_lle) smode = 0;
-        else if (!Hext && (a.solver >= 2 || Nn > 64)) smode = 3;   // (<= 64 nodes: the register-resident elimination is faster)
+        else if (!Hext) smode = 3;   // (also below 65 nodes: as fast as the register-resident elimination on an idle GPU, faster on a loaded one)
     }
     if (smode == 3) {
         int zero_gap = 0;
