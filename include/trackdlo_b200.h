@@ -251,6 +251,11 @@ typedef struct tdlo_seq_batch {
     double* Y_traj;               /* optional out [T][S][n_nodes][3] tracking result after every step              */
     int32_t* iters_traj;          /* optional out [T][S][2]                                                        */
     int32_t* status_traj;         /* optional out [T][S]                                                           */
+    /* optional self-occlusion test of the visibility lists (tdlo_vis_batch): a zero-initialised tail = off */
+    const double* proj;           /* [S][12] row-major 3x4 projection matrix of every sequence's camera, or NULL      */
+    int32_t rows, cols;           /* image size                                                                    */
+    int32_t pixel_width;          /* dlo_pixel_width, 2..512                                                       */
+    int32_t reserved;
 } tdlo_seq_batch;
 int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* batch, const tdlo_track_params* params);
 

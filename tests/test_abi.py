@@ -54,7 +54,8 @@ int main(void){
          sizeof(tdlo_seq_batch), offsetof(tdlo_seq_batch, status_traj));
   printf("%zu %zu ", sizeof(tdlo_err_batch), offsetof(tdlo_err_batch, error));
   printf("%zu %zu %zu %zu ", sizeof(tdlo_frontend_batch), offsetof(tdlo_frontend_batch, status), offsetof(tdlo_cpd_batch, priors_stride), offsetof(tdlo_track_batch, packed_results));
-  printf("%zu %zu %zu\n", offsetof(tdlo_vis_batch, proj), offsetof(tdlo_vis_batch, pixel_width), offsetof(tdlo_vis_batch, not_self_occluded));
+  printf("%zu %zu %zu ", offsetof(tdlo_vis_batch, proj), offsetof(tdlo_vis_batch, pixel_width), offsetof(tdlo_vis_batch, not_self_occluded));
+  printf("%zu %zu\n", offsetof(tdlo_seq_batch, proj), offsetof(tdlo_seq_batch, pixel_width));
   return 0; }
 '''
     import tempfile
@@ -73,6 +74,7 @@ int main(void){
     assert vals[14] == C.sizeof(api.FrontendBatchC) and vals[15] == api.FrontendBatchC.status.offset
     assert vals[16] == api.CpdBatchC.priors_stride.offset and vals[17] == api.TrackBatchC.packed_results.offset
     assert vals[18] == api.VisBatchC.proj.offset and vals[19] == api.VisBatchC.pixel_width.offset and vals[20] == api.VisBatchC.not_self_occluded.offset
+    assert vals[21] == api.SeqBatchC.proj.offset and vals[22] == api.SeqBatchC.pixel_width.offset
 
 
 def test_create_fails_loudly_without_gpu():

@@ -145,3 +145,35 @@ def test_gpu_self_occlusion_argument_checks():
         with pytest.raises(api.TdloError):
             ctx.visibility_batched(X, np.array([0, len(X)], np.int64), Y[None], g["node_coord"][None], proj=g["proj"][None], **kw)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sequence_mode_with_self_occlusion():
+    """Sequence mode with a camera: every step's visibility lists carry the self-occlusion test -- same trajectory as chaining
+    tdlo_visibility_batched(proj) and tdlo_tracking_step_batched by hand, and different from the run without the camera."""
+    from trackdlo_b200 import api
+    g = np.load([p for p in GOLD if p.endswith("selfocc_coil.npz")][0])
+    Y0, X, P = g["Y"], g["X"], g["proj"]; N = len(Y0)
+    rows, cols, width = int(g["rows"]), int(g["cols"]), int(g["pixel_width"])
+    T = 3
+    rng = np.random.default_rng(9)
+    clouds = [X + rng.normal(0, 0.0005, X.shape) + np.array([0.002 * t, 0.0, 0.0]) for t in range(T)]
+    xo = np.zeros(T + 1, np.int64); xo[1:] = np.cumsum([len(c) for c in clouds])
+    rest = g["node_coord"]
+    tp = api.TrackParams(max_iter=8)
+    ctx = api.Context(max_frames=1, max_nodes=N, max_points_total=len(X))
+    r = ctx.track_sequences(np.concatenate(clouds), xo, Y0[None], np.zeros(1), rest[None], tp, T, d_vis=0.06, proj=P[None], rows=rows, cols=cols, pixel_width=width)
+    r0 = ctx.track_sequences(np.concatenate(clouds), xo, Y0[None], np.zeros(1), rest[None], tp, T, d_vis=0.06)
+    one = lambda n: np.array([0, n], np.int64)
+    Y, s2 = Y0.copy(), np.zeros(1)
+    hidden = 0
+    for t in range(T):
+        v = ctx.visibility_batched(clouds[t], one(len(clouds[t])), Y[None], rest[None], tp.visibility_threshold, 0.06, proj=P[None], rows=rows, cols=cols, pixel_width=width)
+        hidden += int((v["not_self_occluded"] == 0).sum())
+        o = ctx.tracking_step_batched(clouds[t], one(len(clouds[t])), Y[None], s2, rest[None], v["visible"], v["visible_offsets"], v["visible_ext"], v["visible_ext_offsets"], tp)
+        Y, s2 = o["Y"][0], o["sigma2"]
+        assert list(r["iters"][t, 0]) == list(o["iters"][0])
+        assert np.array_equal(r["Y_traj"][t, 0], Y)                  # same kernels, same inputs: bit-identical
+    assert hidden > 0
+    assert not np.array_equal(r["Y"], r0["Y"])                       # the occluded nodes changed the registration
+    ctx.close()

@@ -81,7 +81,8 @@ class FrontendBatchC(C.Structure):
 class SeqBatchC(C.Structure):
     _fields_ = [("n_sequences", C.c_int32), ("n_nodes", C.c_int32), ("n_steps", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("X", "x_offsets", "Y", "sigma2", "geodesic_coord")] + [("d_vis", C.c_double)] + \
-               [(n, C.c_void_p) for n in ("Y_traj", "iters_traj", "status_traj")]
+               [(n, C.c_void_p) for n in ("Y_traj", "iters_traj", "status_traj")] + \
+               [("proj", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("pixel_width", C.c_int32), ("reserved", C.c_int32)]
 
 
 @dataclass
@@ -324,13 +325,17 @@ class Context:
         return err
 
     # ------------------------------------------------------------------ sequence mode (visibility + tracking_step per frame on the device)
-    def track_sequences(self, X, x_offsets, Y, sigma2, geodesic_coord, params: TrackParams, n_steps, d_vis=0.06):
+    def track_sequences(self, X, x_offsets, Y, sigma2, geodesic_coord, params: TrackParams, n_steps, d_vis=0.06, proj=None, rows=0, cols=0,
+                        pixel_width=40):
+        """proj [S,3,4] (with rows, cols, pixel_width) adds the self-occlusion test to every step's visibility lists."""
         X = _np(X, np.float64, (-1, 3)); xo = _np(x_offsets, np.int64)
         Y = _np(Y, np.float64).copy(); S, N = Y.shape[0], Y.shape[1]
         s2 = _np(sigma2, np.float64).copy().reshape(S)
         geo = _np(geodesic_coord, np.float64, (S, N))
         traj = np.zeros((n_steps, S, N, 3)); its = np.zeros((n_steps, S, 2), np.int32); st = np.zeros((n_steps, S), np.int32)
-        b = SeqBatchC(S, N, n_steps, _ptr(X), _ptr(xo), _ptr(Y), _ptr(s2), _ptr(geo), d_vis, _ptr(traj), _ptr(its), _ptr(st))
+        pr = None if proj is None else _np(proj, np.float64, (S, 12))
+        b = SeqBatchC(S, N, n_steps, _ptr(X), _ptr(xo), _ptr(Y), _ptr(s2), _ptr(geo), d_vis, _ptr(traj), _ptr(its), _ptr(st),
+                      _ptr(pr), int(rows), int(cols), int(pixel_width), 0)
         pc = params.to_c()
         self._check(self.lib.tdlo_track_sequences(self.h, C.byref(b), C.byref(pc)), "tdlo_track_sequences")
         return dict(Y=Y, sigma2=s2, Y_traj=traj, iters=its, status=st)

@@ -835,6 +835,13 @@ extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, cons
         CK(dalloc(&ctx->d_vdmin, FM * NM)); CK(dalloc(&ctx->d_vvis, FM * NM)); CK(dalloc(&ctx->d_vext, FM * NM));
     }
     const size_t SN = (size_t)S * N;
+    if (b->proj) {
+        if (b->rows < 1 || b->cols < 1 || b->rows > (1 << 20) || b->cols > (1 << 20)) return fail(ctx, TDLO_ERR_INVALID, "self-occlusion test: bad image size %d x %d", b->rows, b->cols);
+        if (b->pixel_width < 2 || b->pixel_width > 2 * SO_MAX_RADIUS) return fail(ctx, TDLO_ERR_INVALID, "self-occlusion test: pixel_width %d outside [2, %d]", b->pixel_width, 2 * SO_MAX_RADIUS);
+        rc = vis_workspace(ctx);
+        if (rc) return rc;
+        H2D(ctx->d_vproj, b->proj, (size_t)S * 12 * sizeof(double));
+    }
     H2D(ctx->d_Y, b->Y, SN * 3 * sizeof(double));
     H2D(ctx->d_sigma2, b->sigma2, (size_t)S * sizeof(double));
     H2D(ctx->d_rest, b->geodesic_coord, SN * sizeof(double));
@@ -853,6 +860,7 @@ extern "C" int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* b, cons
         v.visibility_threshold = p->visibility_threshold; v.d_vis = b->d_vis;
         v.visible = ctx->d_vvis; v.visible_offsets = reinterpret_cast<int64_t*>(ctx->d_visoff);
         v.visible_ext = ctx->d_vext; v.visible_ext_offsets = reinterpret_cast<int64_t*>(ctx->d_extoff);
+        if (b->proj) { v.proj = ctx->d_vproj; v.rows = b->rows; v.cols = b->cols; v.pixel_width = b->pixel_width; }
         rc = vis_launch(ctx, &v, ctx->stream);
         if (rc) return rc;
         tdlo_track_batch d;
