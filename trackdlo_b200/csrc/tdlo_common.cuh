@@ -894,88 +894,80 @@ static __device__ __noinline__ int mct_banded_lle_solve(int n, double sigma2, do
     }
     __syncthreads();
     int bad = 0;
-    // ---- right-looking LDL^T on the band, right-hand sides carried along: warps 0..3, ONE item per thread.  The work of a step
-    // is fixed relative to the pivot row k: 78 pairs (i >= j) of the 12 rows below it + 36 right-hand-side entries = 114 items
-    // (decoded once); per step a thread reads the pivot, its two column-k entries and its own entry, and writes its own entry.
-    // One named barrier per step: the multipliers l_i = u_i / d_k and 1 / d_k overwrite column k one step LATE, when nobody
-    // reads that column any more.  (A single warp is not an option: an in-order warp issues a dependent instruction every ~7
-    // cycles, the first version of this loop -- four items per lane -- took 3100 cycles per step.)
+    // ---- right-looking block LDL^T on the band (2 x 2 pivots = one node (f_t, f'_t) per step: half the dependent chain of a scalar
+    // elimination), right-hand sides carried along: warps 0..3, ONE item per thread.  The work of a step is fixed relative to the
+    // pivot rows p0 = 2t, p1 = 2t + 1: the 11 rows p0+2 .. p0+12 below them (row p0+13 is a derivative row, whose band ends at
+    // distance 3), 66 pairs (i >= j) + 33 right-hand-side entries = 99 items (decoded once).  Per step a thread reads the pivot
+    // block, its rows' entries in the two pivot columns (u, v) and its own entry:
+    //     entry -= [u_i v_i] P^-1 [u_j v_j]^T,   P^-1 = adj(P) / det(P)   (the adjugate products do not wait for the reciprocal)
+    // One named barrier per step: the multipliers [u_i v_i] P^-1 and P^-1 itself overwrite the pivot columns one step LATE, when
+    // nobody reads them any more.  (One warp is not an option: an in-order warp issues a dependent instruction every ~7 cycles;
+    // the first, four-entries-per-lane version of this loop took 3100 cycles per pivot.)
     if (warp < 4) {
         const int it = tid;
-        int di = 0, dj = 0, slot = BL_BW, srcj = BL_BW;
-        if (it < 78) {                                         // pair number `it` of the lower triangle: rows di = 1..12, dj = 1..di
+        int ri = 0, rj = 0, cc = -1;
+        if (it < 66) {                                         // pair number `it`: rows ri = 2..12, rj = 2..ri
             int r = 1, base = 0;
             while (base + r <= it) { base += r; r++; }
-            di = r; dj = it - base + 1;
-            slot = BL_BW - di + dj; srcj = dj * BL_LD + BL_BW - dj;
-        } else if (it < 114) {
-            const int w = it - 78;
-            di = w / 3 + 1; const int cc = w - 3 * (di - 1);
-            slot = 13 + cc; srcj = 13 + cc;                    // second factor: the pivot row's right-hand side
+            ri = r + 1; rj = it - base + 2;
+        } else if (it < 99) {
+            const int w = it - 66;
+            ri = w / 3 + 2; cc = w - 3 * (ri - 2);
         }
-        const bool item = di > 0;
-        const bool lmul = item && it < 78 && dj == 1;          // these 12 threads also own the multiplier of row k + di
-        // invalid threads read the pivot (harmless) and never write; per-thread pointers step one row per pivot
-        const double* pi = A + (item ? di * BL_LD + BL_BW - di : BL_BW);
-        const double* pj = A + (item ? srcj : BL_BW);
-        double* pc = A + (item ? di * BL_LD + slot : BL_BW);
-        double* pd = A + BL_BW;                                 // the pivot's diagonal slot
-        double lprev = 0.0, invprev = 0.0;
-        int k = 0;
-        // main part: every row of the step's window exists (k + 12 < m)
-#pragma unroll 4
-        for (; k + BL_BW < m; k++) {
-            const double dk = *pd, ui = *pi, uj = *pj, cur = *pc;
-            const double t = ui * uj;                           // (independent of the reciprocal: off the dependent chain)
-            const double inv = rcp_fast(dk);
-            if (item) *pc = fma(-t, inv, cur);
-            if (k > 0) {                                        // column k-1: the multipliers and 1 / d of the previous step
-                if (lmul) const_cast<double*>(pi)[-BL_LD] = lprev;
-                if (it == 127) pd[-BL_LD] = invprev;
+        const bool item = ri > 0;
+        const bool lmul = item && cc < 0 && rj == 2;           // these 11 threads also own the multipliers of row p0 + ri
+        // invalid threads read the pivot (harmless) and never write; per-thread pointers step one node (two rows) per pivot
+        const double* pi = A + (item ? ri * BL_LD + BL_BW - ri : BL_BW);                       // u_i, v_i = pi[0], pi[1]
+        const double* pj0 = A + (item ? (cc < 0 ? rj * BL_LD + BL_BW - rj : 13 + cc) : BL_BW);  // u_j (or the pivot rows' right-hand side)
+        const int jstep = (item && cc >= 0) ? BL_LD : 1;                                         // v_j = pj0[jstep]
+        double* pc = A + (item ? (cc < 0 ? ri * BL_LD + BL_BW - ri + rj : ri * BL_LD + 13 + cc) : BL_BW);
+        double* pd = A + BL_BW;                                 // a = pd[0], b = pd[BL_LD - 1], d = pd[BL_LD]
+        double l0p = 0.0, l1p = 0.0, i00p = 0.0, i01p = 0.0, i11p = 0.0;
+        bool plive = false;
+        for (int t = 0; t < n; t++) {
+            const bool live = item && 2 * t + ri < m;
+            const double pa = pd[0], pb = pd[BL_LD - 1], pdd = pd[BL_LD];
+            const double ui = live ? pi[0] : 0.0, vi = live ? pi[1] : 0.0, uj = live ? pj0[0] : 0.0, vj = live ? pj0[jstep] : 0.0, cur = live ? *pc : 0.0;
+            const double det = fma(pa, pdd, -(pb * pb));
+            const double q = fma(ui, fma(pdd, uj, -(pb * vj)), vi * fma(pa, vj, -(pb * uj)));
+            const double inv = rcp_fast(det);
+            if (live) *pc = fma(-q, inv, cur);
+            if (t > 0) {                                        // the previous node's columns: its multipliers and its P^-1
+                if (lmul && plive) { double* w = const_cast<double*>(pi) - 2 * BL_LD; w[0] = l0p; w[1] = l1p; }
+                if (it == 127) { pd[-2 * BL_LD] = i00p; pd[-BL_LD - 1] = i01p; pd[-BL_LD] = i11p; }
             }
-            lprev = ui * inv; invprev = inv;
-            pd += BL_LD; pi += BL_LD; pj += BL_LD; pc += BL_LD;
+            l0p = fma(ui, pdd, -(vi * pb)) * inv; l1p = fma(vi, pa, -(ui * pb)) * inv;
+            i00p = pdd * inv; i01p = -pb * inv; i11p = pa * inv; plive = live;
+            pd += 2 * BL_LD; pi += 2 * BL_LD; pj0 += 2 * BL_LD; pc += 2 * BL_LD;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // tail: the last twelve pivots, rows beyond the end are skipped
-        bool plive = item;
-        for (; k < m; k++) {
-            const bool live = item && k + di < m;
-            const double dk = *pd;
-            const double ui = live ? *pi : 0.0, uj = live ? *pj : 0.0, cur = live ? *pc : 0.0;
-            const double inv = rcp_fast(dk);
-            if (live) *pc = fma(-(ui * uj), inv, cur);
-            if (k > 0) {
-                if (lmul && plive) const_cast<double*>(pi)[-BL_LD] = lprev;
-                if (it == 127) pd[-BL_LD] = invprev;
-            }
-            lprev = ui * inv; invprev = inv; plive = live;
-            pd += BL_LD; pi += BL_LD; pj += BL_LD; pc += BL_LD;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        if (it == 127) pd[-BL_LD] = invprev;                    // (the last pivot has no rows below: no multipliers)
+        if (it == 127) { pd[-2 * BL_LD] = i00p; pd[-BL_LD - 1] = i01p; pd[-BL_LD] = i11p; }     // (the last node has no rows below)
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        // every diagonal slot now holds 1 / d_k: the pivots must have been positive and finite
+        // the diagonal slots now hold the diagonal of every P^-1: positive and finite for a positive definite system
         for (int r = tid; r < m; r += 128) { const double v = A[r * BL_LD + BL_BW]; bad |= !(v > 0.0) || !(v <= 1.79e308); }
-        // ---- back substitution z = L^-T D^-1 y, column oriented: warp 0, lane r < 12 owns the pending sums of the rows j = r (mod 12)
-        // for the three right-hand sides; the owner of row k finishes z_k and broadcasts it (shuffles), every lane adds
-        // l_{k,j} z_k to its pending row j = k - d
-        if (warp == 0) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            int own = (m - 1) % BL_BW;                         // owner lane of row k
-            for (int k2 = m - 1; k2 >= 0; k2--) {
-                double* __restrict__ Ar = A + k2 * BL_LD;
-                int d = own - lane; if (d <= 0) d += BL_BW;    // pending row of this lane: k - d (the owner: its next row, k - 12)
-                const double l = (lane < BL_BW && k2 - d >= 0) ? Ar[BL_BW - d] : 0.0;
-                const double2 iy = *reinterpret_cast<const double2*>(Ar + BL_BW), yy = *reinterpret_cast<const double2*>(Ar + 14);
-                const double z0 = fma(iy.y, iy.x, -a0), z1 = fma(yy.x, iy.x, -a1), z2 = fma(yy.y, iy.x, -a2);      // (meaningful on the owner)
-                const double s0 = __shfl_sync(0xffffffffu, z0, own), s1 = __shfl_sync(0xffffffffu, z1, own), s2 = __shfl_sync(0xffffffffu, z2, own);
-                if (lane == own) {
-                    Ar[13] = s0; *reinterpret_cast<double2*>(Ar + 14) = make_double2(s1, s2);
-                    a0 = 0.0; a1 = 0.0; a2 = 0.0;                 // this lane's next row is k - 12
-                }
-                a0 = fma(l, s0, a0); a1 = fma(l, s1, a1); a2 = fma(l, s2, a2);
-                own = own == 0 ? BL_BW - 1 : own - 1;
+        // ---- back substitution z = L^-T D^-1 y, column oriented, one right-hand side per warp (warps 0..2): lane r < 12 owns the
+        // pending sum of the columns j = r (mod 12).  Per node: z_t = P^-1 y_t - pending (the two owner lanes), broadcast by
+        // shuffles, then every lane adds the two new rows' multipliers times z to its pending column.
+        if (warp < 3) {
+            const int c = warp;
+            double acc = 0.0;
+            int o0 = (m - 2) % BL_BW;                          // owner lane of column p0 (p1: o0 + 1)
+            for (int t = n - 1; t >= 0; t--) {
+                double* __restrict__ A0 = A + (2 * t) * BL_LD;
+                const double i00 = A0[BL_BW], i01 = A0[BL_LD + BL_BW - 1], i11 = A0[BL_LD + BL_BW];
+                const bool owner = lane == o0 || lane == o0 + 1;       // (only they read y: they overwrite it with z below)
+                const double y0v = owner ? A0[13 + c] : 0.0, y1v = owner ? A0[BL_LD + 13 + c] : 0.0;
+                int dd = o0 - lane; if (dd <= 0) dd += BL_BW;   // pending column of this lane: p0 - dd (owners: their next column)
+                const bool act = lane < BL_BW && 2 * t - dd >= 0;
+                const double l0 = act ? A0[BL_BW - dd] : 0.0;                            // row p0, column p0 - dd
+                const double l1 = (act && dd < BL_BW) ? A0[BL_LD + BL_BW - 1 - dd] : 0.0;  // row p1, column p0 - dd (distance dd + 1)
+                const double zc = (lane == o0 ? fma(i00, y0v, i01 * y1v) : fma(i01, y0v, i11 * y1v)) - acc;     // (meaningful on the owners)
+                const double z0 = __shfl_sync(0xffffffffu, zc, o0), z1 = __shfl_sync(0xffffffffu, zc, o0 + 1);
+                __syncwarp();
+                if (lane == o0) { A0[13 + c] = z0; A0[BL_LD + 13 + c] = z1; }
+                if (owner) acc = 0.0;
+                acc = fma(l0, z0, fma(l1, z1, acc));
+                o0 = o0 == 0 ? BL_BW - 2 : o0 - 2;
             }
         }
     }
