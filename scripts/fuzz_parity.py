@@ -24,6 +24,8 @@ for case in range(n_cases):
     f = synth.make_frame(int(rng.integers(0, 10000)), n_nodes=Nn, n_points=Mp, occlusion=occ)
     ctx.set_option("chunk_points", int(rng.choice([0, 256, 512, 1024, 4096])))
     ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
+    ctx.set_option("truncation_rel", float(rng.choice([45.0, 745.2])))
+    ctx.set_option("solver", int(rng.choice([0, 0, 1, 2])))
     ctx.set_option("threads", int(rng.choice([224, 256])))
     one = lambda n: np.array([0, n], np.int64)
     if len(f["vis_ext"]) < 4:
