@@ -287,8 +287,7 @@ int tdlo_profile_phases(tdlo_ctx* ctx, int32_t enable, uint64_t cycles[16]);
  *                         nearest node) are skipped.  Default 45: what is dropped is below 3e-20 of the column sum it would
  *                         enter (half an ulp is 1.1e-16), so every sum is unchanged to the last bit or two; 745.2 = off.
  *  TDLO_OPT_INFLIGHT      frames in flight at once (0 = automatic).
- *  TDLO_OPT_THREADS       kernel variant for Nn <= 64: 256 (default; 2 CTAs/SM, 128 registers),
- *                         224 (3 CTAs/SM, 80 registers; measured equal or slower).  Nn > 64 always uses 256.
+ *  TDLO_OPT_THREADS       threads per CTA: 256 (2 CTAs/SM, 128 registers) is the only variant left; kept for ABI compatibility.
  *  TDLO_OPT_SOLVER        the M-step solve (trackdlo.cpp:394-417).  G is the Matern-3/2 covariance of the nodes' arc
  *                         lengths, so (S G + lambda sigma2 I) W = B and T = Y0 + G W can be computed in O(Nn) without forming
  *                         G or A: with S = diag(P1 + alpha J) by a state-space (Kalman filter + adjoint) recursion over the

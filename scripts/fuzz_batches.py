@@ -28,7 +28,7 @@ for case in range(n_cases):
             frames.append(f)
     engine = "tq"
     ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048])))
-    ctx.set_option("threads", int(rng.choice([224, 256])))
+    ctx.set_option("threads", int(rng.choice([256, 256])))
     s2 = np.where(rng.random(F) < 0.3, 10.0 ** rng.uniform(-6, -3, F), 0.0)
     mi = int(rng.integers(1, 20)); tol = float(rng.choice([0.0, 2e-4]))
     xo = np.zeros(F + 1, np.int64); xo[1:] = np.cumsum([len(f["X"]) for f in frames])

@@ -26,7 +26,7 @@ for case in range(n_cases):
     ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
     ctx.set_option("truncation_rel", float(rng.choice([45.0, 745.2])))
     ctx.set_option("solver", int(rng.choice([0, 0, 1, 2])))
-    ctx.set_option("threads", int(rng.choice([224, 256])))
+    ctx.set_option("threads", int(rng.choice([256, 256])))
     one = lambda n: np.array([0, n], np.int64)
     if len(f["vis_ext"]) < 4:
         continue          # fewer than 4 guide nodes: undefined behaviour in the reference (trackdlo.cpp:92-117, 313-321); the

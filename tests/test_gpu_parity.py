@@ -36,14 +36,14 @@ def ctx():
 
 
 # Engine configurations every golden is run under: the default Gaussian truncation (z_cut = 100) and exact-zero
-# skipping only (z_cut = 745.2), small chunks (many partial sums per frame), both kernel variants (224 / 256 threads).
+# skipping only (z_cut = 745.2), small chunks (many partial sums per frame), several chunk sizes.
 ENGINE_CFGS = {
     "tq": dict(chunk_points=0, truncation=100.0, threads=256, solver=0),
     "dense_solver": dict(solver=1),                         # M-step: dense Gauss-Jordan / blocked Cholesky instead of the O(Nn) state-space solve
     "structured_all": dict(solver=2),                       # ... and the banded information-form solve also for the LLE registrations below 65 nodes
-    "tq_224thr": dict(chunk_points=1024, truncation=100.0, threads=224),
-    "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, truncation_rel=745.2, threads=224),
-    "tq_256thr": dict(chunk_points=2048, truncation=100.0, threads=256),
+    "tq_1024": dict(chunk_points=1024, truncation=100.0, threads=256),
+    "tq_exact_small_chunks": dict(chunk_points=256, truncation=745.2, truncation_rel=745.2, threads=256),
+    "tq_2048": dict(chunk_points=2048, truncation=100.0, threads=256),
 }
 
 
@@ -92,7 +92,7 @@ def test_cpd_against_golden(ctx, golden_dir, name, cfg):
 
 
 @pytest.mark.parametrize("name", ["track_c1", "track_c1_b", "track_occl_head", "track_occl_mid", "track_all_visible"])
-@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_224thr", "dense_solver", "structured_all"])
+@pytest.mark.parametrize("cfg", ["tq", "tq_exact_small_chunks", "tq_1024", "dense_solver", "structured_all"])
 def test_tracking_step_against_golden(ctx, golden_dir, name, cfg):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     X = g["X"].astype(np.float64); Nn = g["Y_in"].shape[0]

@@ -237,7 +237,7 @@ def test_fuzz_slice_single_frames(ctx):
         ctx.set_option("chunk_points", int(rng.choice([0, 256, 512, 1024, 4096])))
         ctx.set_option("truncation", float(rng.choice([100.0, 745.2])))
         ctx.set_option("truncation_rel", float(rng.choice([45.0, 745.2])))
-        ctx.set_option("threads", int(rng.choice([224, 256])))
+        ctx.set_option("threads", int(rng.choice([256, 256])))
         mi = int(rng.integers(1, 25)); tol = float(rng.choice([0.0, 2e-4]))
         try:
             if len(f["vis_ext"]) < 4 or len(f["X"]) == 0:
@@ -273,7 +273,7 @@ def test_fuzz_slice_ragged_batches(ctx):
                                  occlusion=float(rng.choice([0.0, 0.15, 0.4])), occl_start=float(rng.choice([0.3, 0.0, 0.7])))
             if len(f["vis_ext"]) >= 4:
                 frames.append(f)
-        ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048]))); ctx.set_option("threads", int(rng.choice([224, 256])))
+        ctx.set_option("chunk_points", int(rng.choice([0, 256, 1024, 2048]))); ctx.set_option("threads", int(rng.choice([256, 256])))
         try:
             s2 = np.where(rng.random(F) < 0.3, 10.0 ** rng.uniform(-6, -3, F), 0.0)
             mi = int(rng.integers(1, 20)); tol = float(rng.choice([0.0, 2e-4]))

@@ -50,7 +50,7 @@ struct tdlo_ctx {
     unsigned char *d_fe_bgr = nullptr, *d_fe_occl = nullptr; unsigned short* d_fe_depth = nullptr; double* d_fe_proj = nullptr; long long fe_pix_cap = 0;
     // task-queue engine (tdlo_taskq.cuh)
     int tq_chunk = 0;               // raw points per chunk task (0 = automatic: 1024, or 2048 / 4096 for large batches)
-    int tq_threads = 256;           // threads per CTA: 256 (2 CTAs/SM, 128 registers) or 224 (3 CTAs/SM, 80 registers)
+    int tq_threads = 256;           // threads per CTA (2 CTAs/SM, 128 registers)
     int tq_inflight = 0;            // frames in flight (0 = automatic)
     double tq_zcut = 100.0;         // Gaussian truncation exponent (745.2 = exact zeros only)
     double tq_zrel = 45.0;          // relative truncation exponent (745.2 = off)
@@ -199,7 +199,7 @@ extern "C" int tdlo_last_launch_info(const tdlo_ctx* ctx, int32_t info[8]) {
 // kernel variants, one translation unit each (tdlo_tq_inst_*.cu): <node passes, threads, resident CTAs>
 namespace tdlo {
 #define TDLO_TQ_DECL(NAME) cudaError_t NAME##_prepare(int smem, int* occ); cudaError_t NAME##_launch(int grid, int smem, cudaStream_t s, const TqArgs& t);
-TDLO_TQ_DECL(tq_2_224_3) TDLO_TQ_DECL(tq_2_256_2) TDLO_TQ_DECL(tq_4_256_2) TDLO_TQ_DECL(tq_8_256_2)
+TDLO_TQ_DECL(tq_2_256_2) TDLO_TQ_DECL(tq_4_256_2) TDLO_TQ_DECL(tq_8_256_2)
 #undef TDLO_TQ_DECL
 }
 struct TqVariant { int npass, threads; cudaError_t (*prepare)(int, int*); cudaError_t (*launch)(int, int, cudaStream_t, const TqArgs&); };
@@ -252,9 +252,9 @@ static int launch_tq(tdlo_ctx* ctx, KArgs& a, cudaStream_t stream) {
         ctx->tq_alloc_chunk = chunk;
     }
     // kernel variants: <node passes, threads, resident CTAs>; the shared-memory layout is sized for 32*passes nodes
-    static const TqVariant kVariants[] = {{2, 224, tq_2_224_3_prepare, tq_2_224_3_launch}, {2, 256, tq_2_256_2_prepare, tq_2_256_2_launch},
+    static const TqVariant kVariants[] = {{2, 256, tq_2_256_2_prepare, tq_2_256_2_launch},
                                           {4, 256, tq_4_256_2_prepare, tq_4_256_2_launch}, {8, 256, tq_8_256_2_prepare, tq_8_256_2_launch}};
-    const TqVariant& kv = kVariants[nmax <= 64 ? (threads <= 224 ? 0 : 1) : (nmax <= 128 ? 2 : 3)];
+    const TqVariant& kv = kVariants[nmax <= 64 ? 0 : (nmax <= 128 ? 1 : 2)];
     const int npass = kv.npass, threads_eff = kv.threads;
     const TqSmemL L = tq_smem_layout(32 * npass, threads_eff / 32);
     if (L.total > 227 * 1024) return fail(ctx, TDLO_ERR_INVALID, "node count %d does not fit shared memory", nmax);
@@ -902,7 +902,7 @@ extern "C" int tdlo_set_option(tdlo_ctx* ctx, int32_t option, double value) {
             ctx->tq_inflight = (int)value; return TDLO_OK;
         case TDLO_OPT_THREADS: {
             const int t = (int)value;
-            if (t != 224 && t != 256) return fail(ctx, TDLO_ERR_INVALID, "threads must be 224 (3 CTAs/SM) or 256 (2 CTAs/SM)");
+            if (t != 256) return fail(ctx, TDLO_ERR_INVALID, "threads must be 256 (the 224-thread x 3-CTA variant of round 1 no longer fits three CTAs per SM and was removed)");
             ctx->tq_threads = t; return TDLO_OK;
         }
         case TDLO_OPT_SOLVER:

@@ -19,7 +19,7 @@
 
 namespace tdlo {
 
-constexpr int TQ_THREADS = 256;            // upper bound of threads per CTA (the host picks 224 or 256)
+constexpr int TQ_THREADS = 256;            // threads per CTA
 constexpr int TQ_ROWS = 32, TQ_RS = 33;    // P tile of a warp: 32 node rows x 32 points (+1 pad)
 
 enum { TK_PRUNE = 1, TK_DMIN = 2, TK_ESTEP = 3, TK_EXIT = 7 };
@@ -1411,7 +1411,7 @@ static __device__ int tq_finish_call(const TqArgs& a, TqSm& sm, const TqFrame& f
 // ------------------------------------------------------------------------------------------
 // The persistent kernel
 // ------------------------------------------------------------------------------------------
-// THREADS x MINB: 224 x 3 (80 registers, 21 warps/SM) or 256 x 2 (128 registers, 16 warps/SM).  The shared-memory
+// THREADS x MINB: 256 x 2 (128 registers, 16 warps/SM).  The shared-memory
 // layout is a compile-time constant (sized for 32*NPASS nodes) so that no address arithmetic survives in the loops.
 template <int NPASS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) tdlo_tq_kernel(const TqArgs a) {
