@@ -259,6 +259,17 @@ typedef struct tdlo_seq_batch {
 } tdlo_seq_batch;
 int tdlo_track_sequences(tdlo_ctx* ctx, const tdlo_seq_batch* batch, const tdlo_track_params* params);
 
+/* Multi-rank helper for hosts without Python (frames shard across GPUs with no data-path collective; the only exchange is the
+ * gather of the tracked nodes at the end).  All-gathers the packed result records of a sharded batch over an NCCL communicator
+ * the CALLER created: `nccl_comm` is its ncclComm_t (passed as void* so that this header needs no nccl.h).  `packed_all` is
+ * device memory [world * frames_per_rank][3 n_nodes + 4]; this rank's records must already sit at
+ * packed_all + rank * frames_per_rank * (3 n_nodes + 4) -- point tdlo_track_batch::packed_results there and the persistent
+ * kernel writes them in place.  Queued on `stream` behind the tracking call (one ncclAllGather, in place).  libnccl.so.2 is
+ * loaded on first use (dlopen): this library does not link against NCCL.  Returns TDLO_ERR_CUDA with tdlo_last_error set if
+ * NCCL is not available or reports an error. */
+int tdlo_all_gather_packed(tdlo_ctx* ctx, void* nccl_comm, double* packed_all, int32_t frames_per_rank, int32_t n_nodes,
+                           int32_t rank, void* stream);
+
 /* Waits for the most recent *_device call of this context and reports what only the device knows: TDLO_ERR_CUDA if the
  * persistent kernel's watchdog gave up (a CTA waited longer than TDLO_OPT_WATCHDOG_MS for a task; results invalid),
  * TDLO_OK otherwise.  The host-pointer entry points do this themselves. */

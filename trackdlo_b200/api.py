@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "tdlo_tracking_step_batched", "tdlo_tracking_step_batched_device",
     "tdlo_last_launch_info", "tdlo_synchronize", "tdlo_profile_phases", "tdlo_set_option",
     "tdlo_visibility_batched", "tdlo_visibility_batched_device", "tdlo_track_sequences", "tdlo_tracking_error_batched", "tdlo_tracking_error_batched_device",
-    "tdlo_point_cloud_batched", "tdlo_point_cloud_batched_device",
+    "tdlo_point_cloud_batched", "tdlo_point_cloud_batched_device", "tdlo_all_gather_packed",
 ]
 
 

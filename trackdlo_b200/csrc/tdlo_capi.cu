@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <dlfcn.h>
 
 using namespace tdlo;
 
@@ -386,6 +387,34 @@ static int sync_and_check(tdlo_ctx* ctx, cudaStream_t stream) {
         *h_abort = 0;
         return fail(ctx, TDLO_ERR_CUDA, "watchdog: the task queue made no progress for %.0f ms (lost task or missing upload); results of this call are invalid", ctx->watchdog_ms);
     }
+    return TDLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-rank gather of the packed records over the caller's NCCL communicator (NCCL is loaded lazily: no link dependency)
+// ---------------------------------------------------------------------------------------------
+extern "C" int tdlo_all_gather_packed(tdlo_ctx* ctx, void* nccl_comm, double* packed_all, int32_t frames_per_rank, int32_t n_nodes,
+                                      int32_t rank, void* stream) {
+    if (!ctx) return TDLO_ERR_INVALID;
+    if (!nccl_comm || !packed_all || frames_per_rank < 0 || n_nodes < 1 || rank < 0) return fail(ctx, TDLO_ERR_INVALID, "tdlo_all_gather_packed: bad arguments");
+    // ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream)
+    typedef int (*all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    typedef const char* (*errstr_fn)(int);
+    static all_gather_fn p_all_gather = nullptr;
+    static errstr_fn p_errstr = nullptr;
+    if (!p_all_gather) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(ctx, TDLO_ERR_CUDA, "tdlo_all_gather_packed: cannot load libnccl.so.2 (%s)", dlerror());
+        p_all_gather = reinterpret_cast<all_gather_fn>(dlsym(h, "ncclAllGather"));
+        p_errstr = reinterpret_cast<errstr_fn>(dlsym(h, "ncclGetErrorString"));
+        if (!p_all_gather) return fail(ctx, TDLO_ERR_CUDA, "tdlo_all_gather_packed: ncclAllGather not found in libnccl");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t cnt = (size_t)frames_per_rank * (3 * (size_t)n_nodes + 4);
+    constexpr int kNcclFloat64 = 8;                     // ncclFloat64 / ncclDouble (nccl.h)
+    const int rc = p_all_gather(packed_all + (size_t)rank * cnt, packed_all, cnt, kNcclFloat64, nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) return fail(ctx, TDLO_ERR_CUDA, "ncclAllGather: %s", p_errstr ? p_errstr(rc) : "error");
     return TDLO_OK;
 }
 
