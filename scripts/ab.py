@@ -38,6 +38,9 @@ for s in shapes:
     if s == "C4": run("C4", 512, 50, 20000, api.TrackParams(), distinct=64, steps=3)
     if s == "C2x1": run("C2x1", 1, 50, 20000, api.TrackParams(max_iter=50, tol=0.0))
     if s == "C2x16": run("C2x16", 16, 50, 20000, api.TrackParams(max_iter=50, tol=0.0))
+    if s == "P300": run("P300", 1, 45, 300, api.TrackParams())
+    if s == "P1000": run("P1000", 1, 45, 1000, api.TrackParams())
+    if s == "P3000": run("P3000", 1, 45, 3000, api.TrackParams())
     if s == "C1": run("C1", 1, 30, 2000, api.TrackParams(max_iter=20, tol=0.0))
     if s == "C3": run("C3", 1, 50, 50000, api.TrackParams(max_iter=50, tol=0.0), occlusion=0.4)
     if s == "C5": run("C5", 8, 200, 100000, api.TrackParams(max_iter=50, tol=0.0), distinct=2, steps=2)
